@@ -1,0 +1,202 @@
+/*
+ * rsdsfm.h -- C ABI of the B200-native dense optimisation core of RS-aware differential SfM.
+ *
+ * The reference (ThomasZiegler/RS-aware-differential-SfM) has no plugin / FFI boundary: the path
+ * is reached through plain C++ functions and classes.  Each entry point
+ * below names the reference interface it replaces (file:line relative to the reference's src/).
+ * The thin C++ classes in rs-aware-differential-sfm_b200/host/ carry the reference's names and
+ * signatures and forward here; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - POD only, caller-owned buffers, `int` status return (RSDSFM_OK == 0), no exceptions.
+ *   - One rsdsfm_ctx per GPU (and CUDA stream); contexts are independent and may be used from
+ *     different threads; a single context is not re-entrant.
+ *   - `mem` says where the ARRAY arguments of a call live: RSDSFM_HOST (the library stages them
+ *     through device scratch with cudaMemcpyAsync on the context's stream) or RSDSFM_DEVICE
+ *     (device pointers, nothing is copied; the call is asynchronous on the context's stream
+ *     unless a scalar result has to be returned to the host).  Small fixed-size vectors
+ *     (v[3], w[3], K4[4], k, summaries) are always host memory.
+ *   - Layouts follow the reference's Eigen / OpenCV types: Array2Xd = interleaved pairs,
+ *     Array3Xd = interleaved triples, MatrixXd(rows,cols) = column-major, cv::Mat 8UC3 =
+ *     row-major interleaved BGR, cv::Mat_<Point2d> flow = row-major interleaved (dx,dy) doubles.
+ *   - There is NO CPU fallback: every compute entry point fails with RSDSFM_ERR_CUDA when no
+ *     sm_100 device / driver is usable.
+ */
+#ifndef RSDSFM_H
+#define RSDSFM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSDSFM_VERSION 100
+
+#if defined(__GNUC__)
+#define RSDSFM_API __attribute__((visibility("default")))
+#else
+#define RSDSFM_API
+#endif
+
+enum {
+    RSDSFM_OK = 0,
+    RSDSFM_ERR_CUDA = 1,        /* CUDA runtime / driver error (see rsdsfm_last_error) */
+    RSDSFM_ERR_ARG = 2,         /* invalid argument */
+    RSDSFM_ERR_NOMEM = 3,       /* device allocation failed */
+    RSDSFM_ERR_INTERNAL = 4     /* in-kernel watchdog or consistency check tripped */
+};
+
+enum { RSDSFM_HOST = 0, RSDSFM_DEVICE = 1 };
+enum { RSDSFM_DEPTH_COLMAJOR = 0 /* Eigen MatrixXd, (y,x) at y + x*rows */, RSDSFM_DEPTH_ROWMAJOR = 1 };
+
+typedef struct rsdsfm_ctx rsdsfm_ctx;
+
+/* Solver options = the Ceres 1.14 Solver::Options fields the reference leaves at their defaults
+ * (nonlinearRefinement.cc:159-163, :224-228 set only linear_solver_type = DENSE_SCHUR). */
+typedef struct {
+    int max_num_iterations;             /* 50    */
+    double function_tolerance;          /* 1e-6  */
+    double gradient_tolerance;          /* 1e-10 */
+    double parameter_tolerance;         /* 1e-8  */
+    double initial_trust_region_radius; /* 1e4   */
+    double max_trust_region_radius;     /* 1e16  */
+    double min_trust_region_radius;     /* 1e-32 */
+    double min_relative_decrease;       /* 1e-3  */
+    double min_lm_diagonal;             /* 1e-6  */
+    double max_lm_diagonal;             /* 1e32  */
+    int max_num_consecutive_invalid_steps; /* 5  */
+} rsdsfm_lm_options;
+
+enum { RSDSFM_CONVERGENCE = 0, RSDSFM_NO_CONVERGENCE = 1, RSDSFM_FAILURE = 2 };
+enum {
+    RSDSFM_REASON_NONE = 0, RSDSFM_REASON_PARAMETER_TOL = 1, RSDSFM_REASON_FUNCTION_TOL = 2,
+    RSDSFM_REASON_GRADIENT_TOL = 3, RSDSFM_REASON_MAX_ITER = 4, RSDSFM_REASON_MIN_RADIUS = 5,
+    RSDSFM_REASON_INVALID_STEPS = 6, RSDSFM_REASON_EVAL_FAILED = 7, RSDSFM_REASON_NONFINITE_INPUT = 8
+};
+
+/* What ceres::Solver::Summary::BriefReport() / total_time_in_seconds gave the reference
+ * (nonlinearRefinement.cc:165-169, :230-234). */
+typedef struct {
+    int termination;          /* RSDSFM_CONVERGENCE / NO_CONVERGENCE / FAILURE */
+    int reason;
+    int iterations;           /* trust-region steps computed (incl. a final discarded one) */
+    int num_successful;
+    int num_unsuccessful;
+    double initial_cost;
+    double final_cost;
+    double final_radius;
+    double final_gradient_max_norm;
+    double device_ms;         /* GPU time of the solve (CUDA events on the context's stream) */
+} rsdsfm_lm_summary;
+
+/* ---- context ------------------------------------------------------------------------- */
+RSDSFM_API int rsdsfm_version(void);
+RSDSFM_API void rsdsfm_lm_default_options(rsdsfm_lm_options *opts);
+/* device: CUDA ordinal.  stream: a cudaStream_t to run on (e.g. the caller's framework stream),
+ * or NULL to let the context create its own non-blocking stream. */
+RSDSFM_API int rsdsfm_create(int device, void *cuda_stream, rsdsfm_ctx **out);
+RSDSFM_API void rsdsfm_destroy(rsdsfm_ctx *ctx);
+RSDSFM_API const char *rsdsfm_last_error(rsdsfm_ctx *ctx);   /* ctx may be NULL: error of a failed create */
+RSDSFM_API int rsdsfm_synchronize(rsdsfm_ctx *ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+RSDSFM_API long long rsdsfm_launch_count(rsdsfm_ctx *ctx);
+
+/* ---- a2: flatten + normalise glue (main.cc:398-432, errorMeasure.cpp:66-97) --------------- */
+/* flow_img: rows*cols*2.  Outputs (each 2*rows*cols doubles) are pre-filled like the reference
+ * (coord = 1, flow = 0) and the kept pixels (|flow|^2 > flow_threshold) are compacted in
+ * COLUMN-MAJOR pixel order.  pixel_index (nullable, rows*cols int32): pixel_index[i] =
+ * col*rows + row of kept point i.  *n_out = number of kept points (host). */
+RSDSFM_API int rsdsfm_flatten(rsdsfm_ctx *ctx, int mem, const double *flow_img, int rows, int cols, const double *K4,
+                   double gamma, double flow_threshold, double *coord, double *flow, double *coord_px,
+                   double *flow_px, int32_t *pixel_index, int *n_out);
+
+/* ---- a3/a4: minimal::getAlpha / getAlphaK (minimal.cc:179-197) ---------------------------- */
+RSDSFM_API int rsdsfm_alpha(rsdsfm_ctx *ctx, int mem, const double *flow_px, const double *q_px, int n, double h,
+                 double gamma, double *alpha, double *alpha_k);
+
+/* ---- a5: minimal::calculateVelocities (minimal.cc:36-177) -------------------------------- */
+/* Host computation (tiny dense LA, no context needed).  q9,u9: 2x9 interleaved; out7 = w,v,k. */
+RSDSFM_API int rsdsfm_solve9(const double *q9, const double *u9, const double *alpha9, const double *alpha_k9,
+                  int use_alpha_k, double *out7);
+
+/* ---- a6 + a8: minimal::ransac scoring with an injected hypothesis list -------------------- */
+/* (minimal.cc:209-306 with nonlinearRefinement.cc:109-180 inside.)  hyps: H x 7 (w,v,k), host
+ * memory.  For every hypothesis the inverse depth of every point is estimated by the
+ * Ceres-equivalent LM of estimateInverseDepths and inliers are counted (error < tolerance).
+ * Outputs: counts[H], sumerr[H] (host); *best_idx by the reference's rule (more inliers, or as
+ * many and a smaller error sum); mask_best[n] (uint8, 1 = inlier) and inv_depth_best[n] of the
+ * winner live in `mem`. */
+RSDSFM_API int rsdsfm_ransac_score(rsdsfm_ctx *ctx, int mem, const double *q, const double *u, const double *alpha,
+                        const double *alpha_k, int n, const double *hyps, int H, double tolerance,
+                        int *counts, double *sumerr, int *best_idx, uint8_t *mask_best,
+                        double *inv_depth_best);
+
+/* minimal::ransac with an injected SAMPLE list: samples = H x 9 point indices (host).  Runs the
+ * 9-point solver on each sample, then rsdsfm_ransac_score.  hyps_out (nullable, host): H x 7. */
+RSDSFM_API int rsdsfm_ransac(rsdsfm_ctx *ctx, int mem, const double *q, const double *u, const double *alpha,
+                  const double *alpha_k, int n, int use_alpha_k, const int32_t *samples, int H,
+                  double tolerance, int *counts, double *sumerr, int *best_idx, double *best7,
+                  uint8_t *mask_best, double *inv_depth_best, double *hyps_out);
+
+/* tail of minimal::ransac (minimal.cc:291-305): consensus set in ascending index order.
+ * inliers3: 3 x m (x, y, z = 1/inv_depth); *m_out on the host. */
+RSDSFM_API int rsdsfm_gather_inliers(rsdsfm_ctx *ctx, int mem, const double *q, const double *alpha,
+                          const double *alpha_k, int n, const uint8_t *mask, const double *inv_depth,
+                          double *inliers3, double *alpha_in, double *alpha_k_in, int32_t *index_in,
+                          int *m_out);
+
+/* ---- a8: nonlinear_refinement::estimateInverseDepths (nonlinearRefinement.cc:109-180) ----- */
+RSDSFM_API int rsdsfm_estimate_inverse_depths(rsdsfm_ctx *ctx, int mem, const double *coord, const double *flow, int n,
+                                   const double *v, const double *w, double k, const double *alpha,
+                                   const double *alpha_k, double *inv_depth, rsdsfm_lm_summary *summary);
+
+/* ---- a9: nonlinear_refinement::nonLinearRefinement (nonlinearRefinement.cc:183-252) ------- */
+/* flow: the array the caller passes (2 x >= m; residual i reads flow(:,i) of it exactly like the
+ * reference, Q1) unless flow_index (nullable, m int32) gives the repaired pairing.
+ * inliers3: 3 x m (x, y, z).  v, w, k: host, in/out.  z_out[m]: refined depths (1/d).
+ * opts may be NULL (Ceres defaults). */
+RSDSFM_API int rsdsfm_refine(rsdsfm_ctx *ctx, int mem, const double *flow, const double *inliers3, const double *alpha,
+                  const double *alpha_k, int m, double *v, double *w, double *k, int const_acceleration,
+                  const int32_t *flow_index, const rsdsfm_lm_options *opts, double *z_out,
+                  rsdsfm_lm_summary *summary);
+
+/* ---- a10: sign fix + depth raster glue (main.cc:466-509, errorMeasure.cpp:162-210) -------- */
+/* inliers3 z row and v are sign-fixed in place; depth_map (rows*cols doubles, `layout`) is zero
+ * filled and rasterised; depth_img (nullable, rows*cols uint8 row-major) is the 8-bit image. */
+RSDSFM_API int rsdsfm_depth_glue(rsdsfm_ctx *ctx, int mem, double *inliers3, int m, double *v, const double *K4,
+                      int rows, int cols, double z_min_init, int layout, double *depth_map,
+                      uint8_t *depth_img);
+
+/* ---- a12: Camera::setPose -> RsFrame::setRelativePose (camera.cc:340, rsframe.cc:771-800) - */
+/* Host computation.  R: rows x 9 (row-major 3x3), t: rows x 3. */
+RSDSFM_API int rsdsfm_set_relative_pose(const double *v, const double *w, double k, double gamma, int rows, double *R,
+                             double *t);
+
+/* ---- a13 + a14: Camera::backProject / backProjectGs (rsframe.cc:629-736, 803-878) -------- */
+/* image: rows*cols*3 BGR; depth: rows*cols doubles in `layout`; R,t: per-scanline relative poses
+ * (host, rows x 9 / rows x 3).  gs_out: rows*cols*3; coords3d (nullable): rows*cols*3 float. */
+RSDSFM_API int rsdsfm_backproject(rsdsfm_ctx *ctx, int mem, const uint8_t *image, const double *depth, int layout,
+                       int rows, int cols, const double *K4, const double *R, const double *t, int gs_mode,
+                       uint8_t *gs_out, float *coords3d);
+
+/* ---- a15: Camera::interpolateCrackyImage (camera.cc:753-774) ------------------------------ */
+RSDSFM_API int rsdsfm_fill_cracks(rsdsfm_ctx *ctx, int mem, const uint8_t *in, int rows, int cols, unsigned offset,
+                       uint8_t *out);
+
+/* ---- fused driver of the timed region "refine + rectify" (main.cc:457-523) ---------------- */
+/* nonLinearRefinement -> sign fix -> depth raster -> setPose -> backProject(Gs) ->
+ * interpolateCrackyImage(.,1) for one frame pair, without leaving the device.
+ * Array arguments live in `mem`; v,w,k (in/out), K4, summary on the host.
+ * Outputs: z_out[m] (sign-fixed refined depths), depth_map (rows*cols, `layout`),
+ * rectified (rows*cols*3). */
+RSDSFM_API int rsdsfm_refine_rectify(rsdsfm_ctx *ctx, int mem, const double *flow, const double *inliers3,
+                          const double *alpha, const double *alpha_k, int m, double *v, double *w, double *k,
+                          int const_acceleration, int gs_mode, const uint8_t *image, int rows, int cols,
+                          const double *K4, double gamma, int layout, double *z_out, double *depth_map,
+                          uint8_t *rectified, rsdsfm_lm_summary *summary);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSDSFM_H */

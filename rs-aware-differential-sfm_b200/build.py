@@ -1,0 +1,69 @@
+"""In-tree build of librsdsfm.so (sm_100a only) with nvcc.  No JIT cache: the .so lives next to
+this file so it travels with the repository snapshot to the GPU box."""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "librsdsfm.so")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+          "-Xcompiler", "-Wall"]
+# Translation units and extra flags.  --fmad=false where results must be bit-identical to the
+# reference's scalar IEEE arithmetic (RANSAC inlier sets, integer splat targets, alpha factors).
+UNITS = [
+    ("api.cu", []),
+    ("refine.cu", []),
+    ("ransac.cu", ["--fmad=false"]),
+    ("rectify.cu", ["--fmad=false"]),
+    ("preproc.cu", ["--fmad=false"]),
+]
+HEADERS = ["common.cuh", "lm_controller.h", "rs_math.cuh", "solve9.h", os.path.join("..", "..", "include", "rsdsfm.h")]
+
+
+def _nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: the CUDA extension cannot be built")
+    return exe
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    objs = []
+    for src, extra in UNITS:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _stale(o, [s] + hdrs):
+            cmd = [nvcc] + ARCH + COMMON + extra + ["-Xptxas", "-v"] * int(verbose) + ["-c", s, "-o", o]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if verbose or r.returncode != 0:
+                print(" ".join(cmd))
+                print(r.stdout + r.stderr)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed on %s" % src)
+    if force or _stale(LIB, objs):
+        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-Xcompiler", "-fPIC"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            print(r.stdout + r.stderr)
+            raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

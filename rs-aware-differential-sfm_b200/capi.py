@@ -1,0 +1,339 @@
+"""ctypes binding of librsdsfm.so (include/rsdsfm.h) for the tests and bench.py.
+
+Array arguments may be numpy arrays (RSDSFM_HOST: staged by the library) or torch CUDA tensors
+(RSDSFM_DEVICE: used in place).  There is no fallback: if the shared library is missing or no
+B200 is visible, construction of a Context raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librsdsfm.so")
+
+HOST, DEVICE = 0, 1
+DEPTH_COLMAJOR, DEPTH_ROWMAJOR = 0, 1
+
+EXPORTS = [
+    "rsdsfm_version", "rsdsfm_lm_default_options", "rsdsfm_create", "rsdsfm_destroy", "rsdsfm_last_error",
+    "rsdsfm_synchronize", "rsdsfm_launch_count", "rsdsfm_flatten", "rsdsfm_alpha", "rsdsfm_solve9",
+    "rsdsfm_ransac_score", "rsdsfm_ransac", "rsdsfm_gather_inliers", "rsdsfm_estimate_inverse_depths",
+    "rsdsfm_refine", "rsdsfm_depth_glue", "rsdsfm_set_relative_pose", "rsdsfm_backproject", "rsdsfm_fill_cracks",
+    "rsdsfm_refine_rectify",
+]
+
+
+class LmOptions(C.Structure):
+    _fields_ = [("max_num_iterations", C.c_int), ("function_tolerance", C.c_double),
+                ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
+                ("initial_trust_region_radius", C.c_double), ("max_trust_region_radius", C.c_double),
+                ("min_trust_region_radius", C.c_double), ("min_relative_decrease", C.c_double),
+                ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double),
+                ("max_num_consecutive_invalid_steps", C.c_int)]
+
+
+class LmSummary(C.Structure):
+    _fields_ = [("termination", C.c_int), ("reason", C.c_int), ("iterations", C.c_int),
+                ("num_successful", C.c_int), ("num_unsuccessful", C.c_int), ("initial_cost", C.c_double),
+                ("final_cost", C.c_double), ("final_radius", C.c_double),
+                ("final_gradient_max_norm", C.c_double), ("device_ms", C.c_double)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+_lib = None
+
+
+def load():
+    """dlopen the product library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("librsdsfm.so is missing: run __graft_entry__.build() (nvcc, sm_100a); "
+                               "there is no CPU fallback")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.rsdsfm_last_error.restype = C.c_char_p
+        _lib.rsdsfm_last_error.argtypes = [C.c_void_p]
+        _lib.rsdsfm_launch_count.restype = C.c_longlong
+        _lib.rsdsfm_launch_count.argtypes = [C.c_void_p]
+        _lib.rsdsfm_destroy.argtypes = [C.c_void_p]
+        _lib.rsdsfm_destroy.restype = None
+    return _lib
+
+
+def _is_torch(a):
+    return a is not None and type(a).__module__.startswith("torch")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_torch(a):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
+
+
+def _mem(*arrays):
+    kinds = {(_is_torch(a)) for a in arrays if a is not None}
+    if len(kinds) > 1:
+        raise ValueError("mixing host (numpy) and device (torch) arrays in one call")
+    return DEVICE if (kinds and kinds.pop()) else HOST
+
+
+def _f64(a):
+    if _is_torch(a):
+        assert a.is_cuda and a.is_contiguous() and str(a.dtype) == "torch.float64"
+        return a
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _small(a, n):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+    assert a.size == n
+    return a
+
+
+class RsdsfmError(RuntimeError):
+    pass
+
+
+class Context:
+    """One rsdsfm_ctx (one GPU, one stream)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.rsdsfm_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != 0:
+            raise RsdsfmError("rsdsfm_create failed (%d): %s" % (rc, self.lib.rsdsfm_last_error(None).decode()))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rsdsfm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RsdsfmError("rsdsfm error %d: %s" % (rc, self.lib.rsdsfm_last_error(self.h).decode()))
+
+    def synchronize(self):
+        self._ck(self.lib.rsdsfm_synchronize(self.h))
+
+    def launch_count(self):
+        return int(self.lib.rsdsfm_launch_count(self.h))
+
+    # ---- a2
+    def flatten(self, flow_img, K4, gamma, thr=1e-10, out=None):
+        """numpy in -> numpy out: (n, coord, flow, coord_px, flow_px, pixel_index)."""
+        flow_img = _f64(flow_img)
+        rows, cols = int(flow_img.shape[0]), int(flow_img.shape[1])
+        tot = rows * cols
+        K4 = _small(K4, 4)
+        n = C.c_int(0)
+        if _is_torch(flow_img):
+            import torch
+            mk = lambda k, dt: torch.empty(k, dtype=dt, device=flow_img.device)
+            coord, flow, cpx, fpx = (mk(2 * tot, torch.float64) for _ in range(4))
+            pidx = mk(tot, torch.int32)
+        else:
+            coord, flow, cpx, fpx = (np.empty(2 * tot) for _ in range(4))
+            pidx = np.empty(tot, dtype=np.int32)
+        self._ck(self.lib.rsdsfm_flatten(self.h, _mem(flow_img), _ptr(flow_img), rows, cols, _ptr(K4),
+                                         C.c_double(gamma), C.c_double(thr), _ptr(coord), _ptr(flow), _ptr(cpx),
+                                         _ptr(fpx), _ptr(pidx), C.byref(n)))
+        return n.value, coord, flow, cpx, fpx, pidx
+
+    # ---- a3 / a4
+    def alpha(self, flow_px, q_px, n, h, gamma):
+        flow_px = _f64(flow_px); q_px = _f64(q_px)
+        if _is_torch(flow_px):
+            import torch
+            a = torch.empty(n, dtype=torch.float64, device=flow_px.device); ak = torch.empty_like(a)
+        else:
+            a = np.empty(n); ak = np.empty(n)
+        self._ck(self.lib.rsdsfm_alpha(self.h, _mem(flow_px, q_px), _ptr(flow_px), _ptr(q_px), int(n), C.c_double(h),
+                                       C.c_double(gamma), _ptr(a), _ptr(ak)))
+        return a, ak
+
+    # ---- a6 / a8
+    def ransac_score(self, q, u, alpha, alpha_k, n, hyps, tol):
+        q = _f64(q); u = _f64(u); alpha = _f64(alpha); alpha_k = _f64(alpha_k)
+        hyps = np.ascontiguousarray(hyps, dtype=np.float64).reshape(-1, 7)
+        H = hyps.shape[0]
+        counts = np.zeros(H, dtype=np.int32); sumerr = np.zeros(H); best = C.c_int(-1)
+        if _is_torch(q):
+            import torch
+            mask = torch.zeros(max(n, 1), dtype=torch.uint8, device=q.device)
+            invd = torch.zeros(max(n, 1), dtype=torch.float64, device=q.device)
+        else:
+            mask = np.zeros(max(n, 1), dtype=np.uint8); invd = np.zeros(max(n, 1))
+        self._ck(self.lib.rsdsfm_ransac_score(self.h, _mem(q, u, alpha, alpha_k), _ptr(q), _ptr(u), _ptr(alpha),
+                                              _ptr(alpha_k), int(n), _ptr(hyps), H, C.c_double(tol), _ptr(counts),
+                                              _ptr(sumerr), C.byref(best), _ptr(mask), _ptr(invd)))
+        return dict(counts=counts, sumerr=sumerr, best_idx=best.value, mask=mask[:n], inv_depth=invd[:n])
+
+    def ransac(self, q, u, alpha, alpha_k, n, use_alpha_k, samples, tol):
+        q = _f64(q); u = _f64(u); alpha = _f64(alpha); alpha_k = _f64(alpha_k)
+        samples = np.ascontiguousarray(samples, dtype=np.int32).reshape(-1, 9)
+        H = samples.shape[0]
+        counts = np.zeros(H, dtype=np.int32); sumerr = np.zeros(H); best = C.c_int(-1)
+        best7 = np.zeros(7); hyps = np.zeros((H, 7))
+        if _is_torch(q):
+            import torch
+            mask = torch.zeros(n, dtype=torch.uint8, device=q.device)
+            invd = torch.zeros(n, dtype=torch.float64, device=q.device)
+        else:
+            mask = np.zeros(n, dtype=np.uint8); invd = np.zeros(n)
+        self._ck(self.lib.rsdsfm_ransac(self.h, _mem(q, u, alpha, alpha_k), _ptr(q), _ptr(u), _ptr(alpha), _ptr(alpha_k),
+                                        int(n), int(use_alpha_k), _ptr(samples), H, C.c_double(tol), _ptr(counts),
+                                        _ptr(sumerr), C.byref(best), _ptr(best7), _ptr(mask), _ptr(invd), _ptr(hyps)))
+        return dict(counts=counts, sumerr=sumerr, best_idx=best.value, w=best7[0:3].copy(), v=best7[3:6].copy(),
+                    k=float(best7[6]), mask=mask, inv_depth=invd, hyps=hyps)
+
+    def gather_inliers(self, q, alpha, alpha_k, n, mask, inv_depth):
+        q = _f64(q); alpha = _f64(alpha); alpha_k = _f64(alpha_k); inv_depth = _f64(inv_depth)
+        if _is_torch(q):
+            import torch
+            mk = lambda k, dt: torch.empty(max(k, 1), dtype=dt, device=q.device)
+            inl = mk(3 * n, torch.float64); a = mk(n, torch.float64); ak = mk(n, torch.float64); ix = mk(n, torch.int32)
+        else:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+            inl = np.empty(3 * max(n, 1)); a = np.empty(max(n, 1)); ak = np.empty(max(n, 1))
+            ix = np.empty(max(n, 1), dtype=np.int32)
+        m = C.c_int(0)
+        self._ck(self.lib.rsdsfm_gather_inliers(self.h, _mem(q, alpha, alpha_k, mask, inv_depth), _ptr(q), _ptr(alpha),
+                                                _ptr(alpha_k), int(n), _ptr(mask), _ptr(inv_depth), _ptr(inl), _ptr(a),
+                                                _ptr(ak), _ptr(ix), C.byref(m)))
+        m = m.value
+        return inl[:3 * m], a[:m], ak[:m], ix[:m], m
+
+    def estimate_inverse_depths(self, coord, flow, n, v, w, k, alpha, alpha_k):
+        coord = _f64(coord); flow = _f64(flow); alpha = _f64(alpha); alpha_k = _f64(alpha_k)
+        v = _small(v, 3); w = _small(w, 3)
+        if _is_torch(coord):
+            import torch
+            out = torch.empty(max(n, 1), dtype=torch.float64, device=coord.device)
+        else:
+            out = np.empty(max(n, 1))
+        S = LmSummary()
+        self._ck(self.lib.rsdsfm_estimate_inverse_depths(self.h, _mem(coord, flow, alpha, alpha_k), _ptr(coord), _ptr(flow),
+                                                         int(n), _ptr(v), _ptr(w), C.c_double(k), _ptr(alpha),
+                                                         _ptr(alpha_k), _ptr(out), C.byref(S)))
+        return out[:n], S.as_dict()
+
+    # ---- a9
+    def refine(self, flow, inliers3, alpha, alpha_k, m, v, w, k, const_acc, flow_index=None, opts=None):
+        flow = _f64(flow); inliers3 = _f64(inliers3); alpha = _f64(alpha); alpha_k = _f64(alpha_k)
+        v = _small(v, 3).copy(); w = _small(w, 3).copy(); kk = C.c_double(k)
+        if _is_torch(flow):
+            import torch
+            z = torch.empty(max(m, 1), dtype=torch.float64, device=flow.device)
+        else:
+            z = np.empty(max(m, 1))
+            if flow_index is not None:
+                flow_index = np.ascontiguousarray(flow_index, dtype=np.int32)
+        S = LmSummary()
+        self._ck(self.lib.rsdsfm_refine(self.h, _mem(flow, inliers3, alpha, alpha_k, flow_index), _ptr(flow),
+                                        _ptr(inliers3), _ptr(alpha), _ptr(alpha_k), int(m), _ptr(v), _ptr(w),
+                                        C.byref(kk), int(const_acc), _ptr(flow_index),
+                                        C.byref(opts) if opts is not None else None, _ptr(z), C.byref(S)))
+        return v, w, kk.value, z[:m], S.as_dict()
+
+    # ---- a10
+    def depth_glue(self, inliers3, m, v, K4, rows, cols, z_min_init=float("inf"), layout=DEPTH_COLMAJOR, want_img=False):
+        v = _small(v, 3).copy(); K4 = _small(K4, 4)
+        if _is_torch(inliers3):
+            import torch
+            inl = inliers3.clone()
+            dm = torch.empty(rows * cols, dtype=torch.float64, device=inl.device)
+            img = torch.empty(rows * cols, dtype=torch.uint8, device=inl.device) if want_img else None
+        else:
+            inl = _f64(inliers3).copy()
+            dm = np.empty(rows * cols)
+            img = np.empty(rows * cols, dtype=np.uint8) if want_img else None
+        self._ck(self.lib.rsdsfm_depth_glue(self.h, _mem(inl), _ptr(inl), int(m), _ptr(v), _ptr(K4), rows, cols,
+                                            C.c_double(z_min_init), int(layout), _ptr(dm), _ptr(img)))
+        return inl, v, dm, img
+
+    # ---- a12
+    def set_relative_pose(self, v, w, k, gamma, rows):
+        v = _small(v, 3); w = _small(w, 3)
+        R = np.empty(rows * 9); t = np.empty(rows * 3)
+        self._ck(self.lib.rsdsfm_set_relative_pose(_ptr(v), _ptr(w), C.c_double(k), C.c_double(gamma), rows, _ptr(R), _ptr(t)))
+        return R.reshape(rows, 3, 3), t.reshape(rows, 3)
+
+    # ---- a13 / a14
+    def backproject(self, image, depth, K4, R, t, gs_mode=False, layout=DEPTH_COLMAJOR, want_coords=False):
+        K4 = _small(K4, 4)
+        R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1); t = np.ascontiguousarray(t, dtype=np.float64).reshape(-1)
+        depth = _f64(depth)
+        rows, cols = int(image.shape[0]), int(image.shape[1])
+        if _is_torch(image):
+            import torch
+            out = torch.empty_like(image)
+            coords = torch.empty((rows, cols, 3), dtype=torch.float32, device=image.device) if want_coords else None
+        else:
+            image = np.ascontiguousarray(image, dtype=np.uint8)
+            out = np.empty_like(image)
+            coords = np.empty((rows, cols, 3), dtype=np.float32) if want_coords else None
+        self._ck(self.lib.rsdsfm_backproject(self.h, _mem(image, depth), _ptr(image), _ptr(depth), int(layout), rows, cols,
+                                             _ptr(K4), _ptr(R), _ptr(t), int(gs_mode), _ptr(out), _ptr(coords)))
+        return out, coords
+
+    # ---- a15
+    def fill_cracks(self, image, offset=1):
+        rows, cols = int(image.shape[0]), int(image.shape[1])
+        if _is_torch(image):
+            import torch
+            out = torch.empty_like(image)
+        else:
+            image = np.ascontiguousarray(image, dtype=np.uint8)
+            out = np.empty_like(image)
+        self._ck(self.lib.rsdsfm_fill_cracks(self.h, _mem(image), _ptr(image), rows, cols, C.c_uint(offset), _ptr(out)))
+        return out
+
+    # ---- fused driver
+    def refine_rectify(self, flow, inliers3, alpha, alpha_k, m, v, w, k, const_acc, gs_mode, image, K4, gamma,
+                       layout=DEPTH_COLMAJOR, out=None):
+        """Returns dict(v, w, k, z, depth_map, rectified, summary).  `out` may carry preallocated
+        (z, depth_map, rectified) buffers (pinned numpy or torch CUDA)."""
+        flow = _f64(flow); inliers3 = _f64(inliers3); alpha = _f64(alpha); alpha_k = _f64(alpha_k)
+        v = _small(v, 3).copy(); w = _small(w, 3).copy(); kk = C.c_double(k); K4 = _small(K4, 4)
+        rows, cols = int(image.shape[0]), int(image.shape[1])
+        if out is not None:
+            z, dm, rect = out
+        elif _is_torch(flow):
+            import torch
+            z = torch.empty(m, dtype=torch.float64, device=flow.device)
+            dm = torch.empty(rows * cols, dtype=torch.float64, device=flow.device)
+            rect = torch.empty_like(image)
+        else:
+            image = np.ascontiguousarray(image, dtype=np.uint8)
+            z = np.empty(m); dm = np.empty(rows * cols); rect = np.empty_like(image)
+        S = LmSummary()
+        self._ck(self.lib.rsdsfm_refine_rectify(self.h, _mem(flow, inliers3, alpha, alpha_k, image), _ptr(flow),
+                                                _ptr(inliers3), _ptr(alpha), _ptr(alpha_k), int(m), _ptr(v), _ptr(w),
+                                                C.byref(kk), int(const_acc), int(gs_mode), _ptr(image), rows, cols,
+                                                _ptr(K4), C.c_double(gamma), int(layout), _ptr(z), _ptr(dm), _ptr(rect),
+                                                C.byref(S)))
+        return dict(v=v, w=w, k=kk.value, z=z, depth_map=dm, rectified=rect, summary=S.as_dict())
+
+
+def solve9(q9, u9, alpha9, alpha_k9, use_alpha_k):
+    """minimal::calculateVelocities (host).  Returns (w, v, k)."""
+    lib = load()
+    q9 = _small(q9, 18); u9 = _small(u9, 18); a = _small(alpha9, 9); ak = _small(alpha_k9, 9)
+    out = np.empty(7)
+    rc = lib.rsdsfm_solve9(_ptr(q9), _ptr(u9), _ptr(a), _ptr(ak), int(use_alpha_k), _ptr(out))
+    if rc != 0:
+        raise RsdsfmError("rsdsfm_solve9 failed: %d" % rc)
+    return out[0:3].copy(), out[3:6].copy(), float(out[6])

@@ -1,0 +1,165 @@
+// common.cuh -- context, error handling, scratch management and block reductions shared by the
+// sm_100a kernels behind include/rsdsfm.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rsdsfm.h"
+
+namespace rsdsfm {
+
+constexpr int kNumSMsB200 = 148;
+constexpr int kThreads = 256;          // threads per CTA for the per-pixel map-reduce kernels
+constexpr int kWarps = kThreads / 32;
+
+// A grow-only device buffer owned by the context.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace rsdsfm
+
+struct rsdsfm_ctx {
+    int device = 0;
+    int num_sms = rsdsfm::kNumSMsB200;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    long long launches = 0;
+    std::string err;
+    // scratch
+    std::vector<rsdsfm::DevBuf *> bufs;
+    rsdsfm::DevBuf partials, sums, pix, dA, dB, scale_e, misc, stage[16], winner, tmp_img, depth_rm, poses;
+    rsdsfm::DevBuf hyp, rpart, flags, scan;
+    void *pinned = nullptr;   // small pinned host buffer for reduced sums / scalars
+    size_t pinned_cap = 0;
+};
+
+namespace rsdsfm {
+
+extern thread_local std::string g_create_error;
+
+inline int fail(rsdsfm_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    char buf[512];
+    if (e != cudaSuccess)
+        snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    else
+        snprintf(buf, sizeof buf, "%s", what);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define RS_CUDA(ctx, call)                                                        \
+    do {                                                                          \
+        cudaError_t e__ = (call);                                                 \
+        if (e__ != cudaSuccess) return ::rsdsfm::fail((ctx), RSDSFM_ERR_CUDA, #call, e__); \
+    } while (0)
+
+#define RS_TRY(expr)                         \
+    do {                                     \
+        int rc__ = (expr);                   \
+        if (rc__ != RSDSFM_OK) return rc__;  \
+    } while (0)
+
+inline int ensure(rsdsfm_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap && b.p) return RSDSFM_OK;
+    RS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (b.p) { RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t cap = bytes < 256 ? 256 : bytes;
+    cudaError_t e = cudaMalloc(&b.p, cap);
+    if (e != cudaSuccess) return fail(ctx, RSDSFM_ERR_NOMEM, "cudaMalloc", e);
+    b.cap = cap;
+    return RSDSFM_OK;
+}
+
+inline int ensure_pinned(rsdsfm_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->pinned_cap) return RSDSFM_OK;
+    if (ctx->pinned) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; }
+    RS_CUDA(ctx, cudaMallocHost(&ctx->pinned, bytes));
+    ctx->pinned_cap = bytes;
+    return RSDSFM_OK;
+}
+
+// Stage an input array: returns a device pointer holding `bytes` of `src` (which lives in `mem`).
+inline int stage_in(rsdsfm_ctx *ctx, int mem, int slot, const void *src, size_t bytes, const void **dev)
+{
+    if (mem == RSDSFM_DEVICE || src == nullptr) { *dev = src; return RSDSFM_OK; }
+    RS_TRY(ensure(ctx, ctx->stage[slot], bytes));
+    RS_CUDA(ctx, cudaMemcpyAsync(ctx->stage[slot].p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = ctx->stage[slot].p;
+    return RSDSFM_OK;
+}
+// Reserve an output array: a device pointer of `bytes`; call stage_out afterwards.
+inline int stage_out_reserve(rsdsfm_ctx *ctx, int mem, int slot, void *dst, size_t bytes, void **dev)
+{
+    if (mem == RSDSFM_DEVICE || dst == nullptr) { *dev = dst; return RSDSFM_OK; }
+    RS_TRY(ensure(ctx, ctx->stage[slot], bytes));
+    *dev = ctx->stage[slot].p;
+    return RSDSFM_OK;
+}
+inline int stage_out(rsdsfm_ctx *ctx, int mem, void *dst, const void *dev, size_t bytes)
+{
+    if (mem == RSDSFM_DEVICE || dst == nullptr || bytes == 0) return RSDSFM_OK;
+    RS_CUDA(ctx, cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return RSDSFM_OK;
+}
+
+inline int grid_for(const rsdsfm_ctx *ctx, long long n, int per_sm = 2)
+{
+    long long need = (n + kThreads - 1) / kThreads;
+    long long cap = (long long)ctx->num_sms * per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+#ifdef __CUDACC__
+// ---- block reductions -------------------------------------------------------------------------
+// NS sums + NM maxima per thread -> one row of `out` per CTA: out[blockIdx.x * (NS+NM) + j].
+// Fixed shuffle tree + fixed warp order: bit-reproducible for a given launch geometry.
+template <int NS, int NM>
+__device__ __forceinline__ void block_reduce_store(double (&s)[NS > 0 ? NS : 1], double (&mx)[NM > 0 ? NM : 1],
+                                                   double *out)
+{
+    __shared__ double sh[kWarps][NS + NM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        double v = s[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[warp][j] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < NM; ++j) {
+        double v = mx[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (lane == 0) sh[warp][NS + j] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < NS + NM; j += blockDim.x) {
+        double v = sh[0][j];
+        if (j < NS) { for (int w2 = 1; w2 < kWarps; ++w2) v += sh[w2][j]; }
+        else        { for (int w2 = 1; w2 < kWarps; ++w2) v = fmax(v, sh[w2][j]); }
+        out[(size_t)blockIdx.x * (NS + NM) + j] = v;
+    }
+}
+
+// NaN-propagating "bad value" detector usable inside fmax reductions (fmax drops NaNs).
+__device__ __forceinline__ double bad_flag(double a) { return isfinite(a) ? 0.0 : 1.0; }
+#endif
+
+// out[j] = reduce over blocks b of partials[b*(ns+nm)+j]; sums in ascending block order.
+void launch_final_reduce(rsdsfm_ctx *ctx, const double *partials, int nblocks, int ns, int nm, double *out);
+
+}  // namespace rsdsfm

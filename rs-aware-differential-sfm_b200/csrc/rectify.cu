@@ -1,0 +1,252 @@
+// rectify.cu -- sign fix + depth raster glue, per-scanline relative poses, the global-shutter
+// rectification splat and the crack fill.  Compiled with --fmad=false: the per-pixel projection
+// mirrors the reference's operation order so the integer splat targets are reproducible.
+//
+//   a10  main.cc:466-509 / errorMeasure.cpp:162-210      k_glue_* kernels
+//   a12  RsFrame::setRelativePose  rsframe.cc:771-800      k_set_relative_pose
+//   a13  planeToSpace / cameraToWorldFrame / worldToCameraFrame / spaceToPlane  rsframe.cc:629-736
+//   a14  RsFrame::backProject / backProjectGs  rsframe.cc:803-878   k_splat_vote + k_splat_gather
+//   a15  Camera::interpolateCrackyImage  camera.cc:694-774  k_fill_cracks
+//
+// The reference splats sequentially in raster order, so on a collision the source pixel with the
+// highest raster index wins (Q15).  Here every source pixel votes with atomicMax(raster index+1)
+// into a per-target winner map, and a second kernel gathers the winning colours: deterministic
+// and identical to last-writer-wins.
+#include "common.cuh"
+
+namespace rsdsfm {
+
+// ---------------------------------------------------------------- a10: sign fix + depth raster
+// sums[0] = sum z, maxima: [0] = max z, [1] = max(-z)  (=> min z)
+__global__ void __launch_bounds__(kThreads) k_glue_reduce(const double *__restrict__ z, int zs, int m, double *partials)
+{
+    double s[1] = {0.0};
+    double mx[2] = {-INFINITY, -INFINITY};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        const double zi = z[(size_t)i * zs];
+        s[0] += zi;
+        mx[0] = fmax(mx[0], zi);
+        mx[1] = fmax(mx[1], -zi);
+    }
+    block_reduce_store<1, 2>(s, mx, partials);
+}
+
+// stats (device, 8 doubles): [0] sum z, [1] max z, [2] max -z  ->  writes [3] sign (+1/-1),
+// [4] z_min, [5] z_max after the sign fix (z_min starts at z_min_init, z_max at 0 like the reference)
+__global__ void k_glue_stats(double *stats, int m, double z_min_init)
+{
+    const double z_mean = stats[0] * 1.0 / m;
+    const double sign = (z_mean < 0) ? -1.0 : 1.0;
+    double zmax = sign > 0 ? stats[1] : stats[2];
+    double zmin = sign > 0 ? -stats[2] : -stats[1];
+    stats[3] = sign;
+    stats[4] = fmin(z_min_init, zmin);
+    stats[5] = fmax(0.0, zmax);
+}
+
+__device__ __forceinline__ bool to_int_trunc(double a, int &out)
+{
+    if (!(fabs(a) < 2147483648.0)) return false;   // NaN / Inf / overflow: rejected (x86 gives INT_MIN)
+    out = (int)a;
+    return true;
+}
+
+// z (stride zs doubles, e.g. 3 for the z row of an Array3Xd) is sign-fixed in place; xy gives the
+// normalised coordinates (stride 3 when interleaved in inliers3).
+__global__ void k_glue_raster(double *z, int zs, const double *__restrict__ xyz, int xs, int m,
+                              const double *__restrict__ stats, double fx, double fy, double cx, double cy, int rows,
+                              int cols, int layout, double *depth_map, uint8_t *depth_img)
+{
+    const double sign = stats[3], z_min = stats[4], z_max = stats[5];
+    const double multiplier = 244.0 / (z_max - z_min);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        double zi = z[(size_t)i * zs];
+        if (sign < 0) { zi = zi * -1.0; z[(size_t)i * zs] = zi; }
+        const double xd = fx * xyz[(size_t)i * xs] + cx + 0.5;
+        const double yd = fy * xyz[(size_t)i * xs + 1] + cy + 0.5;
+        int x, y;
+        if (!to_int_trunc(xd, x) || !to_int_trunc(yd, y)) continue;
+        if (x < 0 || x >= cols || y < 0 || y >= rows) continue;   // UB in the reference (Q3): skipped
+        if (depth_img) {
+            const double zz = (zi - z_min) * multiplier;
+            int zq = 10;
+            if (fabs(zz) < 2147483000.0) zq = 10 + (int)zz;
+            depth_img[(size_t)y * cols + x] = (uint8_t)zq;
+        }
+        const size_t idx = (layout == RSDSFM_DEPTH_COLMAJOR) ? ((size_t)y + (size_t)x * rows) : ((size_t)y * cols + x);
+        depth_map[idx] = zi;
+    }
+}
+
+// ---------------------------------------------------------------- a12: per-scanline poses
+// motion7 (device): v[3], w[3], k.  stats may be NULL (no sign fix), else stats[3] multiplies v.
+__global__ void k_set_relative_pose(const double *__restrict__ motion7, const double *__restrict__ stats, double gamma,
+                                    int rows, double *R, double *t)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const double sign = stats ? stats[3] : 1.0;
+    double v[3] = {motion7[0], motion7[1], motion7[2]};
+    if (sign < 0) { v[0] *= -1.0; v[1] *= -1.0; v[2] *= -1.0; }
+    const double w0 = motion7[3], w1 = motion7[4], w2 = motion7[5], k = motion7[6];
+    double *Ri = R + 9 * (size_t)i, *ti = t + 3 * (size_t)i;
+    if (i == 0) {
+        Ri[0] = 1; Ri[1] = 0; Ri[2] = 0; Ri[3] = 0; Ri[4] = 1; Ri[5] = 0; Ri[6] = 0; Ri[7] = 0; Ri[8] = 1;
+        ti[0] = 0; ti[1] = 0; ti[2] = 0;
+        return;
+    }
+    const double skew[9] = {0, -w2, w1, w2, 0, -w0, -w1, w0, 0};
+    const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    const double beta_1 = (gamma * i / rows + 0.5 * k * (gamma * gamma * i * i) / (rows * rows)) * (2.0 / (2.0 + k));
+    double Rn[9];
+    for (int a = 0; a < 9; ++a) Rn[a] = I3[a] + beta_1 * skew[a];
+    for (int r = 0; r < 3; ++r)                                   // R0 * R_new with R0 = I (:797)
+        for (int c = 0; c < 3; ++c)
+            Ri[r * 3 + c] = I3[r * 3 + 0] * Rn[0 * 3 + c] + I3[r * 3 + 1] * Rn[1 * 3 + c] + I3[r * 3 + 2] * Rn[2 * 3 + c];
+    for (int a = 0; a < 3; ++a) ti[a] = 0.0 + beta_1 * v[a];
+}
+
+// ---------------------------------------------------------------- a13 + a14: splat
+struct SplatParams {
+    double fx, fy, cx, cy;
+    int rows, cols, layout, gs_mode;
+};
+
+__global__ void __launch_bounds__(kThreads) k_splat_vote(const uint8_t *__restrict__ image, const double *__restrict__ depth,
+                                                         const double *__restrict__ R, const double *__restrict__ t,
+                                                         SplatParams P, unsigned int *winner, float *coords3d)
+{
+    const long long total = (long long)P.rows * P.cols;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(p / P.cols), x = (int)(p - (long long)y * P.cols);
+        const uint8_t b = image[3 * p], g = image[3 * p + 1], r = image[3 * p + 2];
+        if (coords3d) { coords3d[3 * p] = 0.f; coords3d[3 * p + 1] = 0.f; coords3d[3 * p + 2] = 0.f; }
+        if (b == 1 && g == 1 && r == 1) continue;                                   // rsframe.cc:815
+        const int s = P.gs_mode ? 0 : y;
+        const double *Rs = R + 9 * (size_t)s, *ts = t + 3 * (size_t)s;
+        // inverse pose [R^T | -R^T t]  (rsframe.cc:719-733)
+        double Rt[9], ti[3];
+        for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) Rt[a * 3 + c] = Rs[c * 3 + a];
+        for (int a = 0; a < 3; ++a) ti[a] = (-Rt[a * 3 + 0]) * ts[0] + (-Rt[a * 3 + 1]) * ts[1] + (-Rt[a * 3 + 2]) * ts[2];
+        // planeToSpace (rsframe.cc:646-665)
+        const double nx = ((double)x - P.cx) * 1.0 / P.fx;
+        const double ny = ((double)y - P.cy) * 1.0 / P.fy;
+        const double z = depth[(P.layout == RSDSFM_DEPTH_COLMAJOR) ? ((size_t)y + (size_t)x * P.rows) : (size_t)p];
+        const double Pc[3] = {z * nx, z * ny, z * 1.0};
+        double Pw[3], Pg[3];
+        for (int a = 0; a < 3; ++a)
+            Pw[a] = Rt[a * 3 + 0] * Pc[0] + Rt[a * 3 + 1] * Pc[1] + Rt[a * 3 + 2] * Pc[2] + ti[a] * 1.0;
+        for (int a = 0; a < 3; ++a)                                                  // scanline 0 pose (:821)
+            Pg[a] = R[a * 3 + 0] * Pw[0] + R[a * 3 + 1] * Pw[1] + R[a * 3 + 2] * Pw[2] + t[a] * 1.0;
+        const double u = Pg[0] / Pg[2] * P.fx + P.cx;                                // spaceToPlane (:629-642)
+        const double v = Pg[1] / Pg[2] * P.fx + P.cy;                                // y uses f_x too (Q12)
+        if (coords3d) { coords3d[3 * p] = (float)Pw[0]; coords3d[3 * p + 1] = (float)Pw[1]; coords3d[3 * p + 2] = (float)Pw[2]; }
+        int tx, ty;
+        if (!to_int_trunc(u + 0.5, tx) || !to_int_trunc(v + 0.5, ty)) continue;
+        if (tx >= 0 && tx < P.cols && ty >= 0 && ty < P.rows)
+            atomicMax(&winner[(size_t)ty * P.cols + tx], (unsigned int)(p + 1));
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_splat_gather(const uint8_t *__restrict__ image,
+                                                           const unsigned int *__restrict__ winner, long long total,
+                                                           uint8_t *gs)
+{
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+        const unsigned int wv = winner[p];
+        uint8_t b = 0, g = 0, r = 0;
+        if (wv) { const size_t q = (size_t)(wv - 1) * 3; b = image[q]; g = image[q + 1]; r = image[q + 2]; }
+        gs[3 * p] = b; gs[3 * p + 1] = g; gs[3 * p + 2] = r;
+    }
+}
+
+// ---------------------------------------------------------------- a15: crack fill
+__device__ __forceinline__ bool is_black(const uint8_t *p)
+{   // cv::norm(Vec3b) <= 15  <=>  b^2+g^2+r^2 <= 225
+    const int s = (int)p[0] * p[0] + (int)p[1] * p[1] + (int)p[2] * p[2];
+    return s <= 225;
+}
+__device__ __forceinline__ uint8_t saturate_u8(double v)
+{   // cv::saturate_cast<uchar>(double) = cvRound (half to even) + clamp
+    const double r = rint(v);
+    return (uint8_t)(r < 0.0 ? 0.0 : (r > 255.0 ? 255.0 : r));
+}
+
+__global__ void __launch_bounds__(kThreads) k_fill_cracks(const uint8_t *__restrict__ in, int rows, int cols, int off,
+                                                          uint8_t *out)
+{
+    const long long total = (long long)rows * cols;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(p / cols), col = (int)(p - (long long)row * cols);
+        const uint8_t *c = in + 3 * p;
+        uint8_t o0 = c[0], o1 = c[1], o2 = c[2];
+        if (row >= off && row < rows - off && col >= off && col < cols - off && is_black(c)) {
+            const uint8_t *nb[4] = {in + 3 * (p - (long long)off * cols), in + 3 * (p + (long long)off * cols),
+                                    in + 3 * (p - off), in + 3 * (p + off)};
+            double s0 = 0, s1 = 0, s2 = 0;
+            unsigned count = 0;
+            for (int a = 0; a < 4; ++a)
+                if (!is_black(nb[a])) { s0 += nb[a][0]; s1 += nb[a][1]; s2 += nb[a][2]; count++; }
+            if (count > 0) {
+                const double f = 1 / (double)count;
+                o0 = saturate_u8(f * s0); o1 = saturate_u8(f * s1); o2 = saturate_u8(f * s2);
+            }
+        }
+        out[3 * p] = o0; out[3 * p + 1] = o1; out[3 * p + 2] = o2;
+    }
+}
+
+// ---------------------------------------------------------------- host-side launchers (device pointers)
+int glue_device(rsdsfm_ctx *ctx, double *z, int zs, const double *xyz, int xs, int m, const double *K4, int rows,
+                int cols, double z_min_init, int layout, double *depth_map, uint8_t *depth_img, double *stats /*device, 8*/)
+{
+    const int grid = grid_for(ctx, m, 4);
+    RS_TRY(ensure(ctx, ctx->rpart, sizeof(double) * 3 * (size_t)grid));
+    RS_CUDA(ctx, cudaMemsetAsync(depth_map, 0, sizeof(double) * (size_t)rows * cols, ctx->stream));
+    if (depth_img) RS_CUDA(ctx, cudaMemsetAsync(depth_img, 0, (size_t)rows * cols, ctx->stream));
+    if (m > 0) {
+        k_glue_reduce<<<grid, kThreads, 0, ctx->stream>>>(z, zs, m, (double *)ctx->rpart.p);
+        ctx->launches++;
+        launch_final_reduce(ctx, (double *)ctx->rpart.p, grid, 1, 2, stats);
+        k_glue_stats<<<1, 1, 0, ctx->stream>>>(stats, m, z_min_init);
+        ctx->launches++;
+        k_glue_raster<<<grid, kThreads, 0, ctx->stream>>>(z, zs, xyz, xs, m, stats, K4[0], K4[1], K4[2], K4[3], rows,
+                                                          cols, layout, depth_map, depth_img);
+        ctx->launches++;
+    }
+    return RSDSFM_OK;
+}
+
+int poses_device(rsdsfm_ctx *ctx, const double *motion7_dev, const double *stats_dev, double gamma, int rows, double *R,
+                 double *t)
+{
+    k_set_relative_pose<<<(rows + 127) / 128, 128, 0, ctx->stream>>>(motion7_dev, stats_dev, gamma, rows, R, t);
+    ctx->launches++;
+    return RSDSFM_OK;
+}
+
+int backproject_device(rsdsfm_ctx *ctx, const uint8_t *image, const double *depth, int layout, int rows, int cols,
+                       const double *K4, const double *R, const double *t, int gs_mode, uint8_t *gs_out, float *coords3d)
+{
+    const long long total = (long long)rows * cols;
+    RS_TRY(ensure(ctx, ctx->winner, sizeof(unsigned int) * (size_t)total));
+    RS_CUDA(ctx, cudaMemsetAsync(ctx->winner.p, 0, sizeof(unsigned int) * (size_t)total, ctx->stream));
+    SplatParams P{K4[0], K4[1], K4[2], K4[3], rows, cols, layout, gs_mode};
+    const int grid = grid_for(ctx, total, 8);
+    k_splat_vote<<<grid, kThreads, 0, ctx->stream>>>(image, depth, R, t, P, (unsigned int *)ctx->winner.p, coords3d);
+    ctx->launches++;
+    k_splat_gather<<<grid, kThreads, 0, ctx->stream>>>(image, (const unsigned int *)ctx->winner.p, total, gs_out);
+    ctx->launches++;
+    return RSDSFM_OK;
+}
+
+int fill_cracks_device(rsdsfm_ctx *ctx, const uint8_t *in, int rows, int cols, unsigned offset, uint8_t *out)
+{
+    const long long total = (long long)rows * cols;
+    const int grid = grid_for(ctx, total, 8);
+    k_fill_cracks<<<grid, kThreads, 0, ctx->stream>>>(in, rows, cols, (int)offset, out);
+    ctx->launches++;
+    return RSDSFM_OK;
+}
+
+}  // namespace rsdsfm
