@@ -101,6 +101,12 @@ RSDSFM_API const char *rsdsfm_last_error(rsdsfm_ctx *ctx);   /* ctx may be NULL:
 RSDSFM_API int rsdsfm_synchronize(rsdsfm_ctx *ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 RSDSFM_API long long rsdsfm_launch_count(rsdsfm_ctx *ctx);
+/* Per-kernel timing of the LM passes with CUDA events on the context's stream (what Ceres'
+ * Summary::FullReport timing breakdown gave the reference user).  enable resets the counters.
+ * out8: [0] pass-A ms, [1] pass-A launches, [2] pass-A residual blocks processed,
+ *       [3] pass-B ms, [4] pass-B launches, [5] pass-B residual blocks processed, [6..7] reserved. */
+RSDSFM_API int rsdsfm_profile_enable(rsdsfm_ctx *ctx, int on);
+RSDSFM_API int rsdsfm_profile_read(rsdsfm_ctx *ctx, double *out8);
 
 /* ---- a2: flatten + normalise glue (main.cc:398-432, errorMeasure.cpp:66-97) --------------- */
 /* flow_img: rows*cols*2.  Outputs (each 2*rows*cols doubles) are pre-filled like the reference

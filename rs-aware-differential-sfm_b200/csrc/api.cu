@@ -13,6 +13,10 @@ thread_local std::string g_create_error;
 // implemented in the other translation units (device pointers, context stream)
 int refine_device(rsdsfm_ctx *, const double *, const double *, const double *, const double *, int, double *, double *,
                   double *, int, const int32_t *, const rsdsfm_lm_options *, double *, rsdsfm_lm_summary *);
+int refine_async(rsdsfm_ctx *, const double *, const double *, const double *, const double *, int, const double *,
+                 const double *, double, int, const int32_t *, const rsdsfm_lm_options *, double *);
+int lm_collect(rsdsfm_ctx *, int, int, Motion *, rsdsfm_lm_summary *, bool *);
+const double *lm_motion_device(rsdsfm_ctx *);
 int estimate_inverse_depths_device(rsdsfm_ctx *, const double *, const double *, int, const double *, const double *, double,
                                    const double *, const double *, double *, rsdsfm_lm_summary *);
 int glue_device(rsdsfm_ctx *, double *, int, const double *, int, int, const double *, int, int, double, int, double *,
@@ -91,6 +95,8 @@ int rsdsfm_create(int device, void *cuda_stream, rsdsfm_ctx **out)
     }
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
+    cudaEventCreate(&ctx->pe0);
+    cudaEventCreate(&ctx->pe1);
     *out = ctx;
     return RSDSFM_OK;
 }
@@ -107,6 +113,8 @@ void rsdsfm_destroy(rsdsfm_ctx *ctx)
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->pe0) cudaEventDestroy(ctx->pe0);
+    if (ctx->pe1) cudaEventDestroy(ctx->pe1);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -121,6 +129,21 @@ int rsdsfm_synchronize(rsdsfm_ctx *ctx)
 }
 
 long long rsdsfm_launch_count(rsdsfm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int rsdsfm_profile_enable(rsdsfm_ctx *ctx, int on)
+{
+    if (!ctx) return RSDSFM_ERR_ARG;
+    ctx->profile = on != 0;
+    for (double &p : ctx->prof) p = 0.0;
+    return RSDSFM_OK;
+}
+
+int rsdsfm_profile_read(rsdsfm_ctx *ctx, double *out8)
+{
+    if (!ctx || !out8) return RSDSFM_ERR_ARG;
+    for (int j = 0; j < 8; ++j) out8[j] = ctx->prof[j];
+    return RSDSFM_OK;
+}
 
 int rsdsfm_flatten(rsdsfm_ctx *ctx, int mem, const double *flow_img, int rows, int cols, const double *K4, double gamma,
                    double flow_threshold, double *coord, double *flow, double *coord_px, double *flow_px,
@@ -407,35 +430,47 @@ int rsdsfm_refine_rectify(rsdsfm_ctx *ctx, int mem, const double *flow, const do
     RS_TRY(stage_out_reserve(ctx, mem, 5, z_out, sizeof(double) * mm, &d_z));
     RS_TRY(stage_out_reserve(ctx, mem, 6, depth_map, sizeof(double) * tot, &d_dm));
     RS_TRY(stage_out_reserve(ctx, mem, 7, rectified, tot * 3, &d_out));
-    // nonLinearRefinement (main.cc:457)
-    RS_TRY(refine_device(ctx, (const double *)d_f, (const double *)d_i, (const double *)d_a, (const double *)d_ak, m, v, w, k,
-                         const_acceleration, nullptr, nullptr, (double *)d_z, summary));
-    // sign fix + depth raster (main.cc:466-509)
+    rsdsfm_lm_summary local;
+    if (!summary) summary = &local;
+    memset(summary, 0, sizeof *summary);
     RS_TRY(ensure(ctx, ctx->misc, 256));
-    double *stats = (double *)ctx->misc.p, *motion7 = stats + 8;
-    RS_TRY(glue_device(ctx, (double *)d_z, 1, (const double *)d_i, 3, m, K4, rows, cols, INFINITY, layout, (double *)d_dm,
-                       nullptr, stats));
-    // setPose (main.cc:516) -> per-scanline poses, with the sign-fixed v
-    RS_TRY(ensure_pinned(ctx, 1024));
-    double *hm = (double *)ctx->pinned + 16;
-    for (int j = 0; j < 3; ++j) { hm[j] = v[j]; hm[3 + j] = w[j]; }
-    hm[6] = *k;
-    RS_CUDA(ctx, cudaMemcpyAsync(motion7, hm, sizeof(double) * 7, cudaMemcpyHostToDevice, ctx->stream));
     RS_TRY(ensure(ctx, ctx->poses, sizeof(double) * 12 * (size_t)rows));
-    double *dR = (double *)ctx->poses.p, *dt = dR + 9 * (size_t)rows;
-    RS_TRY(poses_device(ctx, motion7, stats, gamma, rows, dR, dt));
-    // backProject / backProjectGs (main.cc:518-522) + interpolateCrackyImage (main.cc:523)
     RS_TRY(ensure(ctx, ctx->tmp_img, tot * 3));
-    RS_TRY(backproject_device(ctx, (const uint8_t *)d_img, (const double *)d_dm, layout, rows, cols, K4, dR, dt, gs_mode,
-                              (uint8_t *)ctx->tmp_img.p, nullptr));
-    RS_TRY(fill_cracks_device(ctx, (const uint8_t *)ctx->tmp_img.p, rows, cols, 1, (uint8_t *)d_out));
-    RS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, stats, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    RS_TRY(stage_out(ctx, mem, z_out, d_z, sizeof(double) * mm));
-    RS_TRY(stage_out(ctx, mem, depth_map, d_dm, sizeof(double) * tot));
-    RS_TRY(stage_out(ctx, mem, rectified, d_out, tot * 3));
-    RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (((double *)ctx->pinned)[3] < 0) { v[0] *= -1.0; v[1] *= -1.0; v[2] *= -1.0; }
-    return RSDSFM_OK;
+    double *stats = (double *)ctx->misc.p;
+    double *dR = (double *)ctx->poses.p, *dt = dR + 9 * (size_t)rows;
+    const int nf = const_acceleration ? 7 : 6;
+    // Everything below is queued on the context's stream without a host round trip: the refined
+    // motion stays in the solver's device control block and feeds the pose kernel directly.
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        // nonLinearRefinement (main.cc:457)
+        RS_TRY(refine_async(ctx, (const double *)d_f, (const double *)d_i, (const double *)d_a, (const double *)d_ak, m, v, w,
+                            *k, const_acceleration, nullptr, nullptr, (double *)d_z));
+        // sign fix + depth raster (main.cc:466-509)
+        RS_TRY(glue_device(ctx, (double *)d_z, 1, (const double *)d_i, 3, m, K4, rows, cols, INFINITY, layout, (double *)d_dm,
+                           nullptr, stats));
+        // setPose (main.cc:516) -> per-scanline poses, with the sign-fixed v
+        RS_TRY(poses_device(ctx, lm_motion_device(ctx), stats, gamma, rows, dR, dt));
+        // backProject / backProjectGs (main.cc:518-522) + interpolateCrackyImage (main.cc:523)
+        RS_TRY(backproject_device(ctx, (const uint8_t *)d_img, (const double *)d_dm, layout, rows, cols, K4, dR, dt, gs_mode,
+                                  (uint8_t *)ctx->tmp_img.p, nullptr));
+        RS_TRY(fill_cracks_device(ctx, (const uint8_t *)ctx->tmp_img.p, rows, cols, 1, (uint8_t *)d_out));
+        RS_TRY(stage_out(ctx, mem, z_out, d_z, sizeof(double) * mm));
+        RS_TRY(stage_out(ctx, mem, depth_map, d_dm, sizeof(double) * tot));
+        RS_TRY(stage_out(ctx, mem, rectified, d_out, tot * 3));
+        double *hstats = (double *)((char *)ctx->pinned + ctx->pinned_cap - 256);
+        RS_CUDA(ctx, cudaMemcpyAsync(hstats, stats, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        Motion mot;
+        for (int j = 0; j < 3; ++j) { mot.v[j] = v[j]; mot.w[j] = w[j]; }
+        mot.k = *k;
+        bool overflow = false;
+        RS_TRY(lm_collect(ctx, nf, m, &mot, summary, &overflow));      // the one synchronisation of the step
+        if (overflow) continue;                                         // exception list enlarged: run again
+        const double sign = (hstats[3] < 0) ? -1.0 : 1.0;
+        for (int j = 0; j < 3; ++j) { v[j] = mot.v[j] * sign; w[j] = mot.w[j]; }
+        *k = mot.k;
+        return RSDSFM_OK;
+    }
+    return fail(ctx, RSDSFM_ERR_INTERNAL, "refine_rectify: exception list overflow persisted");
 }
 
 }  // extern "C"

@@ -37,9 +37,16 @@ struct rsdsfm_ctx {
     // scratch
     std::vector<rsdsfm::DevBuf *> bufs;
     rsdsfm::DevBuf partials, sums, pix, dA, dB, scale_e, misc, stage[16], winner, tmp_img, depth_rm, poses;
-    rsdsfm::DevBuf hyp, rpart, flags, scan;
+    rsdsfm::DevBuf hyp, rpart, flags, scan, lm_shared, exc;
+    int exc_cap = 0;          // capacity (entries) of the clamped-pixel exception list
     void *pinned = nullptr;   // small pinned host buffer for reduced sums / scalars
     size_t pinned_cap = 0;
+    // per-kernel profiling (bench.py's roofline): CUDA events around the LM passes
+    bool profile = false;
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // [0] pass A ms, [1] pass A phases, [2] pass A residual blocks,
+                                                 // [3] pass B ms, [4] pass B phases, [5] pass B residual blocks,
+                                                 // [6] LM kernel ms (CUDA events), [7] LM kernel launches
 };
 
 namespace rsdsfm {

@@ -10,8 +10,20 @@
 // Appendix B).  The O(n) work (residuals, Jacobians, Schur elimination, back substitution) is
 // done by the kernels in refine.cu / ransac.cu, which hand this controller their reduced sums.
 //
-// The struct is plain data + __host__ __device__ methods so the same code drives the
-// host-stepped solver and the persistent on-device solver.
+// Radius-independent Schur sums.  With e = dr/dd (2-vector), n = (-e1, e0) and F = dr/d(motion),
+// the per-pixel projector of the 1x1 e-block elimination is
+//     I - q e e^T ,  q = s_e^2 / (s_e^2 e^Te + clamp(s_e^2 e^Te, min, max) / radius)
+// and for every pixel whose LM diagonal is not clamped it equals
+//     (n n^T + e e^T / (radius + 1)) / e^Te .
+// The passes therefore accumulate   G1 = sum (F^Tn)(n^TF)/e^Te,  G2 = sum (F^Te)(e^TF)/e^Te,
+// h1 = sum (F^Tn)(n^Tr)/e^Te,  h2 = sum (F^Te)(e^Tr)/e^Te   once per evaluation point, and
+//     S = G1 + G2/(radius+1),  rhs = h1 + h2/(radius+1),  F^TF = G1 + G2,  F^Tr = h1 + h2
+// follow for ANY radius: a rejected step needs no new pass over the pixels.  The few pixels
+// whose diagonal IS clamped (|e| ~ 0: at the focus of expansion) put F^TF / F^Tr into G1 / h1
+// and are listed as exceptions; their radius-dependent term is subtracted by the controller.
+//
+// Plain data + __host__ __device__ methods: the same code drives the persistent on-device
+// solver (refine.cu) and the host-stepped RANSAC depth solver (ransac.cu).
 #pragma once
 
 #include <float.h>
@@ -35,20 +47,28 @@ RS_HD inline int tri_index(int nf, int i, int j)   // i <= j
     return i * nf - (i * (i - 1)) / 2 + (j - i);
 }
 
-// Layout of the reduced sums the per-pixel passes deliver.
-// Pass A (evaluation at x + Schur elimination):   sums, then maxima
-struct SumsA {
-    enum { COST = 0, SUMSQ_D = 1, GF = 2, CSF = GF + kMaxNF, RHS = CSF + kMaxNF, S = RHS + kMaxNF,
-           NS = S + kTri };
-    enum { GMAX_E = 0, BAD = 1, NM = 2 };
+// Reduced sums of an evaluation pass (pass A) at the current point; radius independent.
+struct EvalSums {
+    double cost;       // sum 0.5 |r|^2
+    double sumsq_d;    // sum d^2
+    double gmax_e;     // max |e^T r|   (gradient of the depth blocks)
+    double bad;        // > 0: a residual / Jacobian entry was not finite
+    double G1[kTri], G2[kTri], h1[kMaxNF], h2[kMaxNF];
 };
-// Pass B (back substitution + candidate evaluation)
-struct SumsB {
-    enum { MCC = 0, STEP_SQ = 1, CAND_COST = 2, NS = 3 };
-    enum { BAD_STEP = 0, BAD_CAND = 1, NM = 2 };
+// Radius-dependent correction of the clamped pixels: sum q fe fe^T and sum q fe (e^T r).
+struct ExcSums {
+    double S[kTri], rhs[kMaxNF];
+};
+// Reduced sums of a candidate pass (pass B).
+struct CandSums {
+    double mcc;        // sum (J delta)^T (r + J delta / 2)      (= -model_cost_change)
+    double step_sq;    // sum (d - d_cand)^2
+    double cand_cost;  // sum 0.5 |r(x_cand)|^2
+    double bad_step;   // > 0: a depth step was not finite
+    double bad_cand;   // > 0: a candidate residual was not finite
 };
 
-enum LmNext { LM_RUN_A = 0, LM_RUN_B = 1, LM_DONE = 2 };
+enum LmNext { LM_RUN_A = 0, LM_RUN_B = 1, LM_DONE = 2, LM_SOLVE = 3 };
 
 struct LmController {
     rsdsfm_lm_options opt;
@@ -58,9 +78,10 @@ struct LmController {
     double radius, decrease_factor;
     int iteration, step_is_successful, num_consecutive_invalid, reuse_diagonal;
     int phase;            // 0: first evaluation pending, 1: evaluation after an accepted step pending,
-                          // 2: re-elimination at unchanged x (new radius) pending
+                          // 2: same point, new radius
     double x_cost, gmax, x_norm, cand_cost, rho;
-    int accepted_last;    // set by after_B: the candidate became x (caller swaps depth buffers)
+    int accepted_last;    // set by on_candidate: the candidate became x (depth buffers swap)
+    EvalSums ev;          // sums of the last evaluation pass (kept for re-solves at a new radius)
     // results
     int termination, reason, num_successful, num_unsuccessful;
     double initial_cost;
@@ -68,12 +89,15 @@ struct LmController {
     RS_HD void init(const rsdsfm_lm_options &o, int nf_, const double *f0)
     {
         opt = o; nf = nf_;
-        for (int j = 0; j < kMaxNF; ++j) { f[j] = j < nf ? f0[j] : 0.0; f_cand[j] = f[j]; scale_f[j] = 1.0; delta_f[j] = 0.0; diag_f[j] = 0.0; }
+        for (int j = 0; j < kMaxNF; ++j) { f[j] = (j < nf && f0) ? f0[j] : 0.0; f_cand[j] = f[j]; scale_f[j] = 1.0; delta_f[j] = 0.0; diag_f[j] = 0.0; }
         radius = o.initial_trust_region_radius; decrease_factor = 2.0;
         iteration = 0; step_is_successful = 0; num_consecutive_invalid = 0; reuse_diagonal = 0;
         phase = 0; x_cost = 0.0; gmax = 0.0; x_norm = 0.0; cand_cost = 0.0; rho = 0.0; accepted_last = 0;
         termination = RSDSFM_NO_CONVERGENCE; reason = RSDSFM_REASON_NONE; num_successful = 0; num_unsuccessful = 0;
         initial_cost = 0.0;
+        ev.cost = ev.sumsq_d = ev.gmax_e = ev.bad = 0.0;
+        for (int j = 0; j < kTri; ++j) { ev.G1[j] = 0.0; ev.G2[j] = 0.0; }
+        for (int j = 0; j < kMaxNF; ++j) { ev.h1[j] = 0.0; ev.h2[j] = 0.0; }
     }
 
     RS_HD static double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
@@ -112,60 +136,79 @@ struct LmController {
         return true;
     }
 
-    // Consumes the sums of a pass A run at the current x with the current radius.
-    // Returns LM_RUN_B (delta_f holds the motion step to back-substitute), LM_RUN_A (the reduced
-    // solve failed: radius was shrunk, eliminate again) or LM_DONE.
-    RS_HD LmNext after_A(const double *sa, const double *ma)
+    // Consumes the sums of an evaluation pass run at the current x (phase 0 or 1).
+    // Returns LM_SOLVE (call solve_step with the exception sums at `radius`) or LM_DONE.
+    RS_HD LmNext on_eval(const EvalSums &e)
     {
-        const bool bad = ma[SumsA::BAD] > 0.0;
+        const bool bad = e.bad > 0.0;
         if (phase == 0) {
-            // IterationZero: EvaluateGradientAndJacobian + Jacobi scaling fixed here
+            // IterationZero: EvaluateGradientAndJacobian; the Jacobi scaling is fixed here
             if (bad) { initial_cost = 0.0; return finish(RSDSFM_FAILURE, RSDSFM_REASON_EVAL_FAILED); }
-            for (int j = 0; j < nf; ++j) scale_f[j] = 1.0 / (1.0 + sqrt(sa[SumsA::CSF + j]));
-            x_cost = sa[SumsA::COST];
+            for (int j = 0; j < nf; ++j) {
+                const int t = tri_index(nf, j, j);
+                scale_f[j] = 1.0 / (1.0 + sqrt(e.G1[t] + e.G2[t]));
+            }
+            x_cost = e.cost;
             initial_cost = x_cost;
-        } else if (phase == 1) {
+        } else {
             // HandleSuccessfulStep: evaluation at the new x
             if (bad) return finish(RSDSFM_FAILURE, RSDSFM_REASON_EVAL_FAILED);
-            x_cost = sa[SumsA::COST];
+            x_cost = e.cost;
             step_is_successful = 1;
         }
-        if (phase == 0 || phase == 1) {
-            double g = ma[SumsA::GMAX_E], xs = sa[SumsA::SUMSQ_D];
-            for (int j = 0; j < nf; ++j) {
-                // Ceres: |x - Plus(x, -g)|_inf
-                double proj = f[j] + (-sa[SumsA::GF + j]);
-                g = fmax(g, fabs(f[j] - proj));
-                xs += f[j] * f[j];
-            }
-            gmax = g;
-            x_norm = sqrt(xs);
-            // FinalizeIterationAndCheckIfMinimizerCanContinue
-            if (iteration > 0) { if (step_is_successful) num_successful++; else num_unsuccessful++; }
-        } else {
-            if (iteration > 0) num_unsuccessful++;
+        ev = e;
+        double g = e.gmax_e, xs = e.sumsq_d;
+        for (int j = 0; j < nf; ++j) {
+            // Ceres: |x - Plus(x, -g)|_inf with g = F^T r = h1 + h2
+            const double proj = f[j] + (-(e.h1[j] + e.h2[j]));
+            g = fmax(g, fabs(f[j] - proj));
+            xs += f[j] * f[j];
         }
+        gmax = g;
+        x_norm = sqrt(xs);
+        return begin_iteration();
+    }
+
+    // FinalizeIterationAndCheckIfMinimizerCanContinue + start of the next iteration.
+    RS_HD LmNext begin_iteration()
+    {
+        if (iteration > 0) { if (step_is_successful) num_successful++; else num_unsuccessful++; }
         if (iteration >= opt.max_num_iterations) return finish(RSDSFM_NO_CONVERGENCE, RSDSFM_REASON_MAX_ITER);
         if (step_is_successful && gmax <= opt.gradient_tolerance) return finish(RSDSFM_CONVERGENCE, RSDSFM_REASON_GRADIENT_TOL);
         if (radius <= opt.min_trust_region_radius) return finish(RSDSFM_CONVERGENCE, RSDSFM_REASON_MIN_RADIUS);
         iteration++;
         step_is_successful = 0;
         accepted_last = 0;
+        return LM_SOLVE;
+    }
 
-        // LevenbergMarquardtStrategy::ComputeStep on the Schur-reduced system
+    // LevenbergMarquardtStrategy::ComputeStep on the Schur-reduced system at the current radius.
+    // exc: clamped-pixel correction evaluated at this radius (may be NULL when there is none).
+    // Returns LM_RUN_B (delta_f = motion step to back-substitute), LM_SOLVE (the solve failed, the
+    // radius was shrunk: call again with the exception sums at the new radius) or LM_DONE.
+    RS_HD LmNext solve_step(const ExcSums *exc)
+    {
         bool ok = true;
         if (nf > 0) {
             if (!reuse_diagonal)
-                for (int j = 0; j < nf; ++j)
-                    diag_f[j] = clampd(sa[SumsA::CSF + j] * scale_f[j] * scale_f[j], opt.min_lm_diagonal, opt.max_lm_diagonal);
+                for (int j = 0; j < nf; ++j) {
+                    const int t = tri_index(nf, j, j);
+                    diag_f[j] = clampd((ev.G1[t] + ev.G2[t]) * scale_f[j] * scale_f[j], opt.min_lm_diagonal, opt.max_lm_diagonal);
+                }
+            const double eps = 1.0 / (radius + 1.0);
             double lhs[kMaxNF * kMaxNF], rhs[kMaxNF], y[kMaxNF];
             for (int i = 0; i < nf; ++i) {
-                rhs[i] = sa[SumsA::RHS + i] * scale_f[i];
+                double rv = ev.h1[i] + ev.h2[i] * eps;
+                if (exc) rv -= exc->rhs[i];
+                rhs[i] = rv * scale_f[i];
                 for (int j = i; j < nf; ++j) {
-                    double vv = sa[SumsA::S + tri_index(nf, i, j)] * scale_f[i] * scale_f[j];
-                    lhs[i * nf + j] = vv; lhs[j * nf + i] = vv;
+                    const int t = tri_index(nf, i, j);
+                    double sv = ev.G1[t] + ev.G2[t] * eps;
+                    if (exc) sv -= exc->S[t];
+                    sv *= scale_f[i] * scale_f[j];
+                    lhs[i * nf + j] = sv; lhs[j * nf + i] = sv;
                 }
-                double Df = sqrt(diag_f[i] / radius);
+                const double Df = sqrt(diag_f[i] / radius);
                 lhs[i * nf + i] += Df * Df;
             }
             ok = cholesky_solve(lhs, nf, rhs, y);
@@ -191,23 +234,24 @@ struct LmController {
         decrease_factor *= 2.0;
         reuse_diagonal = 1;
         phase = 2;
-        return LM_RUN_A;
+        return begin_iteration();
     }
 
-    // Consumes the sums of a pass B (candidate point).  Returns LM_RUN_A or LM_DONE.
-    RS_HD LmNext after_B(const double *sb, const double *mb)
+    // Consumes the sums of a candidate pass.  Returns LM_RUN_A (accepted: evaluate at the new x),
+    // LM_SOLVE (rejected / invalid: same x, smaller radius) or LM_DONE.
+    RS_HD LmNext on_candidate(const CandSums &c)
     {
-        const double model_cost_change = -sb[SumsB::MCC];
-        const bool step_finite = !(mb[SumsB::BAD_STEP] > 0.0);
+        const double model_cost_change = -c.mcc;
+        const bool step_finite = !(c.bad_step > 0.0);
         if (!(step_finite && model_cost_change > 0.0)) return invalid_step();
         num_consecutive_invalid = 0;
-        double step_sq = sb[SumsB::STEP_SQ];
+        double step_sq = c.step_sq;
         for (int j = 0; j < nf; ++j) {
             f_cand[j] = f[j] + delta_f[j];
-            double dd = f[j] - f_cand[j];
+            const double dd = f[j] - f_cand[j];
             step_sq += dd * dd;
         }
-        cand_cost = (mb[SumsB::BAD_CAND] > 0.0) ? DBL_MAX : sb[SumsB::CAND_COST];
+        cand_cost = (c.bad_cand > 0.0) ? DBL_MAX : c.cand_cost;
         // ParameterToleranceReached (tested on the candidate, which is then discarded)
         const double step_norm = sqrt(step_sq);
         if (step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance))
@@ -227,13 +271,13 @@ struct LmController {
             decrease_factor = 2.0;
             reuse_diagonal = 0;
             phase = 1;
-        } else {
-            radius = radius / decrease_factor;
-            decrease_factor *= 2.0;
-            reuse_diagonal = 1;
-            phase = 2;
+            return LM_RUN_A;
         }
-        return LM_RUN_A;
+        radius = radius / decrease_factor;
+        decrease_factor *= 2.0;
+        reuse_diagonal = 1;
+        phase = 2;
+        return begin_iteration();
     }
 
     RS_HD void fill_summary(rsdsfm_lm_summary *s) const

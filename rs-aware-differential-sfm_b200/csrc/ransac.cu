@@ -267,6 +267,7 @@ int ransac_score_device(rsdsfm_ctx *ctx, const double *q, const double *u, const
     double *partials = (double *)ctx->partials.p, *sums = (double *)ctx->sums.p;
 
     std::vector<LmController> ctl((size_t)H);
+    std::vector<LmNext> pend((size_t)H, LM_RUN_A);
     memset(hh, 0, sizeof(HypDev) * (size_t)gy * kHG);
     int n_active = 0;
     for (int h = 0; h < H; ++h) {
@@ -296,15 +297,18 @@ int ransac_score_device(rsdsfm_ctx *ctx, const double *q, const double *u, const
             if (!hh[h].active) continue;
             const double *row = hs + (size_t)(h / kHG) * widthP;
             const double *ss = row + (h % kHG) * RS_NS, *mm = row + kHG * RS_NS + (h % kHG) * RM_NM;
-            double sa[SumsA::NS], ma[SumsA::NM], sb[SumsB::NS], mb[SumsB::NM];
-            for (int j = 0; j < SumsA::NS; ++j) sa[j] = 0.0;
-            sa[SumsA::COST] = ss[RS_COST]; sa[SumsA::SUMSQ_D] = ss[RS_SUMSQ_D];
-            ma[SumsA::GMAX_E] = mm[RM_GMAX_E]; ma[SumsA::BAD] = mm[RM_BAD];
-            sb[SumsB::MCC] = ss[RS_MCC]; sb[SumsB::STEP_SQ] = ss[RS_STEP_SQ]; sb[SumsB::CAND_COST] = ss[RS_CAND_COST];
-            mb[SumsB::BAD_STEP] = mm[RM_BAD_STEP]; mb[SumsB::BAD_CAND] = mm[RM_BAD_CAND];
+            EvalSums e;
+            memset(&e, 0, sizeof e);
+            e.cost = ss[RS_COST]; e.sumsq_d = ss[RS_SUMSQ_D]; e.gmax_e = mm[RM_GMAX_E]; e.bad = mm[RM_BAD];
+            CandSums c;
+            c.mcc = ss[RS_MCC]; c.step_sq = ss[RS_STEP_SQ]; c.cand_cost = ss[RS_CAND_COST];
+            c.bad_step = mm[RM_BAD_STEP]; c.bad_cand = mm[RM_BAD_CAND];
             const double used_radius = hh[h].radius;
-            LmNext next = ctl[h].after_A(sa, ma);
-            if (next == LM_RUN_B) next = ctl[h].after_B(sb, mb);
+            LmNext next = pend[h];
+            if (next == LM_RUN_A) next = ctl[h].on_eval(e);               // evaluation at a new point
+            while (next == LM_SOLVE) next = ctl[h].solve_step(nullptr);   // no f-blocks: nothing to solve
+            if (next == LM_RUN_B) next = ctl[h].on_candidate(c);
+            pend[h] = next;
             if (next == LM_DONE) {
                 hh[h].active = 0;
                 hh[h].failed = (ctl[h].termination == RSDSFM_FAILURE) ? 1 : 0;

@@ -16,6 +16,23 @@
 
 namespace rsdsfm {
 
+// out[j] = reduce over CTA rows b of partials[b*(ns+nm)+j]; sums in ascending row order
+__global__ void k_final_reduce(const double *__restrict__ partials, int nblocks, int ns, int nm, double *out)
+{
+    const int j = threadIdx.x;
+    if (j >= ns + nm) return;
+    double v = partials[j];
+    if (j < ns) for (int b = 1; b < nblocks; ++b) v += partials[(size_t)b * (ns + nm) + j];
+    else        for (int b = 1; b < nblocks; ++b) v = fmax(v, partials[(size_t)b * (ns + nm) + j]);
+    out[j] = v;
+}
+
+void launch_final_reduce(rsdsfm_ctx *ctx, const double *partials, int nblocks, int ns, int nm, double *out)
+{
+    k_final_reduce<<<1, 64, 0, ctx->stream>>>(partials, nblocks, ns, nm, out);
+    ctx->launches++;
+}
+
 // ---------------------------------------------------------------- a10: sign fix + depth raster
 // sums[0] = sum z, maxima: [0] = max z, [1] = max(-z)  (=> min z)
 __global__ void __launch_bounds__(kThreads) k_glue_reduce(const double *__restrict__ z, int zs, int m, double *partials)

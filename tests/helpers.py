@@ -9,11 +9,12 @@ def small_K(scale):
 
 
 def make_case(O, synth, rows, cols, K4, k=0.0, const_acc=False, seed=1, noise=0.1, outliers=0.05, zero_frac=0.0,
-              H=12, tol=0.01, gamma=0.95, flow_f32=False, sample_seed=3):
+              H=12, tol=0.01, gamma=0.95, flow_f32=False, sample_seed=3, v=(0.30, 0.05, 0.02),
+              w=(0.002, -0.004, 0.0087)):
     """Synthetic pair -> flatten -> alpha -> RANSAC (oracle) -> consensus set.  Everything a
     refinement / rectification parity test needs, computed by the CPU oracle."""
     P = synth.make_pair(rows, cols, K4, gamma=gamma, seed=seed, k=k, noise_sigma_px=noise, outlier_frac=outliers,
-                        zero_flow_frac=zero_frac, flow_f32=flow_f32)
+                        zero_flow_frac=zero_frac, flow_f32=flow_f32, v=v, w=w)
     n, coord, flow, cpx, fpx = O.flatten(P["flow_img"], K4, gamma)
     alpha = O.get_alpha(fpx, n, rows, gamma)
     alpha_k = O.get_alpha_k(cpx, fpx, n, rows, gamma)

@@ -138,6 +138,30 @@ def test_refine_matches_oracle(ctx, oracle, case_cv, case_ca, which, pairing):
     _depth_close(z, z_o)
 
 
+@pytest.mark.parametrize("const_acc", [False, True])
+def test_refine_focus_of_expansion_inside_image(ctx, oracle, synth, const_acc):
+    """Forward motion: the focus of expansion lies inside the image, so a few pixels have a
+    vanishing depth column and hit Ceres' min_lm_diagonal clamp (the solver's exception list)."""
+    c = helpers.make_case(oracle, synth, 240, 320, (1500.0, 1500.0, 160.0, 120.0), k=0.4 if const_acc else 0.0,
+                          const_acc=const_acc, H=10, seed=9, v=(0.02, 0.01, 0.30), w=(0.001, 0.002, -0.003), noise=0.05,
+                          outliers=0.0, tol=0.05)
+    R = c["ransac"]
+    assert c["m"] == c["n"]
+    # make sure the clamp is really exercised by this case: |e| s_e < 1e-3 for some inlier
+    x = c["inliers3"][0::3]; y = c["inliers3"][1::3]
+    beta = (2 / (2 + R["k"])) * (c["alpha_in"] + R["k"] * c["alpha_k_in"])
+    e = np.hypot(beta * (R["v"][0] - x * R["v"][2]), beta * (R["v"][1] - y * R["v"][2]))
+    assert ((e / (1 + e)) ** 2 < 1e-6).sum() > 0
+    v_o, w_o, k_o, z_o, s_o = oracle.nonlinear_refinement(c["flow"], c["inliers3"], c["alpha_in"], c["alpha_k_in"], c["m"],
+                                                          R["v"], R["w"], R["k"], const_acc)
+    v, w, k, z, s = ctx.refine(c["flow"], c["inliers3"], c["alpha_in"], c["alpha_k_in"], c["m"], R["v"], R["w"], R["k"], const_acc)
+    assert s["termination"] == s_o["termination"] and s["iterations"] == s_o["iterations"], (s, s_o)
+    _motion_close(v, v_o, "v")
+    _motion_close(w, w_o, "w")
+    assert abs(k - k_o) <= MOTION_RTOL * max(abs(k_o), 1.0)
+    _depth_close(z, z_o)
+
+
 def test_refine_nonfinite_input_fails_like_ceres(ctx, oracle, case_cv):
     c = case_cv
     R = c["ransac"]
