@@ -242,6 +242,10 @@ def run_ours(args):
                        "lm_iterations_per_pair": its / args.steps, "sharding": "independent frame pairs per rank, no collective",
                        "l2": "inputs larger than L2: %d distinct pairs cycled (~%.0f MB device inputs each)" % (N_PAIRS, h2d / 1e6)},
             "ms_per_lm_iteration": lm_ms,
+            "lm_phase_breakdown_us": {
+                "pass_a": {k: 1e3 * prof[k] / max(prof["pass_a_launches"], 1) for k in ("a_loop_ms", "a_reduce_ms", "a_ctl_ms")},
+                "pass_b": {k: 1e3 * prof[k] / max(prof["pass_b_launches"], 1) for k in ("b_loop_ms", "b_reduce_ms", "b_ctl_ms")},
+                "kernel_ms_per_solve": prof["kernel_ms"] / max(prof["kernel_launches"], 1)},
             "clocks": clocks,
             "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},

@@ -17,7 +17,7 @@ DEPTH_COLMAJOR, DEPTH_ROWMAJOR = 0, 1
 
 EXPORTS = [
     "rsdsfm_version", "rsdsfm_lm_default_options", "rsdsfm_create", "rsdsfm_destroy", "rsdsfm_last_error",
-    "rsdsfm_synchronize", "rsdsfm_launch_count", "rsdsfm_profile_enable", "rsdsfm_profile_read", "rsdsfm_flatten", "rsdsfm_alpha", "rsdsfm_solve9",
+    "rsdsfm_synchronize", "rsdsfm_launch_count", "rsdsfm_profile_enable", "rsdsfm_profile_read", "rsdsfm_profile_detail", "rsdsfm_flatten", "rsdsfm_alpha", "rsdsfm_solve9",
     "rsdsfm_ransac_score", "rsdsfm_ransac", "rsdsfm_gather_inliers", "rsdsfm_estimate_inverse_depths",
     "rsdsfm_refine", "rsdsfm_depth_glue", "rsdsfm_set_relative_pose", "rsdsfm_backproject", "rsdsfm_fill_cracks",
     "rsdsfm_refine_rectify",
@@ -137,8 +137,13 @@ class Context:
     def profile_read(self):
         out = np.zeros(8)
         self._ck(self.lib.rsdsfm_profile_read(self.h, _ptr(out)))
+        det = np.zeros(6)
+        self._ck(self.lib.rsdsfm_profile_detail(self.h, _ptr(det)))
         return dict(pass_a_ms=out[0], pass_a_launches=int(out[1]), pass_a_blocks=out[2],
-                    pass_b_ms=out[3], pass_b_launches=int(out[4]), pass_b_blocks=out[5])
+                    pass_b_ms=out[3], pass_b_launches=int(out[4]), pass_b_blocks=out[5],
+                    kernel_ms=out[6], kernel_launches=int(out[7]),
+                    a_loop_ms=det[0], a_reduce_ms=det[1], a_ctl_ms=det[2],
+                    b_loop_ms=det[3], b_reduce_ms=det[4], b_ctl_ms=det[5])
 
     # ---- a2
     def flatten(self, flow_img, K4, gamma, thr=1e-10, out=None):

@@ -107,7 +107,8 @@ void rsdsfm_destroy(rsdsfm_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->partials, &ctx->sums, &ctx->pix, &ctx->dA, &ctx->dB, &ctx->scale_e, &ctx->misc, &ctx->winner,
-                     &ctx->tmp_img, &ctx->depth_rm, &ctx->poses, &ctx->hyp, &ctx->rpart, &ctx->flags, &ctx->scan};
+                     &ctx->tmp_img, &ctx->depth_rm, &ctx->poses, &ctx->hyp, &ctx->rpart, &ctx->flags, &ctx->scan,
+                     &ctx->lm_shared, &ctx->exc};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (auto &b : ctx->stage) if (b.p) cudaFree(b.p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -135,6 +136,7 @@ int rsdsfm_profile_enable(rsdsfm_ctx *ctx, int on)
     if (!ctx) return RSDSFM_ERR_ARG;
     ctx->profile = on != 0;
     for (double &p : ctx->prof) p = 0.0;
+    for (double &p : ctx->prof_detail) p = 0.0;
     return RSDSFM_OK;
 }
 
@@ -142,6 +144,13 @@ int rsdsfm_profile_read(rsdsfm_ctx *ctx, double *out8)
 {
     if (!ctx || !out8) return RSDSFM_ERR_ARG;
     for (int j = 0; j < 8; ++j) out8[j] = ctx->prof[j];
+    return RSDSFM_OK;
+}
+
+int rsdsfm_profile_detail(rsdsfm_ctx *ctx, double *out6)
+{
+    if (!ctx || !out6) return RSDSFM_ERR_ARG;
+    for (int j = 0; j < 6; ++j) out6[j] = ctx->prof_detail[j];
     return RSDSFM_OK;
 }
 

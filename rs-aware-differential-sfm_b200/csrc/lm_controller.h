@@ -53,6 +53,7 @@ struct EvalSums {
     double sumsq_d;    // sum d^2
     double gmax_e;     // max |e^T r|   (gradient of the depth blocks)
     double bad;        // > 0: a residual / Jacobian entry was not finite
+    double ee_max;     // max e^Te (first evaluation: bounds the depth-column Jacobi scales from below)
     double G1[kTri], G2[kTri], h1[kMaxNF], h2[kMaxNF];
 };
 // Radius-dependent correction of the clamped pixels: sum q fe fe^T and sum q fe (e^T r).
@@ -82,6 +83,7 @@ struct LmController {
     double x_cost, gmax, x_norm, cand_cost, rho;
     int accepted_last;    // set by on_candidate: the candidate became x (depth buffers swap)
     EvalSums ev;          // sums of the last evaluation pass (kept for re-solves at a new radius)
+    double ee_fast_min;   // e^Te >= this  =>  the pixel's LM diagonal is certainly not clamped from below
     // results
     int termination, reason, num_successful, num_unsuccessful;
     double initial_cost;
@@ -95,7 +97,8 @@ struct LmController {
         phase = 0; x_cost = 0.0; gmax = 0.0; x_norm = 0.0; cand_cost = 0.0; rho = 0.0; accepted_last = 0;
         termination = RSDSFM_NO_CONVERGENCE; reason = RSDSFM_REASON_NONE; num_successful = 0; num_unsuccessful = 0;
         initial_cost = 0.0;
-        ev.cost = ev.sumsq_d = ev.gmax_e = ev.bad = 0.0;
+        ev.cost = ev.sumsq_d = ev.gmax_e = ev.bad = ev.ee_max = 0.0;
+        ee_fast_min = 0.0;
         for (int j = 0; j < kTri; ++j) { ev.G1[j] = 0.0; ev.G2[j] = 0.0; }
         for (int j = 0; j < kMaxNF; ++j) { ev.h1[j] = 0.0; ev.h2[j] = 0.0; }
     }
@@ -104,42 +107,18 @@ struct LmController {
 
     RS_HD LmNext finish(int term, int why) { termination = term; reason = why; return LM_DONE; }
 
-    // Dense Cholesky (LL^T) of the nf x nf reduced system, Eigen::LLT semantics: fails when a
-    // pivot is not positive (or NaN).  a: full row-major nf x nf.
-    RS_HD static bool cholesky_solve(const double *a, int n, const double *b, double *x)
-    {
-        double l[kMaxNF * kMaxNF];
-        for (int i = 0; i < n * n; ++i) l[i] = 0.0;
-        for (int j = 0; j < n; ++j) {
-            double d = a[j * n + j];
-            for (int k = 0; k < j; ++k) d -= l[j * n + k] * l[j * n + k];
-            if (!(d > 0.0)) return false;
-            d = sqrt(d);
-            l[j * n + j] = d;
-            for (int i = j + 1; i < n; ++i) {
-                double s = a[i * n + j];
-                for (int k = 0; k < j; ++k) s -= l[i * n + k] * l[j * n + k];
-                l[i * n + j] = s / d;
-            }
-        }
-        double y[kMaxNF];
-        for (int i = 0; i < n; ++i) {
-            double s = b[i];
-            for (int k = 0; k < i; ++k) s -= l[i * n + k] * y[k];
-            y[i] = s / l[i * n + i];
-        }
-        for (int i = n - 1; i >= 0; --i) {
-            double s = y[i];
-            for (int k = i + 1; k < n; ++k) s -= l[k * n + i] * x[k];
-            x[i] = s / l[i * n + i];
-        }
-        return true;
-    }
-
     // Consumes the sums of an evaluation pass run at the current x (phase 0 or 1).
     // Returns LM_SOLVE (call solve_step with the exception sums at `radius`) or LM_DONE.
-    RS_HD LmNext on_eval(const EvalSums &e)
+    RS_HD LmNext on_eval(const EvalSums &e_in)
     {
+        ev = e_in;
+        return on_eval_stored();
+    }
+
+    // Same, with the sums already written into this->ev (the device controller fills it in place).
+    RS_HD LmNext on_eval_stored()
+    {
+        const EvalSums &e = ev;
         const bool bad = e.bad > 0.0;
         if (phase == 0) {
             // IterationZero: EvaluateGradientAndJacobian; the Jacobi scaling is fixed here
@@ -150,13 +129,15 @@ struct LmController {
             }
             x_cost = e.cost;
             initial_cost = x_cost;
+            // s_e = 1/(1+|e(x0)|) >= 1/(1+sqrt(ee_max)):  e^Te >= min_diag (1+sqrt(ee_max))^2  =>  s_e^2 e^Te >= min_diag
+            const double t = 1.0 + sqrt(e.ee_max);
+            ee_fast_min = opt.min_lm_diagonal * t * t;
         } else {
             // HandleSuccessfulStep: evaluation at the new x
             if (bad) return finish(RSDSFM_FAILURE, RSDSFM_REASON_EVAL_FAILED);
             x_cost = e.cost;
             step_is_successful = 1;
         }
-        ev = e;
         double g = e.gmax_e, xs = e.sumsq_d;
         for (int j = 0; j < nf; ++j) {
             // Ceres: |x - Plus(x, -g)|_inf with g = F^T r = h1 + h2
@@ -189,37 +170,86 @@ struct LmController {
     RS_HD LmNext solve_step(const ExcSums *exc)
     {
         bool ok = true;
-        if (nf > 0) {
-            if (!reuse_diagonal)
-                for (int j = 0; j < nf; ++j) {
-                    const int t = tri_index(nf, j, j);
-                    diag_f[j] = clampd((ev.G1[t] + ev.G2[t]) * scale_f[j] * scale_f[j], opt.min_lm_diagonal, opt.max_lm_diagonal);
-                }
-            const double eps = 1.0 / (radius + 1.0);
-            double lhs[kMaxNF * kMaxNF], rhs[kMaxNF], y[kMaxNF];
-            for (int i = 0; i < nf; ++i) {
-                double rv = ev.h1[i] + ev.h2[i] * eps;
-                if (exc) rv -= exc->rhs[i];
-                rhs[i] = rv * scale_f[i];
-                for (int j = i; j < nf; ++j) {
-                    const int t = tri_index(nf, i, j);
-                    double sv = ev.G1[t] + ev.G2[t] * eps;
-                    if (exc) sv -= exc->S[t];
-                    sv *= scale_f[i] * scale_f[j];
-                    lhs[i * nf + j] = sv; lhs[j * nf + i] = sv;
-                }
-                const double Df = sqrt(diag_f[i] / radius);
-                lhs[i * nf + i] += Df * Df;
-            }
-            ok = cholesky_solve(lhs, nf, rhs, y);
-            for (int j = 0; j < nf && ok; ++j) {
-                if (!isfinite(y[j])) ok = false;
-                delta_f[j] = -y[j] * scale_f[j];     // step = -y ; delta = step o scale
-            }
-        }
+        if (nf == 6) ok = solve_fixed<6>(exc);
+        else if (nf == 7) ok = solve_fixed<7>(exc);
         reuse_diagonal = 1;
         if (!ok) return invalid_step();
         return LM_RUN_B;
+    }
+
+    // Compose S(radius), add the LM diagonal, Cholesky-factorise (Eigen::LLT semantics: fails on a
+    // non-positive or NaN pivot) and solve.  N is a compile-time constant so that every loop
+    // unrolls and the N x N system lives in registers (this runs on ONE thread of the last CTA,
+    // with the whole grid waiting for it).
+    template <int N>
+    RS_HD bool solve_fixed(const ExcSums *exc)
+    {
+        double sc[N], l[N][N], y[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) sc[j] = scale_f[j];
+        if (!reuse_diagonal) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const int t = j * N - (j * (j - 1)) / 2;
+                diag_f[j] = clampd((ev.G1[t] + ev.G2[t]) * sc[j] * sc[j], opt.min_lm_diagonal, opt.max_lm_diagonal);
+            }
+        }
+        const double eps = 1.0 / (radius + 1.0);
+        // lower triangle of the scaled, damped system (l[i][j], i >= j), then in-place LL^T
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double rv = ev.h1[i] + ev.h2[i] * eps;
+            if (exc) rv -= exc->rhs[i];
+            y[i] = rv * sc[i];
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                const int t = j * N - (j * (j - 1)) / 2 + (i - j);      // tri_index(N, j, i)
+                double sv = ev.G1[t] + ev.G2[t] * eps;
+                if (exc) sv -= exc->S[t];
+                l[i][j] = sv * (sc[i] * sc[j]);
+            }
+            const double Df = sqrt(diag_f[i] / radius);
+            l[i][i] += Df * Df;
+        }
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double d = l[j][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) d -= l[j][k] * l[j][k];
+            if (!(d > 0.0)) ok = false;
+            d = sqrt(d);
+            l[j][j] = d;
+            const double inv = 1.0 / d;
+#pragma unroll
+            for (int i = j + 1; i < N; ++i) {
+                double s = l[i][j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) s -= l[i][k] * l[j][k];
+                l[i][j] = s * inv;
+            }
+        }
+        if (!ok) return false;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double s = y[i];
+#pragma unroll
+            for (int k = 0; k < i; ++k) s -= l[i][k] * y[k];
+            y[i] = s / l[i][i];
+        }
+#pragma unroll
+        for (int i = N - 1; i >= 0; --i) {
+            double s = y[i];
+#pragma unroll
+            for (int k = i + 1; k < N; ++k) s -= l[k][i] * y[k];
+            y[i] = s / l[i][i];
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            if (!isfinite(y[j])) ok = false;
+            delta_f[j] = -y[j] * sc[j];          // step = -y ; delta = step o scale
+        }
+        return ok;
     }
 
     RS_HD LmNext invalid_step()

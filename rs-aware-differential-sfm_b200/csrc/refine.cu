@@ -3,10 +3,12 @@
 //   a9  nonlinear_refinement::nonLinearRefinement    (nonlinearRefinement.cc:183-252)  NF = 6 | 7
 //
 // ONE persistent cooperative kernel runs the whole solve: one CTA per SM stays resident and
-// loops over LM phases; a phase is a coalesced pass over the residual blocks followed by a grid
-// reduction (registers -> shared-memory transpose -> warp shuffles -> one row per CTA -> the last
-// CTA to arrive sums the rows in fixed order) and the O(1) controller (lm_controller.h: Ceres 1.14
-// trust-region semantics, 7x7 Cholesky) executed by that last CTA, which then releases the grid.
+// loops over LM phases.  A phase is a pass over the residual blocks, streamed through a ring of
+// shared-memory stages by TMA bulk copies (cp.async.bulk + mbarrier complete_tx; one elected
+// thread issues, kStages tiles of 256 blocks in flight per SM), followed by a grid reduction
+// (registers -> shared-memory transpose -> warp shuffles -> one row per CTA -> the last CTA to
+// arrive sums the rows in a fixed order) and the O(1) controller (lm_controller.h: Ceres 1.14
+// trust-region semantics, 7x7 Cholesky) run by that last CTA, which then releases the grid.
 // No host round trip per iteration; the host launches once and reads one summary back.
 //
 //   pass A (evaluation at x): residual + analytic Jacobian, closed-form 1x1 Schur elimination of
@@ -15,28 +17,33 @@
 //   pass B (candidate): depth back-substitution, candidate point + cost, model cost change, |step|^2.
 //   A rejected step re-solves from the stored factors: it costs a pass B only.
 //
-// Data layout in HBM (structure of arrays, one entry per residual block, 16-byte vector loads):
+// Data layout in HBM (structure of arrays, one entry per residual block, 16-byte aligned):
 //   xy[m] double2 (x, y) | uu[m] double2 (ux, uy; Q1 pairing applied once by the gather kernel)
 //   aa[m] double2 (alpha, alpha_k) | d[2][m] inverse depth ping-pong (x / candidate)
-//   se[m] Jacobi scale of the depth column, fixed at iteration 0 (only used for the clamp test)
-// Algorithmic bytes: pass A 24 B, pass B 32 B per residual block.
-#include <cooperative_groups.h>
-
+// The Jacobi scale of a depth column (fixed at iteration 0 by Ceres) only matters for the
+// min/max_lm_diagonal clamp; it is bounded from below by a global quantity, so the passes test
+// e^Te against that bound and only the handful of pixels below it (focus of expansion) recompute
+// their scale from the start point.  Nothing per-pixel besides the arrays above is stored.
+// Traffic per residual block: pass A reads 56 B, pass B reads 56 B and writes 8 B
+// (algorithmic minimum, SURVEY.md 8d: 24 B / 32 B -- x, y, alpha, alpha_k are inputs of the C ABI).
 #include "common.cuh"
 #include "lm_controller.h"
 #include "rs_math.cuh"
 
 namespace rsdsfm {
 
+constexpr int kTile = 512;                      // residual blocks per tile (two per thread)
+
+// Tile-blocked SoA: tile t holds xy[kTile], uu[kTile], aa[kTile] (double2 each) contiguously, so a
+// whole tile arrives with ONE TMA bulk copy (the per-copy issue cost, not bandwidth, limits small
+// copies: measured 6 TB/s with 14 KB copies vs 16 TB/s from L2 / 7 TB/s from HBM with 32 KB copies).
 struct RefineData {
-    const double2 *xy;
-    const double2 *uu;
-    const double2 *aa;
-    double *se;
+    const double2 *blk;      // [num_tiles][3][kTile]
     int m;
 };
+__host__ __device__ inline size_t blk_index(int i, int field) { return (size_t)(i / kTile) * (3 * kTile) + (size_t)field * kTile + (size_t)(i % kTile); }
 
-struct ExcEntry {            // a pixel whose LM diagonal is clamped (or whose e-column is degenerate)
+struct ExcEntry {            // a pixel whose LM diagonal is (possibly) clamped, or whose e-column is degenerate
     double ees, se2, er;     // s_e^2 e^Te, s_e^2, e^T r
     double fe[kMaxNF];       // F^T e
 };
@@ -47,15 +54,17 @@ struct Bcast {
     Motion mot, cand;
     double delta_f[kMaxNF];
     double radius;
+    double ee_fast_min;
 };
 
 // Device-resident control block of one solve.
 struct LmShared {
     LmController ctl;
-    Motion base;             // values of the motion parameters that are not free
+    Motion base;             // start values of the motion (non-free parameters keep them)
     Bcast bc;
-    // ---- per-phase device timing (globaltimer ns): [0] pass A total, [1] phases, [2] pass B total, [3] phases
-    unsigned long long t_phase[4];
+    // device timing (globaltimer ns): [0] pass A total, [1] phases, [2] pass B total, [3] phases,
+    // [4..6] pass A pixel loop / CTA reduce / controller, [7..9] same for pass B
+    unsigned long long t_phase[12];
     // ---- grid synchronisation
     unsigned int arrive, generation;
     unsigned int n_exc, exc_overflow;
@@ -69,17 +78,16 @@ struct LmShared {
 // ------------------------------------------------------------------------------------------
 __global__ void k_refine_gather(const double *__restrict__ flow, const double *__restrict__ inliers3,
                                 const double *__restrict__ alpha, const double *__restrict__ alpha_k,
-                                const int32_t *__restrict__ flow_index, int m, double2 *xy, double2 *uu, double2 *aa,
-                                double *d0, LmShared *sh)
+                                const int32_t *__restrict__ flow_index, int m, double2 *blk, double *d0, LmShared *sh)
 {
     int bad = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
         const double x = inliers3[3 * (size_t)i], y = inliers3[3 * (size_t)i + 1], z = inliers3[3 * (size_t)i + 2];
         const int fi = flow_index ? flow_index[i] : i;
         const double2 u = reinterpret_cast<const double2 *>(flow)[fi];
-        xy[i] = make_double2(x, y);
-        uu[i] = u;
-        aa[i] = make_double2(alpha[i], alpha_k[i]);
+        blk[blk_index(i, 0)] = make_double2(x, y);
+        blk[blk_index(i, 1)] = u;
+        blk[blk_index(i, 2)] = make_double2(alpha[i], alpha_k[i]);
         const double d = 1.0 / z;                              // nonlinearRefinement.cc:213
         d0[i] = d;
         if (!isfinite(d)) bad = 1;
@@ -88,12 +96,16 @@ __global__ void k_refine_gather(const double *__restrict__ flow, const double *_
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(&sh->nonfinite_input, 1);
 }
 
-// a8 variant: coordinates / flow already interleaved pairs, depth starts at 1.0 (:140)
-__global__ void k_depth_gather(const double *__restrict__ alpha, const double *__restrict__ alpha_k, int n,
-                               double2 *aa, double *d0)
+// a8 variant: depth starts at 1.0 (:140); coord / flow are copied so the solver's 16-byte
+// alignment requirement never leaks into the C ABI.
+__global__ void k_depth_gather(const double *__restrict__ coord, const double *__restrict__ flow,
+                               const double *__restrict__ alpha, const double *__restrict__ alpha_k, int n, double2 *blk,
+                               double *d0)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        aa[i] = make_double2(alpha[i], alpha_k[i]);
+        blk[blk_index(i, 0)] = make_double2(coord[2 * (size_t)i], coord[2 * (size_t)i + 1]);
+        blk[blk_index(i, 1)] = make_double2(flow[2 * (size_t)i], flow[2 * (size_t)i + 1]);
+        blk[blk_index(i, 2)] = make_double2(alpha[i], alpha_k[i]);
         d0[i] = 1.0;
     }
 }
@@ -111,7 +123,6 @@ __device__ __forceinline__ double fast_rcp(double x)
     r = fma(r, t, r);
     return r;
 }
-
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p)
 {
     unsigned int v;
@@ -128,39 +139,86 @@ __device__ __forceinline__ unsigned long long globaltimer()
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
+// ---- TMA bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    const uint32_t a = smem_u32(bar);
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 
-struct PhaseParams {           // shared-memory copy of the broadcast block (+ options)
+struct PhaseParams {           // shared-memory copy of the broadcast block (+ options, start point)
     int next, which_x, first, pad0;
     Motion mot, cand;
     double delta_f[kMaxNF];
     double radius;
+    double ee_fast_min;
     double min_diag, max_diag;
+    Motion base;
     int error;
 };
-static_assert(offsetof(PhaseParams, radius) == offsetof(Bcast, radius), "PhaseParams must start with Bcast");
+static_assert(offsetof(PhaseParams, ee_fast_min) == offsetof(Bcast, ee_fast_min), "PhaseParams must start with Bcast");
+
+constexpr int kStages = 5;                      // tiles in flight per CTA (5 x 28 KB)
+struct Stage {
+    double2 xy[kTile], uu[kTile], aa[kTile];
+    double d[kTile];
+};
+static_assert(sizeof(Stage) == 28672 && kTile == 2 * kThreads, "stage layout");
+
+struct Loaded {
+    double2 p, u, a;
+    double d;
+};
+
+// ------------------------------------------------------------------------------------------
+// Pass A layout: NS = 2 + 2*TRI + 2*NF sums (cost2, sum d^2, G1, G2, h1, h2), NM = 3 maxima
+// ------------------------------------------------------------------------------------------
+template <int NF>
+struct PassA {
+    static constexpr int TRI = NF * (NF + 1) / 2;
+    static constexpr int oG1 = 2, oG2 = oG1 + TRI, oH1 = oG2 + TRI, oH2 = oH1 + NF;
+    static constexpr int NS = oH2 + NF, NM = 3, NV = NS + NM;
+    static constexpr int iGMAX = NS, iBAD = NS + 1, iEEMAX = NS + 2;
+};
+constexpr int kNB = 5;                          // pass B: 3 sums (mcc, step^2, cost2) + 2 maxima
 
 template <int NF> constexpr int red_rows()
-{   // rows of the shared reduction scratch: pass A values, pass B values (5), exception sums (kTri + kMaxNF)
-    int r = 2 + NF * (NF + 1) + 2 * NF + 2;
-    if (r < 5) r = 5;
+{   // rows of the shared reduction scratch: pass A values, pass B values, exception sums
+    int r = PassA<NF>::NV;
+    if (r < kNB) r = kNB;
     if (NF > 0 && r < kTri + kMaxNF) r = kTri + kMaxNF;
     return r;
 }
 template <int NF> constexpr int kRedRows = red_rows<NF>();
-
-struct Loaded {
-    double2 p, u, a;
-    double d, se;
-};
-__device__ __forceinline__ Loaded load_px(const RefineData &D, const double *__restrict__ d, int i, bool want_se)
+template <int NF> constexpr size_t smem_bytes()
 {
-    Loaded L;
-    L.p = D.xy[i]; L.u = D.uu[i]; L.a = D.aa[i]; L.d = d[i];
-    L.se = want_se ? D.se[i] : 1.0;
-    return L;
+    size_t a = sizeof(double) * (size_t)kRedRows<NF> * kThreads, b = sizeof(Stage) * (size_t)kStages;
+    return a > b ? a : b;
 }
 
-// NV values per thread (first NS sums, then NM maxima) -> one row of NV doubles for this CTA.
+// NV values per thread (first NS sums, then NM maxima, all maxima >= 0) -> one row of NV doubles.
 // red: shared scratch of NV * kThreads doubles.  Fixed order => bit-reproducible.
 template <int NS, int NM>
 __device__ __forceinline__ void cta_reduce(const double (&v)[NS + NM], double *red, double *row)
@@ -189,17 +247,6 @@ __device__ __forceinline__ void cta_reduce(const double (&v)[NS + NM], double *r
     __syncthreads();
 }
 
-// ------------------------------------------------------------------------------------------
-// Pass A body: NS = 2 + 2*TRI + 2*NF sums (cost2, sum d^2, G1, G2, h1, h2), NM = 2 maxima
-// ------------------------------------------------------------------------------------------
-template <int NF>
-struct PassA {
-    static constexpr int TRI = NF * (NF + 1) / 2;
-    static constexpr int oG1 = 2, oG2 = oG1 + TRI, oH1 = oG2 + TRI, oH2 = oH1 + NF;
-    static constexpr int NS = oH2 + NF, NM = 2, NV = NS + NM;
-    static constexpr int iGMAX = NS, iBAD = NS + 1;
-};
-
 // f = F^T (pi0, pi1)  with  F = -beta [d A | B | (dbeta/beta) p]  (see rs_math.cuh)
 template <int NF>
 __device__ __forceinline__ void ft_times(double beta, double dbeta, double d, double x, double y, double xy, double xx1,
@@ -215,149 +262,225 @@ __device__ __forceinline__ void ft_times(double beta, double dbeta, double d, do
     if (NF == 7) f[6] = -dbeta * fma(p0, pi0, p1 * pi1);
 }
 
-template <int NF>
-__device__ __forceinline__ void pass_a_pixel(const Loaded &L, const PhaseParams &P, double c2, double (&acc)[PassA<NF>::NV],
-                                             const RefineData &D, int i, LmShared *sh, ExcEntry *exc, unsigned int exc_cap)
+// Jacobi scale of this pixel's depth column: 1/(1+|e(x0)|), e(x0) evaluated at the start motion.
+__device__ __forceinline__ double depth_scale_at_start(const Loaded &L, const Motion &b)
 {
-    using A = PassA<NF>;
-    const double x = L.p.x, y = L.p.y, d = L.d;
-    const Motion &m = P.mot;
-    const double ak = fma(m.k, L.a.y, L.a.x);
-    const double beta = c2 * ak;
-    const double a0 = fma(-x, m.v[2], m.v[0]), a1 = fma(-y, m.v[2], m.v[1]);
-    const double xy = x * y, xx1 = fma(x, x, 1.0), yy1 = fma(y, y, 1.0);
-    const double b0 = fma(-xy, m.w[0], fma(xx1, m.w[1], -y * m.w[2]));
-    const double b1 = fma(-yy1, m.w[0], fma(xy, m.w[1], x * m.w[2]));
-    const double p0 = fma(d, a0, b0), p1 = fma(d, a1, b1);
-    const double r0 = fma(-beta, p0, L.u.x), r1 = fma(-beta, p1, L.u.y);
-    const double e0 = -beta * a0, e1 = -beta * a1;
-    const double ee = fma(e0, e0, e1 * e1);
-    double se = L.se;
-    if (P.first) { se = 1.0 / (1.0 + sqrt(ee)); D.se[i] = se; }      // jacobian_scaling_, fixed at iteration 0
-    acc[0] = fma(r0, r0, fma(r1, r1, acc[0]));
-    acc[1] = fma(d, d, acc[1]);
-    const double re = fma(e0, r0, e1 * r1);                          // e^T r
-    acc[A::iGMAX] = fmax(acc[A::iGMAX], fabs(re));
-    double bad = bad_flag(r0 + r1 + ee);
-    if (NF > 0) {
-        const double dbeta = (NF == 7) ? c2 * fma(-ak, 0.5 * c2, L.a.y) : 0.0;
-        const double ees = ee * se * se;
-        if (ees >= P.min_diag && ees <= P.max_diag) {
-            // unclamped: projector = (n n^T + e e^T/(radius+1)) / e^Te -- accumulate the two factors
-            const double mu = fast_rcp(ee);
-            const double rn = fma(-e1, r0, e0 * r1);                 // n^T r, n = (-e1, e0)
-            double fn[NF > 0 ? NF : 1], fe[NF > 0 ? NF : 1];
-            ft_times<NF>(beta, dbeta, d, x, y, xy, xx1, yy1, p0, p1, -e1, e0, fn);
-            ft_times<NF>(beta, dbeta, d, x, y, xy, xx1, yy1, p0, p1, e0, e1, fe);
-            int t = 0;
-#pragma unroll
-            for (int j = 0; j < NF; ++j) {
-                const double gn = mu * fn[j], ge = mu * fe[j];
-                acc[A::oH1 + j] = fma(gn, rn, acc[A::oH1 + j]);
-                acc[A::oH2 + j] = fma(ge, re, acc[A::oH2 + j]);
-#pragma unroll
-                for (int c = j; c < NF; ++c, ++t) {
-                    acc[A::oG1 + t] = fma(gn, fn[c], acc[A::oG1 + t]);
-                    acc[A::oG2 + t] = fma(ge, fe[c], acc[A::oG2 + t]);
-                }
-            }
-            bad += bad_flag(mu);
-        } else {
-            // clamped LM diagonal (|e| ~ 0) or non-finite: F^TF / F^Tr go to G1 / h1, the
-            // radius-dependent term q (F^Te)(e^TF) is applied by the controller from the exception list
-            double F0[NF > 0 ? NF : 1], F1[NF > 0 ? NF : 1], fe[NF > 0 ? NF : 1];
-            ft_times<NF>(beta, dbeta, d, x, y, xy, xx1, yy1, p0, p1, 1.0, 0.0, F0);
-            ft_times<NF>(beta, dbeta, d, x, y, xy, xx1, yy1, p0, p1, 0.0, 1.0, F1);
-            int t = 0;
-#pragma unroll
-            for (int j = 0; j < NF; ++j) {
-                fe[j] = fma(F0[j], e0, F1[j] * e1);
-                bad += bad_flag(fe[j]);
-                acc[A::oH1 + j] += fma(F0[j], r0, F1[j] * r1);
-#pragma unroll
-                for (int c = j; c < NF; ++c, ++t) acc[A::oG1 + t] += fma(F0[j], F0[c], F1[j] * F1[c]);
-            }
-            const unsigned int slot = atomicAdd(&sh->n_exc, 1u);
-            if (slot < exc_cap) {
-                ExcEntry E;
-                E.ees = ees; E.se2 = se * se; E.er = re;
-#pragma unroll
-                for (int j = 0; j < kMaxNF; ++j) E.fe[j] = (j < NF) ? fe[j] : 0.0;
-                exc[slot] = E;
-            } else {
-                sh->exc_overflow = 1u;
-            }
-        }
-    }
-    acc[A::iBAD] = fmax(acc[A::iBAD], bad);
+    const double beta0 = (2.0 / (2.0 + b.k)) * fma(b.k, L.a.y, L.a.x);
+    const double s0 = beta0 * fma(-L.p.x, b.v[2], b.v[0]), s1 = beta0 * fma(-L.p.y, b.v[2], b.v[1]);
+    return 1.0 / (1.0 + sqrt(fma(s0, s0, s1 * s1)));
 }
 
-// ------------------------------------------------------------------------------------------
-// Pass B body: sums mcc, step^2, candidate cost2; maxima bad_step, bad_cand
-// ------------------------------------------------------------------------------------------
-template <int NF>
-__device__ __forceinline__ void pass_b_pixel(const Loaded &L, const PhaseParams &P, double c2, double c2c, double rfac,
-                                             double inv_radius, double (&acc)[5], double *__restrict__ d_cand, int i)
+// Common per-pixel quantities of both passes at the point (mot, d).
+struct PxEval {
+    double x, y, xy, xx1, yy1, ak, beta, p0, p1, r0, r1, e0, e1, ee;
+};
+__device__ __forceinline__ void px_eval(const Loaded &L, const Motion &m, double c2, double d, PxEval &E)
 {
-    const double x = L.p.x, y = L.p.y, d = L.d;
-    const Motion &m = P.mot;
-    const double ak = fma(m.k, L.a.y, L.a.x);
-    const double beta = c2 * ak;
-    const double a0 = fma(-x, m.v[2], m.v[0]), a1 = fma(-y, m.v[2], m.v[1]);
-    const double xy = x * y, xx1 = fma(x, x, 1.0), yy1 = fma(y, y, 1.0);
-    const double b0 = fma(-xy, m.w[0], fma(xx1, m.w[1], -y * m.w[2]));
-    const double b1 = fma(-yy1, m.w[0], fma(xy, m.w[1], x * m.w[2]));
-    const double p0 = fma(d, a0, b0), p1 = fma(d, a1, b1);
-    const double r0 = fma(-beta, p0, L.u.x), r1 = fma(-beta, p1, L.u.y);
-    const double e0 = -beta * a0, e1 = -beta * a1;
-    const double ee = fma(e0, e0, e1 * e1);
-    // q = s_e^2 / (s_e^2 e^Te + clamp(s_e^2 e^Te)/radius)
-    const double se2 = L.se * L.se;
-    const double ees = ee * se2;
-    double q;
-    if (ees >= P.min_diag && ees <= P.max_diag) q = fast_rcp(ee) * rfac;              // rfac = radius/(radius+1)
-    else q = se2 / (ees + fmin(fmax(ees, P.min_diag), P.max_diag) * inv_radius);
-    // F delta_f = -beta (d A dv + B dw) - dbeta p dk
-    double m0 = 0.0, m1 = 0.0;
-    if (NF >= 6) {
-        const double *df = P.delta_f;
-        const double da0 = fma(-x, df[2], df[0]), da1 = fma(-y, df[2], df[1]);
-        const double db0 = fma(-xy, df[3], fma(xx1, df[4], -y * df[5]));
-        const double db1 = fma(-yy1, df[3], fma(xy, df[4], x * df[5]));
-        m0 = -beta * fma(d, da0, db0);
-        m1 = -beta * fma(d, da1, db1);
-        if (NF == 7) {
-            const double dbk = c2 * fma(-ak, 0.5 * c2, L.a.y) * df[6];
-            m0 = fma(-dbk, p0, m0);
-            m1 = fma(-dbk, p1, m1);
+    E.x = L.p.x; E.y = L.p.y;
+    E.ak = fma(m.k, L.a.y, L.a.x);
+    E.beta = c2 * E.ak;
+    const double a0 = fma(-E.x, m.v[2], m.v[0]), a1 = fma(-E.y, m.v[2], m.v[1]);
+    E.xy = E.x * E.y; E.xx1 = fma(E.x, E.x, 1.0); E.yy1 = fma(E.y, E.y, 1.0);
+    const double b0 = fma(-E.xy, m.w[0], fma(E.xx1, m.w[1], -E.y * m.w[2]));
+    const double b1 = fma(-E.yy1, m.w[0], fma(E.xy, m.w[1], E.x * m.w[2]));
+    E.p0 = fma(d, a0, b0); E.p1 = fma(d, a1, b1);
+    E.r0 = fma(-E.beta, E.p0, L.u.x); E.r1 = fma(-E.beta, E.p1, L.u.y);
+    E.e0 = -E.beta * a0; E.e1 = -E.beta * a1;
+    E.ee = fma(E.e0, E.e0, E.e1 * E.e1);
+}
+
+// Rare path of pass A: a pixel whose LM diagonal may be clamped (|e| ~ 0, focus of expansion) or
+// whose values are not finite.  F^TF / F^Tr go to G1 / h1; the radius-dependent term
+// q (F^Te)(e^TF) is applied by the controller from the exception list.
+template <int NF>
+__device__ __forceinline__ void pass_a_slow(const Loaded &L, const PhaseParams &P, double c2, double (&acc)[PassA<NF>::NV],
+                                         LmShared *sh, ExcEntry *exc, unsigned int exc_cap)
+{
+    using A = PassA<NF>;
+    PxEval E;
+    px_eval(L, P.mot, c2, L.d, E);
+    const double dbeta = (NF == 7) ? c2 * fma(-E.ak, 0.5 * c2, L.a.y) : 0.0;
+    const double se = P.first ? 1.0 / (1.0 + sqrt(E.ee)) : depth_scale_at_start(L, P.base);
+    double F0[NF > 0 ? NF : 1], F1[NF > 0 ? NF : 1], fe[NF > 0 ? NF : 1];
+    ft_times<NF>(E.beta, dbeta, L.d, E.x, E.y, E.xy, E.xx1, E.yy1, E.p0, E.p1, 1.0, 0.0, F0);
+    ft_times<NF>(E.beta, dbeta, L.d, E.x, E.y, E.xy, E.xx1, E.yy1, E.p0, E.p1, 0.0, 1.0, F1);
+    double bad = 0.0;
+    int t = 0;
+#pragma unroll
+    for (int j = 0; j < NF; ++j) {
+        fe[j] = fma(F0[j], E.e0, F1[j] * E.e1);
+        bad += bad_flag(fe[j]);
+        acc[A::oH1 + j] += fma(F0[j], E.r0, F1[j] * E.r1);
+#pragma unroll
+        for (int c = j; c < NF; ++c, ++t) acc[A::oG1 + t] += fma(F0[j], F0[c], F1[j] * F1[c]);
+    }
+    acc[A::iBAD] = fmax(acc[A::iBAD], bad);
+    const unsigned int slot = atomicAdd(&sh->n_exc, 1u);
+    if (slot < exc_cap) {
+        ExcEntry X;
+        X.ees = E.ee * se * se; X.se2 = se * se; X.er = fma(E.e0, E.r0, E.e1 * E.r1);
+#pragma unroll
+        for (int j = 0; j < kMaxNF; ++j) X.fe[j] = (j < NF) ? fe[j] : 0.0;
+        exc[slot] = X;
+    } else {
+        sh->exc_overflow = 1u;
+    }
+}
+
+// Pass A on TWO residual blocks per thread: every stage of the computation is written for both
+// pixels side by side (no branches on the common path) so the two dependency chains interleave.
+template <int NF>
+__device__ __forceinline__ void pass_a_pair(const Loaded (&L)[2], const bool (&valid)[2], const PhaseParams &P, double c2,
+                                            double (&acc)[PassA<NF>::NV], LmShared *sh, ExcEntry *exc, unsigned int exc_cap)
+{
+    using A = PassA<NF>;
+    PxEval E[2];
+    double d[2], re[2], rn[2], mu[2];
+    bool slow[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        d[p] = L[p].d;
+        px_eval(L[p], P.mot, c2, d[p], E[p]);
+        if (!valid[p]) { E[p].r0 = 0.0; E[p].r1 = 0.0; E[p].e0 = 0.0; E[p].e1 = 0.0; E[p].ee = 0.0; d[p] = 0.0; }
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        acc[0] = fma(E[p].r0, E[p].r0, fma(E[p].r1, E[p].r1, acc[0]));
+        acc[1] = fma(d[p], d[p], acc[1]);
+        re[p] = fma(E[p].e0, E[p].r0, E[p].e1 * E[p].r1);               // e^T r
+        rn[p] = fma(-E[p].e1, E[p].r0, E[p].e0 * E[p].r1);              // n^T r, n = (-e1, e0)
+        acc[A::iGMAX] = fmax(acc[A::iGMAX], fabs(re[p]));
+        acc[A::iEEMAX] = fmax(acc[A::iEEMAX], E[p].ee);
+        acc[A::iBAD] = fmax(acc[A::iBAD], bad_flag(E[p].r0 + E[p].r1 + E[p].ee));
+    }
+    if (NF > 0) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            // is the LM diagonal of this depth certainly not clamped?  (first evaluation: the Jacobi
+            // scale is 1/(1+|e|) of this very point; later: global lower bound of the scales)
+            bool fast;
+            if (P.first) {
+                const double se = 1.0 / (1.0 + sqrt(E[p].ee));
+                const double ees = E[p].ee * se * se;
+                fast = (ees >= P.min_diag && ees <= P.max_diag);
+            } else {
+                fast = (E[p].ee >= P.ee_fast_min && E[p].ee <= P.max_diag);
+            }
+            slow[p] = valid[p] && !fast;
+            const double r = fast_rcp(E[p].ee);
+            mu[p] = (valid[p] && fast) ? r : 0.0;
+        }
+        // projector = (n n^T + e e^T/(radius+1)) / e^Te: accumulate the two radius-independent factors
+        double fn[2][NF > 0 ? NF : 1], fe[2][NF > 0 ? NF : 1];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const double dbeta = (NF == 7) ? c2 * fma(-E[p].ak, 0.5 * c2, L[p].a.y) : 0.0;
+            ft_times<NF>(E[p].beta, dbeta, d[p], E[p].x, E[p].y, E[p].xy, E[p].xx1, E[p].yy1, E[p].p0, E[p].p1, -E[p].e1, E[p].e0, fn[p]);
+            ft_times<NF>(E[p].beta, dbeta, d[p], E[p].x, E[p].y, E[p].xy, E[p].xx1, E[p].yy1, E[p].p0, E[p].p1, E[p].e0, E[p].e1, fe[p]);
+        }
+        int t = 0;
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+            double gn[2], ge[2];
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                gn[p] = mu[p] * fn[p][j]; ge[p] = mu[p] * fe[p][j];
+                acc[A::oH1 + j] = fma(gn[p], rn[p], acc[A::oH1 + j]);
+                acc[A::oH2 + j] = fma(ge[p], re[p], acc[A::oH2 + j]);
+            }
+#pragma unroll
+            for (int c = j; c < NF; ++c, ++t) {
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    acc[A::oG1 + t] = fma(gn[p], fn[p][c], acc[A::oG1 + t]);
+                    acc[A::oG2 + t] = fma(ge[p], fe[p][c], acc[A::oG2 + t]);
+                }
+            }
+        }
+        if (slow[0] || slow[1]) {
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+                if (slow[p]) pass_a_slow<NF>(L[p], P, c2, acc, sh, exc, exc_cap);
         }
     }
-    const double delta_e = -q * fma(e0, r0 + m0, e1 * (r1 + m1));
-    m0 = fma(e0, delta_e, m0);
-    m1 = fma(e1, delta_e, m1);                                                      // J delta
-    acc[0] += fma(m0, fma(0.5, m0, r0), m1 * fma(0.5, m1, r1));
-    const double dc = d + delta_e;
-    const double dd = d - dc;
-    acc[1] = fma(dd, dd, acc[1]);
-    d_cand[i] = dc;
-    // candidate residual
-    const Motion &c = P.cand;
-    const double akc = fma(c.k, L.a.y, L.a.x);
-    const double betac = c2c * akc;
-    const double ca0 = fma(-x, c.v[2], c.v[0]), ca1 = fma(-y, c.v[2], c.v[1]);
-    const double cb0 = fma(-xy, c.w[0], fma(xx1, c.w[1], -y * c.w[2]));
-    const double cb1 = fma(-yy1, c.w[0], fma(xy, c.w[1], x * c.w[2]));
-    const double s0 = fma(-betac, fma(dc, ca0, cb0), L.u.x), s1 = fma(-betac, fma(dc, ca1, cb1), L.u.y);
-    acc[2] = fma(s0, s0, fma(s1, s1, acc[2]));
-    acc[3] = fmax(acc[3], bad_flag(delta_e));
-    acc[4] = fmax(acc[4], bad_flag(s0 + s1));
 }
+
+// Pass B on two residual blocks per thread.
+template <int NF>
+__device__ __forceinline__ void pass_b_pair(const Loaded (&L)[2], const bool (&valid)[2], const int (&idx)[2],
+                                            const PhaseParams &P, double c2, double c2c, double rfac, double inv_radius,
+                                            double (&acc)[kNB], double *__restrict__ d_cand)
+{
+    PxEval E[2];
+    double q[2], m0[2], m1[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) px_eval(L[p], P.mot, c2, L[p].d, E[p]);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        // q = s_e^2 / (s_e^2 e^Te + clamp(s_e^2 e^Te)/radius)  ( = radius/((radius+1) e^Te) when not clamped )
+        q[p] = fast_rcp(E[p].ee) * rfac;
+        if (!(E[p].ee >= P.ee_fast_min && E[p].ee <= P.max_diag)) {
+            const double se = depth_scale_at_start(L[p], P.base);
+            const double se2 = se * se, ees = E[p].ee * se2;
+            q[p] = se2 / (ees + fmin(fmax(ees, P.min_diag), P.max_diag) * inv_radius);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        // F delta_f = -beta (d A dv + B dw) - dbeta p dk
+        m0[p] = 0.0; m1[p] = 0.0;
+        if (NF >= 6) {
+            const double *df = P.delta_f;
+            const double da0 = fma(-E[p].x, df[2], df[0]), da1 = fma(-E[p].y, df[2], df[1]);
+            const double db0 = fma(-E[p].xy, df[3], fma(E[p].xx1, df[4], -E[p].y * df[5]));
+            const double db1 = fma(-E[p].yy1, df[3], fma(E[p].xy, df[4], E[p].x * df[5]));
+            m0[p] = -E[p].beta * fma(L[p].d, da0, db0);
+            m1[p] = -E[p].beta * fma(L[p].d, da1, db1);
+            if (NF == 7) {
+                const double dbk = c2 * fma(-E[p].ak, 0.5 * c2, L[p].a.y) * df[6];
+                m0[p] = fma(-dbk, E[p].p0, m0[p]);
+                m1[p] = fma(-dbk, E[p].p1, m1[p]);
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const double delta_e = -q[p] * fma(E[p].e0, E[p].r0 + m0[p], E[p].e1 * (E[p].r1 + m1[p]));
+        const double j0 = fma(E[p].e0, delta_e, m0[p]), j1 = fma(E[p].e1, delta_e, m1[p]);      // J delta
+        const double dc = L[p].d + delta_e;
+        const double dd = L[p].d - dc;
+        // candidate residual
+        const Motion &c = P.cand;
+        const double betac = c2c * fma(c.k, L[p].a.y, L[p].a.x);
+        const double ca0 = fma(-E[p].x, c.v[2], c.v[0]), ca1 = fma(-E[p].y, c.v[2], c.v[1]);
+        const double cb0 = fma(-E[p].xy, c.w[0], fma(E[p].xx1, c.w[1], -E[p].y * c.w[2]));
+        const double cb1 = fma(-E[p].yy1, c.w[0], fma(E[p].xy, c.w[1], E[p].x * c.w[2]));
+        const double s0 = fma(-betac, fma(dc, ca0, cb0), L[p].u.x), s1 = fma(-betac, fma(dc, ca1, cb1), L[p].u.y);
+        if (valid[p]) {
+            d_cand[idx[p]] = dc;
+            acc[0] += fma(j0, fma(0.5, j0, E[p].r0), j1 * fma(0.5, j1, E[p].r1));
+            acc[1] = fma(dd, dd, acc[1]);
+            acc[2] = fma(s0, s0, fma(s1, s1, acc[2]));
+            acc[3] = fmax(acc[3], bad_flag(delta_e));
+            acc[4] = fmax(acc[4], bad_flag(s0 + s1));
+        }
+    }
+}
+
 
 // ------------------------------------------------------------------------------------------
 // The persistent kernel
 // ------------------------------------------------------------------------------------------
-constexpr int kParts = 3;                         // row segments summed concurrently in the final reduce
 constexpr unsigned long long kWatchdogNs = 4000000000ull;   // 4 s: a stuck grid barrier aborts the solve
+
+// elected thread: queue the TMA bulk copies of one tile into a stage
+__device__ __forceinline__ void issue_tile(const RefineData &D, const double *dx, int tile, Stage *st, uint64_t *bar)
+{
+    // the tile-blocked arrays and the depth buffers are padded to whole tiles: fixed copy sizes
+    mbar_expect_tx(bar, (unsigned)(3 * kTile * sizeof(double2) + kTile * sizeof(double)));
+    bulk_g2s(st->xy, D.blk + (size_t)tile * (3 * kTile), (unsigned)(3 * kTile * sizeof(double2)), bar);
+    bulk_g2s(st->d, dx + (size_t)tile * kTile, (unsigned)(kTile * sizeof(double)), bar);
+}
 
 template <int NF>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -365,18 +488,31 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
                 const double *z_in, int z_stride, double *out, int invert_out)
 {
     using A = PassA<NF>;
-    extern __shared__ double red[];                       // kRedRows<NF> * kThreads doubles
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *red = reinterpret_cast<double *>(smem_raw);           // kRedRows<NF> * kThreads doubles, aliases the stages
+    Stage *stages = reinterpret_cast<Stage *>(smem_raw);
+    __shared__ __align__(8) uint64_t full[kStages];
     __shared__ PhaseParams P;
     __shared__ LmController s_ctl;
     __shared__ double fin[kRedRows<NF>];
-    __shared__ double part[kRedRows<NF> * kParts];
+    __shared__ double part[kWarps][kRedRows<NF>];
     __shared__ ExcSums s_exc;
-    __shared__ int s_flag[4];                             // [0] is_last, [1] next, [2] n_exc
+    __shared__ int s_flag[4];                                     // [0] is_last, [1] next, [2] n_exc
 
-    const int tid = threadIdx.x;
-    const int stride = gridDim.x * kThreads;
-    const int start = blockIdx.x * kThreads + tid;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x;
+    const int NT = (D.m + kTile - 1) / kTile;
+    const int n_my = ((int)blockIdx.x < NT) ? (NT - 1 - (int)blockIdx.x) / G + 1 : 0;
     unsigned int gen = 0;
+    unsigned int consumed = 0;                                    // tiles consumed by this CTA since kernel start
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < (int)(sizeof(Motion) / sizeof(int)))
+        reinterpret_cast<int *>(&P.base)[tid] = __ldcg(reinterpret_cast<const int *>(&sh->base) + tid);
+    __syncthreads();
 
     for (;;) {
         // ---- phase parameters
@@ -394,95 +530,143 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
         double *row = partials + (size_t)blockIdx.x * A::NV;
         const unsigned long long t_begin = (blockIdx.x == 0 && tid == 0) ? globaltimer() : 0ull;
 
-        if (run_a) {
-            double acc[A::NV];
+        // ---- prologue: fill the ring
+        if (tid == 0) {
+            fence_proxy_async();                                   // the scratch was written through the generic proxy
+            const int pre = n_my < kStages ? n_my : kStages;
+            for (int k = 0; k < pre; ++k) {
+                const unsigned g = consumed + (unsigned)k;
+                issue_tile(D, dx, (int)blockIdx.x + k * G, &stages[g % kStages], &full[g % kStages]);
+            }
+        }
+
+        double accA[A::NV];
+        double accB[kNB] = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-            for (int j = 0; j < A::NV; ++j) acc[j] = 0.0;
-            const double c2 = 2.0 / (2.0 + P.mot.k);
-            const bool want_se = !P.first;
-            int i = start;
-            Loaded cur;
-            if (i < D.m) cur = load_px(D, dx, i, want_se);
-            while (i < D.m) {
-                const int ni = i + stride;
-                Loaded nxt = cur;
-                if (ni < D.m) nxt = load_px(D, dx, ni, want_se);         // software prefetch
-                pass_a_pixel<NF>(cur, P, c2, acc, D, i, sh, exc, exc_cap);
-                cur = nxt;
-                i = ni;
+        for (int j = 0; j < A::NV; ++j) accA[j] = 0.0;
+        const double c2 = 2.0 / (2.0 + P.mot.k), c2c = 2.0 / (2.0 + P.cand.k);
+        const double rfac = P.radius / (P.radius + 1.0), inv_radius = 1.0 / P.radius;
+
+        // one 512-block tile per iteration: every thread works on two residual blocks at a time
+        for (int k = 0; k < n_my; ++k) {
+            const unsigned g = consumed + (unsigned)k;
+            const int s = (int)(g % kStages);
+            const int base_i = ((int)blockIdx.x + k * G) * kTile;
+            Loaded L[2];
+            bool valid[2];
+            int idx[2];
+            mbar_wait(&full[s], (g / kStages) & 1u);
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const int j = tid + p * kThreads;
+                idx[p] = base_i + j;
+                valid[p] = idx[p] < D.m;
+                L[p].p = stages[s].xy[j]; L[p].u = stages[s].uu[j]; L[p].a = stages[s].aa[j]; L[p].d = stages[s].d[j];
+                if (!valid[p]) { L[p].p = make_double2(0.0, 0.0); L[p].u = L[p].p; L[p].a = make_double2(1.0, 0.0); L[p].d = 1.0; }
             }
-            cta_reduce<A::NS, A::NM>(acc, red, row);
-        } else {
-            double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-            const double c2 = 2.0 / (2.0 + P.mot.k), c2c = 2.0 / (2.0 + P.cand.k);
-            const double rfac = P.radius / (P.radius + 1.0), inv_radius = 1.0 / P.radius;
-            int i = start;
-            Loaded cur;
-            if (i < D.m) cur = load_px(D, dx, i, true);
-            while (i < D.m) {
-                const int ni = i + stride;
-                Loaded nxt = cur;
-                if (ni < D.m) nxt = load_px(D, dx, ni, true);
-                pass_b_pixel<NF>(cur, P, c2, c2c, rfac, inv_radius, acc, dcand, i);
-                cur = nxt;
-                i = ni;
+            // stage s may be refilled once every thread has read it: the consumer warps only ARRIVE on
+            // the stage's named barrier and run on; warp 0 (the producer) waits for the 256 arrivals
+            if (warp == 0) asm volatile("bar.sync %0, %1;" ::"r"(1 + s), "r"(kThreads) : "memory");
+            else asm volatile("bar.arrive %0, %1;" ::"r"(1 + s), "r"(kThreads) : "memory");
+            if (tid == 0 && k + kStages < n_my) {
+                fence_proxy_async();
+                issue_tile(D, dx, (int)blockIdx.x + (k + kStages) * G, &stages[s], &full[s]);
             }
-            cta_reduce<3, 2>(acc, red, row);
+            if (run_a) pass_a_pair<NF>(L, valid, P, c2, accA, sh, exc, exc_cap);
+            else pass_b_pair<NF>(L, valid, idx, P, c2, c2c, rfac, inv_radius, accB, dcand);
+        }
+        consumed += (unsigned)n_my;
+        __syncthreads();
+        const unsigned long long t_loop = t_begin ? globaltimer() : 0ull;
+        if (run_a) cta_reduce<A::NS, A::NM>(accA, red, row);
+        else cta_reduce<3, 2>(accB, red, row);
+        if (t_begin) {
+            const unsigned long long t2 = globaltimer();
+            sh->t_phase[run_a ? 4 : 7] += t_loop - t_begin; sh->t_phase[run_a ? 5 : 8] += t2 - t_loop;
         }
 
         // ---- grid barrier: the last CTA to arrive reduces the rows and runs the controller
         if (tid == 0) {
             __threadfence();
             const unsigned int ticket = atomicAdd(&sh->arrive, 1u);
-            s_flag[0] = (ticket == (gen + 1u) * gridDim.x - 1u) ? 1 : 0;
+            s_flag[0] = (ticket == (gen + 1u) * (unsigned)G - 1u) ? 1 : 0;
         }
         __syncthreads();
         if (s_flag[0]) {
             __threadfence();
-            const int nv = run_a ? A::NV : 5, ns = run_a ? A::NS : 3;
-            const int rows = gridDim.x;
-            for (int idx = tid; idx < nv * kParts; idx += kThreads) {
-                const int j = idx / kParts, pt = idx - j * kParts;
-                const int lo = (rows * pt) / kParts, hi = (rows * (pt + 1)) / kParts;
-                const double *p = partials + j;
-                double s = (j < ns) ? 0.0 : -INFINITY;
-                if (j < ns) for (int b = lo; b < hi; ++b) s += __ldcg(p + (size_t)b * A::NV);
-                else        for (int b = lo; b < hi; ++b) s = fmax(s, __ldcg(p + (size_t)b * A::NV));
-                part[idx] = s;
+            const unsigned long long t_ctl = (tid == 0) ? globaltimer() : 0ull;
+            const int nv = run_a ? A::NV : kNB, ns = run_a ? A::NS : 3;
+            // final reduce: warp w sums rows w, w+8, ...; lanes cover the columns (coalesced); loads are
+            // issued in batches of 8 rows before they are combined, in a fixed order
+            {
+                double v[3] = {0.0, 0.0, 0.0};
+                for (int r0 = 0; r0 * kWarps + warp < G; r0 += 8) {
+                    double t[8][3];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int b = (r0 + u) * kWarps + warp;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const int j = lane + 32 * c;
+                            t[u][c] = (b < G && j < nv) ? __ldcg(partials + (size_t)b * A::NV + j) : 0.0;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const int j = lane + 32 * c;
+                            v[c] = (j < ns) ? v[c] + t[u][c] : fmax(v[c], t[u][c]);
+                        }
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { const int j = lane + 32 * c; if (j < nv) part[warp][j] = v[c]; }
             }
             // controller state: global -> shared
             for (int w = tid; w < (int)(sizeof(LmController) / sizeof(int)); w += kThreads)
                 reinterpret_cast<int *>(&s_ctl)[w] = __ldcg(reinterpret_cast<const int *>(&sh->ctl) + w);
             __syncthreads();
             if (tid < nv) {
-                double s = part[tid * kParts];
-                if (tid < ns) for (int pt = 1; pt < kParts; ++pt) s += part[tid * kParts + pt];
-                else          for (int pt = 1; pt < kParts; ++pt) s = fmax(s, part[tid * kParts + pt]);
+                double s = part[0][tid];
+                if (tid < ns) for (int w = 1; w < kWarps; ++w) s += part[w][tid];
+                else          for (int w = 1; w < kWarps; ++w) s = fmax(s, part[w][tid]);
                 fin[tid] = s;
             }
             __syncthreads();
+            if (run_a) {
+                // EvalSums in place (unused triangle / vector entries are zero)
+                if (tid < kTri) {
+                    s_ctl.ev.G1[tid] = (tid < A::TRI) ? fin[A::oG1 + (tid < A::TRI ? tid : 0)] : 0.0;
+                    s_ctl.ev.G2[tid] = (tid < A::TRI) ? fin[A::oG2 + (tid < A::TRI ? tid : 0)] : 0.0;
+                }
+                if (tid < kMaxNF) {
+                    s_ctl.ev.h1[tid] = (tid < NF) ? fin[A::oH1 + (tid < NF ? tid : 0)] : 0.0;
+                    s_ctl.ev.h2[tid] = (tid < NF) ? fin[A::oH2 + (tid < NF ? tid : 0)] : 0.0;
+                }
+                if (tid == 32) {
+                    s_ctl.ev.cost = 0.5 * fin[0]; s_ctl.ev.sumsq_d = fin[1]; s_ctl.ev.gmax_e = fin[A::iGMAX];
+                    s_ctl.ev.bad = fin[A::iBAD]; s_ctl.ev.ee_max = fin[A::iEEMAX];
+                }
+                __syncthreads();
+            }
             if (tid == 0) {
                 LmNext nx;
                 if (run_a) {
-                    EvalSums e;
-                    e.cost = 0.5 * fin[0]; e.sumsq_d = fin[1]; e.gmax_e = fin[A::iGMAX]; e.bad = fin[A::iBAD];
-                    for (int t = 0; t < kTri; ++t) { e.G1[t] = (t < A::TRI) ? fin[A::oG1 + t] : 0.0; e.G2[t] = (t < A::TRI) ? fin[A::oG2 + t] : 0.0; }
-                    for (int j = 0; j < kMaxNF; ++j) { e.h1[j] = (j < NF) ? fin[A::oH1 + j] : 0.0; e.h2[j] = (j < NF) ? fin[A::oH2 + j] : 0.0; }
-                    nx = s_ctl.on_eval(e);
+                    nx = s_ctl.on_eval_stored();
                 } else {
                     CandSums c;
                     c.mcc = fin[0]; c.step_sq = fin[1]; c.cand_cost = 0.5 * fin[2]; c.bad_step = fin[3]; c.bad_cand = fin[4];
                     nx = s_ctl.on_candidate(c);
                 }
                 s_flag[1] = (int)nx;
-                unsigned int ne = __ldcg(&sh->n_exc);
+                const unsigned int ne = __ldcg(&sh->n_exc);
                 s_flag[2] = (int)(ne < exc_cap ? ne : exc_cap);
             }
             __syncthreads();
             // ---- (re)solve at the current radius; the clamped-pixel correction is summed by the whole CTA
             while (s_flag[1] == (int)LM_SOLVE) {
                 const int ne = s_flag[2];
-                if (NF > 0 && ne > 0) {
+                if constexpr (NF > 0) if (ne > 0) {
                     const double R = s_ctl.radius, lo = s_ctl.opt.min_lm_diagonal, hi = s_ctl.opt.max_lm_diagonal;
                     double a[kTri + kMaxNF];
 #pragma unroll
@@ -501,6 +685,7 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
                             for (int c = j; c < NF; ++c, ++t) a[t] = fma(qf, E.fe[c], a[t]);
                         }
                     }
+                    // a[] is packed with the NF-triangle first; spread into the kMaxNF layout the controller uses
                     cta_reduce<kTri + kMaxNF, 0>(a, red, fin);
                     if (tid < kTri) s_exc.S[tid] = fin[tid];
                     if (tid < kMaxNF) s_exc.rhs[tid] = fin[kTri + tid];
@@ -513,16 +698,17 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
             if (tid == 0) {
                 const LmNext nx = (LmNext)s_flag[1];
                 if (s_ctl.accepted_last && nx == LM_RUN_A) sh->bc.which_x = P.which_x ^ 1;
-                Motion mo = sh->base, ca = sh->base;
+                Motion mo = P.base, ca = P.base;
                 if (NF >= 6) for (int j = 0; j < 3; ++j) {
                     mo.v[j] = s_ctl.f[j]; mo.w[j] = s_ctl.f[3 + j];
                     ca.v[j] = s_ctl.f[j] + s_ctl.delta_f[j]; ca.w[j] = s_ctl.f[3 + j] + s_ctl.delta_f[3 + j];
                 }
                 if (NF == 7) { mo.k = s_ctl.f[6]; ca.k = s_ctl.f[6] + s_ctl.delta_f[6]; }
-                if (nx == LM_DONE && s_ctl.termination == RSDSFM_FAILURE) mo = sh->base;   // Ceres restores the start values
+                if (nx == LM_DONE && s_ctl.termination == RSDSFM_FAILURE) mo = P.base;   // Ceres restores the start values
                 sh->bc.mot = mo; sh->bc.cand = ca;
                 for (int j = 0; j < kMaxNF; ++j) sh->bc.delta_f[j] = s_ctl.delta_f[j];
                 sh->bc.radius = s_ctl.radius;
+                sh->bc.ee_fast_min = s_ctl.ee_fast_min;
                 sh->bc.first = 0;
                 sh->bc.next = (int)nx;
                 if (nx == LM_RUN_A) sh->n_exc = 0u;       // a new evaluation rebuilds the exception list
@@ -534,13 +720,17 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
             for (int w = tid; w < (int)(sizeof(LmController) / sizeof(int)); w += kThreads)
                 reinterpret_cast<int *>(&sh->ctl)[w] = reinterpret_cast<const int *>(&s_ctl)[w];
             __syncthreads();
-            if (tid == 0) { __threadfence(); st_release(&sh->generation, gen + 1u); }
+            if (tid == 0) {
+                sh->t_phase[run_a ? 6 : 9] += globaltimer() - t_ctl;
+                __threadfence();
+                st_release(&sh->generation, gen + 1u);
+            }
         }
         // ---- everybody waits for the controller's release
         if (tid == 0) {
             const unsigned long long t0 = globaltimer();
             while (ld_acquire(&sh->generation) <= gen) {
-                __nanosleep(40);
+                __nanosleep(32);
                 if (globaltimer() - t0 > kWatchdogNs) { sh->error = 1; break; }
             }
             if (t_begin && !s_flag[0]) {
@@ -556,7 +746,7 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
     // start values (solver.cc Minimize): 1/z_in for a9 (double reciprocal, :213/:247), 1.0 for a8.
     const bool failed = (__ldcg(&sh->ctl.termination) == RSDSFM_FAILURE) || P.error;
     const double *dfin = P.which_x ? d1 : d0;
-    for (int i = start; i < D.m; i += stride) {
+    for (int i = blockIdx.x * kThreads + tid; i < D.m; i += G * kThreads) {
         double dv;
         if (failed) dv = z_in ? 1.0 / z_in[(size_t)i * z_stride] : 1.0;
         else dv = dfin[i];
@@ -572,7 +762,7 @@ static int launch_persistent(rsdsfm_ctx *ctx, RefineData D, double *d0, double *
                              ExcEntry *exc, unsigned int exc_cap, const double *z_in, int z_stride, double *out,
                              int invert_out, int grid)
 {
-    const size_t smem = sizeof(double) * (size_t)kRedRows<NF> * kThreads;
+    const size_t smem = smem_bytes<NF>();
     RS_CUDA(ctx, cudaFuncSetAttribute(k_lm_persistent<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void *args[] = {&D, &d0, &d1, &sh, &partials, &exc, &exc_cap, &z_in, &z_stride, &out, &invert_out};
     if (ctx->profile) cudaEventRecord(ctx->pe0, ctx->stream);
@@ -660,6 +850,7 @@ int lm_collect(rsdsfm_ctx *ctx, int nf, int m, Motion *mot, rsdsfm_lm_summary *s
         ctx->prof[3] += (double)h->t_phase[2] * 1e-6; ctx->prof[4] += (double)h->t_phase[3];
         ctx->prof[5] += (double)h->t_phase[3] * m;
         ctx->prof[6] += kms; ctx->prof[7] += 1.0;
+        for (int j = 0; j < 6; ++j) ctx->prof_detail[j] += (double)h->t_phase[4 + j] * 1e-6;
     }
     if (mot && h->ctl.termination != RSDSFM_FAILURE) {
         if (nf >= 6) for (int j = 0; j < 3; ++j) { mot->v[j] = h->ctl.f[j]; mot->w[j] = h->ctl.f[3 + j]; }
@@ -675,6 +866,16 @@ const double *lm_motion_device(rsdsfm_ctx *ctx)
     return reinterpret_cast<const double *>((const char *)ctx->lm_shared.p + offsetof(LmShared, bc) + offsetof(Bcast, mot));
 }
 
+static int ensure_lm_buffers(rsdsfm_ctx *ctx, size_t mm)
+{
+    const size_t tiles = (mm + kTile - 1) / kTile;             // everything is padded to whole tiles
+    RS_TRY(ensure(ctx, ctx->pix, sizeof(double2) * 3 * kTile * tiles));
+    RS_TRY(ensure(ctx, ctx->dA, sizeof(double) * kTile * tiles));
+    RS_TRY(ensure(ctx, ctx->dB, sizeof(double) * kTile * tiles));
+    RS_TRY(ensure(ctx, ctx->lm_shared, sizeof(LmShared)));
+    return RSDSFM_OK;
+}
+
 // a9 on device pointers: queues gather + solve on the stream, no synchronisation.
 int refine_async(rsdsfm_ctx *ctx, const double *flow, const double *inliers3, const double *alpha,
                  const double *alpha_k, int m, const double *v, const double *w, double k, int const_acc,
@@ -683,19 +884,14 @@ int refine_async(rsdsfm_ctx *ctx, const double *flow, const double *inliers3, co
     rsdsfm_lm_options o;
     if (opts) o = *opts; else rsdsfm_lm_default_options(&o);
     const size_t mm = (size_t)m;
-    RS_TRY(ensure(ctx, ctx->pix, sizeof(double2) * 3 * mm));
-    RS_TRY(ensure(ctx, ctx->dA, sizeof(double) * mm));
-    RS_TRY(ensure(ctx, ctx->dB, sizeof(double) * mm));
-    RS_TRY(ensure(ctx, ctx->scale_e, sizeof(double) * mm));
-    RS_TRY(ensure(ctx, ctx->lm_shared, sizeof(LmShared)));
-    double2 *xy = (double2 *)ctx->pix.p, *uu = xy + mm, *aa = uu + mm;
+    RS_TRY(ensure_lm_buffers(ctx, mm));
+    double2 *blk = (double2 *)ctx->pix.p;
     double *d0 = (double *)ctx->dA.p, *d1 = (double *)ctx->dB.p;
     LmShared *sh = (LmShared *)ctx->lm_shared.p;
     RS_CUDA(ctx, cudaMemsetAsync(&sh->nonfinite_input, 0, sizeof(int), ctx->stream));
-    k_refine_gather<<<grid_for(ctx, m, 8), kThreads, 0, ctx->stream>>>(flow, inliers3, alpha, alpha_k, flow_index, m, xy, uu,
-                                                                      aa, d0, sh);
+    k_refine_gather<<<grid_for(ctx, m, 8), kThreads, 0, ctx->stream>>>(flow, inliers3, alpha, alpha_k, flow_index, m, blk, d0, sh);
     ctx->launches++;
-    RefineData D{xy, uu, aa, (double *)ctx->scale_e.p, m};
+    RefineData D{blk, m};
     Motion mot;
     for (int j = 0; j < 3; ++j) { mot.v[j] = v[j]; mot.w[j] = w[j]; }
     mot.k = k;
@@ -726,7 +922,7 @@ int refine_device(rsdsfm_ctx *ctx, const double *flow, const double *inliers3, c
     return fail(ctx, RSDSFM_ERR_INTERNAL, "refine: exception list overflow persisted");
 }
 
-// a8 on device pointers: coord / flow are interleaved pairs already.
+// a8 on device pointers.
 int estimate_inverse_depths_device(rsdsfm_ctx *ctx, const double *coord, const double *flow, int n, const double *v,
                                    const double *w, double k, const double *alpha, const double *alpha_k,
                                    double *inv_depth, rsdsfm_lm_summary *summary)
@@ -738,15 +934,12 @@ int estimate_inverse_depths_device(rsdsfm_ctx *ctx, const double *coord, const d
     memset(summary, 0, sizeof *summary);
     if (n == 0) { summary->termination = RSDSFM_CONVERGENCE; summary->reason = RSDSFM_REASON_FUNCTION_TOL; return RSDSFM_OK; }
     const size_t nn = (size_t)n;
-    RS_TRY(ensure(ctx, ctx->pix, sizeof(double2) * nn));
-    RS_TRY(ensure(ctx, ctx->dA, sizeof(double) * nn));
-    RS_TRY(ensure(ctx, ctx->dB, sizeof(double) * nn));
-    RS_TRY(ensure(ctx, ctx->scale_e, sizeof(double) * nn));
-    double2 *aa = (double2 *)ctx->pix.p;
+    RS_TRY(ensure_lm_buffers(ctx, nn));
+    double2 *blk = (double2 *)ctx->pix.p;
     double *d0 = (double *)ctx->dA.p, *d1 = (double *)ctx->dB.p;
-    k_depth_gather<<<grid_for(ctx, n, 8), kThreads, 0, ctx->stream>>>(alpha, alpha_k, n, aa, d0);
+    k_depth_gather<<<grid_for(ctx, n, 8), kThreads, 0, ctx->stream>>>(coord, flow, alpha, alpha_k, n, blk, d0);
     ctx->launches++;
-    RefineData D{(const double2 *)coord, (const double2 *)flow, aa, (double *)ctx->scale_e.p, n};
+    RefineData D{blk, n};
     Motion mot;
     for (int j = 0; j < 3; ++j) { mot.v[j] = v[j]; mot.w[j] = w[j]; }
     mot.k = k;
