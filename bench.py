@@ -36,6 +36,7 @@ WORKLOAD = ("synthetic analytic RS flow 1920x1080 (galaxy_stabil K, gamma 0.95),
 ALGO_BYTES_PASS_A = 24.0   # read flow 16 B + inverse depth 8 B per residual block
 ALGO_BYTES_PASS_B = 32.0   # read flow 16 B + inverse depth 8 B, write candidate inverse depth 8 B
 N_PAIRS = 3                # distinct pairs cycled through: >= 3 x ~170 MB of inputs, larger than the 126 MB L2
+CONST_ACC = True           # headline workload: constant-acceleration trajectory (k estimated); --const-vel: k = 0 fixed
 
 
 def load_peaks():
@@ -100,7 +101,7 @@ class ClockSampler:
 
 def gen_pair(synth, seed):
     return synth.make_pair(ROWS, COLS, "galaxy_stabil", gamma=0.95, v=(0.30, 0.05, 0.02), w=(0.002, -0.004, 0.0087),
-                           k=0.5, seed=seed, noise_sigma_px=0.3, outlier_frac=0.05)
+                           k=0.5 if CONST_ACC else 0.0, seed=seed, noise_sigma_px=0.3, outlier_frac=0.05)
 
 
 def prepare_pair_gpu(ctx, synth, torch, seed, H=16, tol=0.05):
@@ -113,7 +114,7 @@ def prepare_pair_gpu(ctx, synth, torch, seed, H=16, tol=0.05):
     coord, flow, cpx, fpx = coord[:2 * n], flow[:2 * n], cpx[:2 * n], fpx[:2 * n]
     alpha, alpha_k = ctx.alpha(fpx, cpx, n, ROWS, P["gamma"])
     samples = synth.sample_list(n, H, seed=seed + 100)
-    R = ctx.ransac(coord, flow, alpha, alpha_k, n, True, samples, tol)
+    R = ctx.ransac(coord, flow, alpha, alpha_k, n, CONST_ACC, samples, tol)
     inl, a_in, ak_in, ix, m = ctx.gather_inliers(coord, alpha, alpha_k, n, R["mask"], R["inv_depth"])
     image = torch.from_numpy(P["image"]).to(dev)
     d = dict(flow=flow.contiguous(), inliers3=inl.contiguous(), alpha=a_in.contiguous(), alpha_k=ak_in.contiguous(),
@@ -142,7 +143,7 @@ def prepare_pair_cpu(O, synth, seed, H=16, tol=0.05):
     alpha = O.get_alpha(fpx, n, ROWS, P["gamma"])
     alpha_k = O.get_alpha_k(cpx, fpx, n, ROWS, P["gamma"])
     samples = synth.sample_list(n, H, seed=seed + 100)
-    R = O.ransac(coord[:2 * n], flow[:2 * n], alpha, alpha_k, n, True, tol, samples=samples)
+    R = O.ransac(coord[:2 * n], flow[:2 * n], alpha, alpha_k, n, CONST_ACC, tol, samples=samples)
     inl, a_in, ak_in = O.gather_inliers(coord, alpha, alpha_k, n, R["mask"], R["inv_depth"])
     m = len(a_in)
     h = dict(flow=flow[:2 * m].copy(), inliers3=inl, alpha=a_in, alpha_k=ak_in, image=P["image"])
@@ -150,13 +151,13 @@ def prepare_pair_cpu(O, synth, seed, H=16, tol=0.05):
 
 
 def step_device(ctx, capi, p):
-    return ctx.refine_rectify(p["flow"], p["inliers3"], p["alpha"], p["alpha_k"], p["m"], p["v"], p["w"], p["k"], True, False,
+    return ctx.refine_rectify(p["flow"], p["inliers3"], p["alpha"], p["alpha_k"], p["m"], p["v"], p["w"], p["k"], CONST_ACC, False,
                               p["image"], p["K4"], p["gamma"], layout=capi.DEPTH_ROWMAJOR, out=p["out"])
 
 
 def step_host(ctx, capi, p):
     h = p["host"]
-    return ctx.refine_rectify(h["flow"], h["inliers3"], h["alpha"], h["alpha_k"], p["m"], p["v"], p["w"], p["k"], True, False,
+    return ctx.refine_rectify(h["flow"], h["inliers3"], h["alpha"], h["alpha_k"], p["m"], p["v"], p["w"], p["k"], CONST_ACC, False,
                               h["image"], p["K4"], p["gamma"], layout=capi.DEPTH_ROWMAJOR, out=h["out"])
 
 
@@ -243,8 +244,8 @@ def run_ours(args):
                        "l2": "inputs larger than L2: %d distinct pairs cycled (~%.0f MB device inputs each)" % (N_PAIRS, h2d / 1e6)},
             "ms_per_lm_iteration": lm_ms,
             "lm_phase_breakdown_us": {
-                "pass_a": {k: 1e3 * prof[k] / max(prof["pass_a_launches"], 1) for k in ("a_loop_ms", "a_reduce_ms", "a_ctl_ms")},
-                "pass_b": {k: 1e3 * prof[k] / max(prof["pass_b_launches"], 1) for k in ("b_loop_ms", "b_reduce_ms", "b_ctl_ms")},
+                "pass_a": {k: 1e3 * prof[k] / max(prof["pass_a_launches"], 1) for k in ("a_loop_ms", "a_reduce_ms", "a_ctl_ms", "a_logic_ms")},
+                "pass_b": {k: 1e3 * prof[k] / max(prof["pass_b_launches"], 1) for k in ("b_loop_ms", "b_reduce_ms", "b_ctl_ms", "b_logic_ms")},
                 "kernel_ms_per_solve": prof["kernel_ms"] / max(prof["kernel_launches"], 1)},
             "clocks": clocks,
             "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
@@ -272,7 +273,7 @@ def cpu_baseline(p, threads, budget_s, min_reps=1):
     from oracle import pyoracle as O
     O.build()
     h = p["host"]
-    args = (h["flow"], h["inliers3"], h["alpha"], h["alpha_k"], p["m"], p["v"], p["w"], p["k"], True, False, h["image"],
+    args = (h["flow"], h["inliers3"], h["alpha"], h["alpha_k"], p["m"], p["v"], p["w"], p["k"], CONST_ACC, False, h["image"],
             p["K4"], p["gamma"])
     done = [0]
     t0 = time.perf_counter()
@@ -331,7 +332,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--const-vel", action="store_true",
+                    help="secondary workload: constant-velocity trajectory and model (the reference's default mode)")
     args = ap.parse_args()
+    if args.const_vel:
+        global CONST_ACC, WORKLOAD
+        CONST_ACC = False
+        WORKLOAD = WORKLOAD.replace("constant-acceleration trajectory k=0.5", "constant-velocity trajectory k=0").replace(
+            "refine (const-acc, 7 motion parameters", "refine (const-vel, 6 motion parameters")
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

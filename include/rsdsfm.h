@@ -107,9 +107,10 @@ RSDSFM_API long long rsdsfm_launch_count(rsdsfm_ctx *ctx);
  *       [3] pass-B ms, [4] pass-B launches, [5] pass-B residual blocks processed, [6..7] reserved. */
 RSDSFM_API int rsdsfm_profile_enable(rsdsfm_ctx *ctx, int on);
 RSDSFM_API int rsdsfm_profile_read(rsdsfm_ctx *ctx, double *out8);
-/* out6 (ms, accumulated like above): pass-A pixel loop, CTA reduction, grid reduction + controller;
- * then the same three for pass B -- measured by CTA 0 / the controller CTA with %globaltimer. */
-RSDSFM_API int rsdsfm_profile_detail(rsdsfm_ctx *ctx, double *out6);
+/* out8 (ms, accumulated like above): pass-A pixel loop, CTA reduction, grid reduction + controller;
+ * the same three for pass B; then the controller logic alone (after the row reduction) for pass A
+ * and pass B -- measured by CTA 0 / the controller CTA with %globaltimer. */
+RSDSFM_API int rsdsfm_profile_detail(rsdsfm_ctx *ctx, double *out8);
 
 /* ---- a2: flatten + normalise glue (main.cc:398-432, errorMeasure.cpp:66-97) --------------- */
 /* flow_img: rows*cols*2.  Outputs (each 2*rows*cols doubles) are pre-filled like the reference

@@ -137,13 +137,13 @@ class Context:
     def profile_read(self):
         out = np.zeros(8)
         self._ck(self.lib.rsdsfm_profile_read(self.h, _ptr(out)))
-        det = np.zeros(6)
+        det = np.zeros(8)
         self._ck(self.lib.rsdsfm_profile_detail(self.h, _ptr(det)))
         return dict(pass_a_ms=out[0], pass_a_launches=int(out[1]), pass_a_blocks=out[2],
                     pass_b_ms=out[3], pass_b_launches=int(out[4]), pass_b_blocks=out[5],
                     kernel_ms=out[6], kernel_launches=int(out[7]),
                     a_loop_ms=det[0], a_reduce_ms=det[1], a_ctl_ms=det[2],
-                    b_loop_ms=det[3], b_reduce_ms=det[4], b_ctl_ms=det[5])
+                    b_loop_ms=det[3], b_reduce_ms=det[4], b_ctl_ms=det[5], a_logic_ms=det[6], b_logic_ms=det[7])
 
     # ---- a2
     def flatten(self, flow_img, K4, gamma, thr=1e-10, out=None):

@@ -147,10 +147,10 @@ int rsdsfm_profile_read(rsdsfm_ctx *ctx, double *out8)
     return RSDSFM_OK;
 }
 
-int rsdsfm_profile_detail(rsdsfm_ctx *ctx, double *out6)
+int rsdsfm_profile_detail(rsdsfm_ctx *ctx, double *out8)
 {
-    if (!ctx || !out6) return RSDSFM_ERR_ARG;
-    for (int j = 0; j < 6; ++j) out6[j] = ctx->prof_detail[j];
+    if (!ctx || !out8) return RSDSFM_ERR_ARG;
+    for (int j = 0; j < 8; ++j) out8[j] = ctx->prof_detail[j];
     return RSDSFM_OK;
 }
 

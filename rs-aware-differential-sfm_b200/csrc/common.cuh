@@ -44,7 +44,7 @@ struct rsdsfm_ctx {
     // per-kernel profiling (bench.py's roofline): CUDA events around the LM passes
     bool profile = false;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
-    double prof_detail[6] = {0, 0, 0, 0, 0, 0};  // ms: pass A pixel loop / CTA reduce / controller, same for pass B
+    double prof_detail[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // ms: pass A pixel loop / CTA reduce / controller, same for pass B
     double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // [0] pass A ms, [1] pass A phases, [2] pass A residual blocks,
                                                  // [3] pass B ms, [4] pass B phases, [5] pass B residual blocks,
                                                  // [6] LM kernel ms (CUDA events), [7] LM kernel launches

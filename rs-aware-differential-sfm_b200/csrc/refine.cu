@@ -633,6 +633,7 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
                 fin[tid] = s;
             }
             __syncthreads();
+            const unsigned long long t_fin = (tid == 0) ? globaltimer() : 0ull;
             if (run_a) {
                 // EvalSums in place (unused triangle / vector entries are zero)
                 if (tid < kTri) {
@@ -696,6 +697,8 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
             }
             // ---- publish the next phase
             if (tid == 0) {
+                const unsigned long long t_solved = globaltimer();
+                sh->t_phase[run_a ? 10 : 11] += t_solved - t_fin;     // controller logic only (after the row reduction)
                 const LmNext nx = (LmNext)s_flag[1];
                 if (s_ctl.accepted_last && nx == LM_RUN_A) sh->bc.which_x = P.which_x ^ 1;
                 Motion mo = P.base, ca = P.base;
@@ -850,7 +853,7 @@ int lm_collect(rsdsfm_ctx *ctx, int nf, int m, Motion *mot, rsdsfm_lm_summary *s
         ctx->prof[3] += (double)h->t_phase[2] * 1e-6; ctx->prof[4] += (double)h->t_phase[3];
         ctx->prof[5] += (double)h->t_phase[3] * m;
         ctx->prof[6] += kms; ctx->prof[7] += 1.0;
-        for (int j = 0; j < 6; ++j) ctx->prof_detail[j] += (double)h->t_phase[4 + j] * 1e-6;
+        for (int j = 0; j < 8; ++j) ctx->prof_detail[j] += (double)h->t_phase[4 + j] * 1e-6;
     }
     if (mot && h->ctl.termination != RSDSFM_FAILURE) {
         if (nf >= 6) for (int j = 0; j < 3; ++j) { mot->v[j] = h->ctl.f[j]; mot->w[j] = h->ctl.f[3 + j]; }
