@@ -1,0 +1,3 @@
+// errorMeasure.h -- same header name as the reference's src/errorMeasure.h: the declarations live in rsdsfm_host.h.
+#pragma once
+#include "rsdsfm_host.h"

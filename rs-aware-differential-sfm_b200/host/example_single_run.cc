@@ -1,0 +1,93 @@
+// example_single_run.cc -- the glue of the reference's evaluateSingleRun() (main.cc:398-523) written
+// against the host shim: flatten -> alpha -> RANSAC -> nonLinearRefinement -> sign fix -> depth
+// raster -> setPose -> backProject -> interpolateCrackyImage, on a small analytic RS pair.
+//
+//   g++ -std=c++17 -O2 -I include -I rs-aware-differential-sfm_b200/host
+//       rs-aware-differential-sfm_b200/host/example_single_run.cc
+//       -L rs-aware-differential-sfm_b200 -lrsdsfm -Wl,-rpath,'$ORIGIN/..' -o rs-aware-differential-sfm_b200/host/example_single_run
+//
+// Prints the recovered motion; exits non-zero if w is not recovered (exact constant-velocity data).
+#include <cmath>
+#include <cstdio>
+
+#include "camera.h"
+#include "errorMeasure.h"
+#include "minimal.h"
+#include "nonlinearRefinement.h"
+
+using Eigen::ArrayXd;
+using nonlinear_refinement::nonLinearRefinement;
+
+int main()
+{
+    const int rows = 240, cols = 320;
+    const double gamma = 0.95;
+    const Eigen::Vector3d v_true(0.30, 0.05, 0.02), w_true(0.002, -0.004, 0.0087);
+
+    Camera camera;
+    Eigen::Matrix3d Kin;
+    Kin(0, 0) = 400.0; Kin(1, 1) = 398.0; Kin(0, 2) = 160.0; Kin(1, 2) = 120.0; Kin(2, 2) = 1.0;
+    camera.setIntrinsics(Kin);
+    cv::Mat rs1(rows, cols, CV_8UC3), rs2(rows, cols, CV_8UC3);
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x)
+            rs1.at<cv::Vec3b>(y, x) = cv::Vec3b((unsigned char)(40 + (x * 3 + y) % 200), (unsigned char)(60 + (x + 2 * y) % 180), (unsigned char)(90 + (x * y) % 150));
+    camera.addFrameReal(rs1);
+    camera.addFrameReal(rs2);
+    camera.setGamma(gamma);
+
+    // exact constant-velocity RS flow: u = alpha (A v d + B w), alpha = 1 + gamma flow_y / h  (closed form)
+    Eigen::Matrix3d K = camera.getIntrinsics();
+    const double f_x = K(0, 0), f_y = K(1, 1), c_x = K(0, 2), c_y = K(1, 2);
+    cv::Mat_<cv::Point_<double>> flow_image(rows, cols);
+    for (int j = 0; j < rows; ++j)
+        for (int i = 0; i < cols; ++i) {
+            const double x = (i - c_x) / f_x, y = (j - c_y) / f_y;
+            const double d = 0.08 + 0.05 * std::sin(0.03 * i) * std::cos(0.02 * j) + 0.03 * x;
+            const double gx = (v_true(0) - x * v_true(2)) * d + (-x * y * w_true(0) + (1 + x * x) * w_true(1) - y * w_true(2));
+            const double gy = (v_true(1) - y * v_true(2)) * d + (-(1 + y * y) * w_true(0) + x * y * w_true(1) + x * w_true(2));
+            const double uy = gy / (1.0 - gy * f_y / rows), a = 1.0 + uy * f_y / rows;
+            flow_image(j, i) = cv::Point_<double>(a * gx * f_x / gamma, uy * f_y / gamma);
+        }
+    camera.setCachedFlow(flow_image);
+
+    // ---- main.cc:398-432
+    error_measure::Flattened F = error_measure::flattenFlow(camera.calculateDeepFlow(1, 2), K, gamma, 1e-10, false);
+    Eigen::Matrix2Xd &coord = F.coord, &flow = F.flow, &coord_pixel = F.coord_pixel, &flow_pixel = F.flow_pixel;
+    // ---- main.cc:437-438
+    ArrayXd alpha = minimal::getAlpha(flow_pixel, rows, gamma);
+    ArrayXd alphaK = minimal::getAlphaK(coord_pixel, flow_pixel, rows, gamma);
+    // ---- main.cc:447
+    RansacValues ransac_results = minimal::ransac(coord, flow, alpha, alphaK, false, 5, 0.05, false);
+    std::cout << "ransac numInliers: " << ransac_results.num_inliers << std::endl;
+    std::cout << "ransac w: " << ransac_results.w.transpose() << std::endl;
+    std::cout << "ransac v: " << ransac_results.v.transpose() << std::endl;
+    // ---- main.cc:455-458
+    RansacValues results = nonLinearRefinement(flow, ransac_results, false, true);
+    // ---- main.cc:466-478
+    double count_z = 0;
+    for (int i = 0; i < results.num_inliers; ++i) count_z += results.inliers(2, i);
+    if (count_z * 1.0 / results.num_inliers < 0) { results.inliers.row(2) *= -1.0; results.v *= -1.0; }
+    std::cout << "final w: " << results.w.transpose() << std::endl;
+    std::cout << "final v: " << results.v.transpose() << std::endl;
+    // ---- main.cc:496-509
+    Eigen::MatrixXd depth_map = Eigen::MatrixXd::Zero(rows, cols);
+    for (int i = 0; i < results.num_inliers; i++) {
+        const int x = int(f_x * results.inliers(0, i) + c_x + 0.5), y = int(f_y * results.inliers(1, i) + c_y + 0.5);
+        if (x >= 0 && x < cols && y >= 0 && y < rows) depth_map(y, x) = results.inliers(2, i);
+    }
+    // ---- main.cc:516-523
+    camera.setPose(1, results.k, results.v, results.w);
+    camera.setDepthMap(1, depth_map);
+    camera.backProject(1);
+    cv::Mat backprojection = camera.interpolateCrackyImage(camera.getFrame(1).getGsImage(), 1);
+    long filled = 0;
+    for (int y = 0; y < rows; ++y) for (int x = 0; x < cols; ++x) if (backprojection.at<cv::Vec3b>(y, x) != cv::Vec3b(0, 0, 0)) filled++;
+    std::printf("rectified image: %ld of %d pixels filled\n", filled, rows * cols);
+
+    double werr = 0;
+    for (int a = 0; a < 3; ++a) werr = std::fmax(werr, std::fabs(results.w(a) - w_true(a)));
+    const double cosang = results.v.dot(v_true) / (results.v.norm() * v_true.norm());
+    std::printf("max |w - w_true| = %.3e, angle(v, v_true) = %.3e rad\n", werr, std::acos(std::fmin(1.0, cosang)));
+    return (werr < 1e-6 && cosang > 1.0 - 1e-9 && filled > rows * cols * 9 / 10) ? 0 : 1;
+}

@@ -1,0 +1,3 @@
+// nonlinearRefinement.h -- same header name as the reference's src/nonlinearRefinement.h: the declarations live in rsdsfm_host.h.
+#pragma once
+#include "rsdsfm_host.h"

@@ -1,0 +1,490 @@
+// rsdsfm_host.h -- host-side mirror of the reference's C++ surface for the dense optimisation
+// core (Camera, RsFrame, Scanline, minimal::*, nonlinear_refinement::*, error_measure::*).
+// Same names, argument meaning and (absence of) error behaviour as the reference headers
+//   minimal.h:41-160, nonlinearRefinement.h:42-111, camera.h:33-340, rsframe.h:33-315,
+//   scanline.h:30-101, errorMeasure.h:18-64
+// so that drivers written like main.cc:398-523 / errorMeasure.cpp:66-226 compile against it
+// unchanged; every computation forwards to the sm_100a library through include/rsdsfm.h.
+// Header-only; link with librsdsfm.so.  There is no CPU fallback: without a B200 the first call
+// throws std::runtime_error carrying rsdsfm_last_error().
+#pragma once
+
+#include <cmath>
+#include <cstdlib>
+#include <ctime>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "rs_cv.h"
+#include "rs_eigen.h"
+#include "rsdsfm.h"
+
+namespace rsdsfm_host {
+
+// One context per thread (contexts are independent; a single one is not re-entrant).
+inline rsdsfm_ctx *context()
+{
+    thread_local struct Holder {
+        rsdsfm_ctx *ctx = nullptr;
+        ~Holder() { if (ctx) rsdsfm_destroy(ctx); }
+    } h;
+    if (!h.ctx) {
+        const char *dev = std::getenv("RSDSFM_DEVICE");
+        if (rsdsfm_create(dev ? std::atoi(dev) : 0, nullptr, &h.ctx) != RSDSFM_OK)
+            throw std::runtime_error(std::string("rsdsfm: ") + rsdsfm_last_error(nullptr));
+    }
+    return h.ctx;
+}
+inline void check(int rc, const char *what)
+{
+    if (rc != RSDSFM_OK) throw std::runtime_error(std::string(what) + ": " + rsdsfm_last_error(context()));
+}
+
+}  // namespace rsdsfm_host
+
+// ---------------------------------------------------------------------------- minimal.h:41-76
+struct Velocities {
+    Eigen::Vector3d w;
+    Eigen::Vector3d v;
+    double k;
+    Velocities(Eigen::Vector3d w_init, Eigen::Vector3d v_init) : w(w_init), v(v_init), k(0) {}
+    Velocities(Eigen::Vector3d w_init, Eigen::Vector3d v_init, double k_init) : w(w_init), v(v_init), k(k_init) {}
+};
+
+struct RansacValues {
+    int num_inliers;
+    Eigen::Array3Xd inliers;      // 3 x m: x, y, depth z (= 1 / inverse depth)
+    Eigen::VectorXd beta;
+    Eigen::VectorXd alpha;
+    Eigen::VectorXd alpha_k;
+    Eigen::Vector3d w;
+    Eigen::Vector3d v;
+    double k;
+    RansacValues(int num_inliers_init, Eigen::Array3Xd inliers_init, Eigen::VectorXd beta_init, Eigen::Vector3d w_init,
+                 Eigen::Vector3d v_init)
+        : num_inliers(num_inliers_init), inliers(inliers_init), beta(beta_init), alpha(beta_init), alpha_k(beta_init),
+          w(w_init), v(v_init), k(0) {}
+    RansacValues(int num_inliers_init, Eigen::Array3Xd inliers_init, Eigen::VectorXd alpha_init, Eigen::VectorXd alpha_k_init,
+                 Eigen::Vector3d w_init, Eigen::Vector3d v_init, double k_init)
+        : num_inliers(num_inliers_init), inliers(inliers_init), beta(alpha_init), alpha(alpha_init), alpha_k(alpha_k_init),
+          w(w_init), v(v_init), k(k_init) {}
+};
+
+// ---------------------------------------------------------------------------- nonlinearRefinement.h:77-111
+namespace nonlinear_refinement {
+
+inline Eigen::ArrayXd estimateInverseDepths(const Eigen::Array2Xd &normalized_coordinates, const Eigen::Array2Xd &flow,
+                                            const Eigen::Vector3d &linear_velocity, const Eigen::Vector3d &angular_velocity,
+                                            const double &k, const Eigen::ArrayXd &alpha, const Eigen::ArrayXd &alphaK,
+                                            bool show_messages)
+{
+    const int n = (int)normalized_coordinates.cols();
+    Eigen::ArrayXd out(n);
+    rsdsfm_lm_summary s;
+    rsdsfm_host::check(rsdsfm_estimate_inverse_depths(rsdsfm_host::context(), RSDSFM_HOST, normalized_coordinates.data(), flow.data(),
+                                                      n, linear_velocity.data(), angular_velocity.data(), k, alpha.data(),
+                                                      alphaK.data(), out.data(), &s),
+                       "estimateInverseDepths");
+    if (show_messages)
+        std::cout << std::endl << "LM: iterations " << s.iterations << ", cost " << s.initial_cost << " -> " << s.final_cost
+                  << ", " << s.device_ms * 1e-3 << " s on the GPU" << std::endl;
+    return out;
+}
+
+inline double estimateInverseDepth(const Eigen::Vector2d &normalized_coordinates, const Eigen::Vector3d &linear_velocity,
+                                   const Eigen::Vector3d &angular_velocity, const Eigen::Vector2d &flow, const double &k,
+                                   const double &alpha, const double &alphaK, bool show_messages)
+{
+    Eigen::Array2Xd q(2, 1), u(2, 1);
+    q(0, 0) = normalized_coordinates(0); q(1, 0) = normalized_coordinates(1);
+    u(0, 0) = flow(0); u(1, 0) = flow(1);
+    Eigen::ArrayXd a(1), ak(1);
+    a(0) = alpha; ak(0) = alphaK;
+    return estimateInverseDepths(q, u, linear_velocity, angular_velocity, k, a, ak, show_messages)(0);
+}
+
+// flow: the array the caller has (residual i reads flow(:, i), exactly like nonlinearRefinement.cc:209-212).
+inline RansacValues nonLinearRefinement(const Eigen::Array2Xd &flow, const RansacValues &inliers, bool const_acceleration,
+                                        bool show_messages)
+{
+    const int m = inliers.num_inliers;
+    Eigen::Vector3d v = inliers.v, w = inliers.w;
+    double k = inliers.k;
+    std::vector<double> z((size_t)(m > 0 ? m : 1));
+    rsdsfm_lm_summary s;
+    rsdsfm_host::check(rsdsfm_refine(rsdsfm_host::context(), RSDSFM_HOST, flow.data(), inliers.inliers.data(), inliers.alpha.data(),
+                                     inliers.alpha_k.data(), m, v.data(), w.data(), &k, const_acceleration ? 1 : 0, nullptr, nullptr,
+                                     z.data(), &s),
+                       "nonLinearRefinement");
+    if (show_messages)
+        std::cout << "LM: iterations " << s.iterations << ", cost " << s.initial_cost << " -> " << s.final_cost << ", "
+                  << s.device_ms * 1e-3 << " s on the GPU" << std::endl << std::endl;
+    Eigen::Array3Xd new_inliers = Eigen::Array3Xd::Zero(3, m);
+    for (int i = 0; i < m; ++i) {
+        new_inliers(0, i) = inliers.inliers(0, i);
+        new_inliers(1, i) = inliers.inliers(1, i);
+        new_inliers(2, i) = z[(size_t)i];
+    }
+    return RansacValues(m, new_inliers, inliers.alpha, inliers.alpha_k, w, v, k);
+}
+
+}  // namespace nonlinear_refinement
+
+// ---------------------------------------------------------------------------- minimal.h:91-160
+namespace minimal {
+
+inline Velocities calculateVelocities(const Eigen::Array2Xd &q, const Eigen::Array2Xd &u, const Eigen::ArrayXd &alpha,
+                                      const Eigen::ArrayXd &alpha_k, bool use_alpha_k)
+{
+    double out[7];
+    rsdsfm_solve9(q.data(), u.data(), alpha.data(), alpha_k.data(), use_alpha_k ? 1 : 0, out);
+    return Velocities(Eigen::Vector3d(out[0], out[1], out[2]), Eigen::Vector3d(out[3], out[4], out[5]), out[6]);
+}
+
+inline Eigen::ArrayXd getAlpha(const Eigen::Array2Xd &flow, double h, double gamma)
+{
+    const int n = (int)flow.cols();
+    Eigen::ArrayXd alpha(n);
+    rsdsfm_host::check(rsdsfm_alpha(rsdsfm_host::context(), RSDSFM_HOST, flow.data(), nullptr, n, h, gamma, alpha.data(), nullptr), "getAlpha");
+    return alpha;
+}
+
+inline Eigen::ArrayXd getAlphaK(const Eigen::Array2Xd &q, const Eigen::Array2Xd &flow, double h, double gamma)
+{
+    const int n = (int)q.cols();
+    Eigen::ArrayXd alpha_k(n);
+    rsdsfm_host::check(rsdsfm_alpha(rsdsfm_host::context(), RSDSFM_HOST, flow.data(), q.data(), n, h, gamma, nullptr, alpha_k.data()), "getAlphaK");
+    return alpha_k;
+}
+
+// minimal::ransac with the sample list made explicit (the reference draws it with srand(time)/rand).
+inline RansacValues ransacWithSamples(const Eigen::Array2Xd &q, const Eigen::Array2Xd &u, const Eigen::ArrayXd &alpha,
+                                      const Eigen::ArrayXd &alpha_k, bool use_alpha_k, const std::vector<int32_t> &samples,
+                                      double tolerance, bool show_messages)
+{
+    const int n = (int)q.cols(), H = (int)(samples.size() / 9);
+    std::vector<int> counts((size_t)H);
+    std::vector<double> sumerr((size_t)H), invd((size_t)n);
+    std::vector<uint8_t> mask((size_t)n);
+    int best = -1;
+    double best7[7];
+    rsdsfm_ctx *ctx = rsdsfm_host::context();
+    rsdsfm_host::check(rsdsfm_ransac(ctx, RSDSFM_HOST, q.data(), u.data(), alpha.data(), alpha_k.data(), n, use_alpha_k ? 1 : 0,
+                                     samples.data(), H, tolerance, counts.data(), sumerr.data(), &best, best7, mask.data(),
+                                     invd.data(), nullptr),
+                       "ransac");
+    if (show_messages)
+        for (int i = 0, mx = -1; i < H; ++i) {
+            if (counts[(size_t)i] > mx) mx = counts[(size_t)i];
+            std::cout << "Finished " << i + 1 << " RANSAC trials. The current maximum number of inliers is " << mx << "." << std::endl;
+        }
+    std::vector<double> inl((size_t)3 * n + 3), a((size_t)n + 1), ak((size_t)n + 1);
+    int m = 0;
+    rsdsfm_host::check(rsdsfm_gather_inliers(ctx, RSDSFM_HOST, q.data(), alpha.data(), alpha_k.data(), n, mask.data(), invd.data(),
+                                             inl.data(), a.data(), ak.data(), nullptr, &m),
+                       "ransac (gather)");
+    Eigen::Array3Xd pts = Eigen::Array3Xd::Zero(3, m);
+    Eigen::VectorXd al(m), alk(m);
+    for (int j = 0; j < m; ++j) {
+        pts(0, j) = inl[(size_t)3 * j]; pts(1, j) = inl[(size_t)3 * j + 1]; pts(2, j) = inl[(size_t)3 * j + 2];
+        al(j) = a[(size_t)j]; alk(j) = ak[(size_t)j];
+    }
+    return RansacValues(m, pts, al, alk, Eigen::Vector3d(best7[0], best7[1], best7[2]), Eigen::Vector3d(best7[3], best7[4], best7[5]),
+                        best7[6]);
+}
+
+// Same draw as minimal.cc:226-244: srand(time(NULL)) before every trial, partial Fisher-Yates on a
+// persistent index vector with rand() % n_temp (Q5) -- then all trials are scored in one batch.
+inline RansacValues ransac(const Eigen::Array2Xd &q, const Eigen::Array2Xd &u, const Eigen::ArrayXd &alpha,
+                           const Eigen::ArrayXd &alpha_k, bool use_alpha_k, int iterations, double tolerance, bool show_messages)
+{
+    const int n = (int)q.cols();
+    std::vector<int> indices((size_t)n);
+    for (int i = 0; i < n; ++i) indices[(size_t)i] = i;
+    std::vector<int32_t> samples;
+    for (int i = 0; i < iterations; ++i) {
+        srand((unsigned)time(NULL));
+        int n_temp = n;
+        for (int j = 0; j < 9; ++j) {
+            const int random_choice = rand() % n_temp;
+            std::swap(indices[(size_t)n_temp - 1], indices[(size_t)random_choice]);
+            samples.push_back(indices[(size_t)n_temp - 1]);
+            n_temp--;
+        }
+    }
+    return ransacWithSamples(q, u, alpha, alpha_k, use_alpha_k, samples, tolerance, show_messages);
+}
+inline RansacValues ransac(const Eigen::Array2Xd &q, const Eigen::Array2Xd &u, const Eigen::ArrayXd &alpha, int iterations,
+                           double tolerance, bool show_messages)
+{
+    return ransac(q, u, alpha, alpha, false, iterations, tolerance, show_messages);
+}
+inline RansacValues ransac(const Eigen::Array2Xd &q, const Eigen::Array2Xd &u, const Eigen::ArrayXd &alpha,
+                           const Eigen::ArrayXd &alpha_k, int iterations, double tolerance, bool show_messages)
+{
+    return ransac(q, u, alpha, alpha_k, true, iterations, tolerance, show_messages);
+}
+
+}  // namespace minimal
+
+// ---------------------------------------------------------------------------- scanline.h:30-101
+class Scanline {
+public:
+    Scanline() {}
+    Scanline(const Eigen::Matrix3d &rotation, const Eigen::Vector3d &translation) : rotation_(rotation), translation_(translation) {}
+    const Eigen::Matrix3d &getRotation() const { return rotation_; }
+    const Eigen::Matrix3d &getRelativeRotation() const { return relative_rotation_; }
+    const Eigen::Vector3d &getTranslation() const { return translation_; }
+    const Eigen::Vector3d &getRelativeTranslation() const { return relative_translation_; }
+    void setRotation(const Eigen::Matrix3d &rotation) { rotation_ = rotation; }
+    void setTranslation(const Eigen::Vector3d &translation) { translation_ = translation; }
+    void setRelativeRotation(const Eigen::Matrix3d &rotation) { relative_rotation_ = rotation; }
+    void setRelativeTranslation(const Eigen::Vector3d &translation) { relative_translation_ = translation; }
+
+private:
+    Eigen::Matrix3d rotation_;
+    Eigen::Vector3d translation_;
+    Eigen::Matrix3d relative_rotation_;
+    Eigen::Vector3d relative_translation_;
+};
+
+// ---------------------------------------------------------------------------- rsframe.h:33-315 (hot-path slice)
+class RsFrame {
+public:
+    void setImage(cv::Mat image)
+    {   // rsframe.cc:32-40
+        rows_ = image.rows; cols_ = image.cols; image_ = image;
+        for (int i = 0; i < rows_; ++i) scanlines_.push_back(Scanline());
+    }
+    void setDepthMap(const Eigen::MatrixXd &depth_map) { depth_map_ = depth_map; }
+    void setGsImage(cv::Mat image) { gs_image_ = image; }
+    void setGamma(const double gamma) { gamma_ = gamma; }
+    void setIntrinsics(const Eigen::Matrix3d &intrinsics)
+    {   // rsframe.cc:556-561
+        f_x_ = intrinsics(0, 0); f_y_ = intrinsics(1, 1); c_x_ = intrinsics(0, 2); c_y_ = intrinsics(1, 2);
+    }
+    int getRows() const { return rows_; }
+    int getCols() const { return cols_; }
+    cv::Mat getRsImage() { return image_; }
+    cv::Mat getGsImage() { return gs_image_; }
+    Eigen::MatrixXd getDepthMap() { return depth_map_; }
+    cv::Mat get3dCoordinates() { return coordinates_3d_; }
+    unsigned long getNrScannlines() const { return scanlines_.size(); }
+
+    // rsframe.cc:771-800
+    void setRelativePose(const Eigen::Vector3d &linear_velocity, const Eigen::Vector3d &angular_velocity, const double k)
+    {
+        std::vector<double> R((size_t)9 * rows_), t((size_t)3 * rows_);
+        rsdsfm_set_relative_pose(linear_velocity.data(), angular_velocity.data(), k, gamma_, rows_, R.data(), t.data());
+        for (int i = 0; i < rows_; ++i) {
+            Eigen::Matrix3d Ri;
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Ri(r, c) = R[(size_t)9 * i + 3 * r + c];
+            scanlines_[(size_t)i].setRelativeRotation(Ri);
+            scanlines_[(size_t)i].setRelativeTranslation(Eigen::Vector3d(t[(size_t)3 * i], t[(size_t)3 * i + 1], t[(size_t)3 * i + 2]));
+        }
+    }
+
+    // rsframe.cc:629-736 -- scalar helpers kept on the host (they are not on the per-pixel path here)
+    Eigen::Vector2d spaceToPlane(const Eigen::Vector3d &Point)
+    {
+        return Eigen::Vector2d(Point.x() / Point.z() * f_x_ + c_x_, Point.y() / Point.z() * f_x_ + c_y_);   // y uses f_x (Q12)
+    }
+    Eigen::Vector3d planeToSpace(const Eigen::Vector2d &point, double z_value = 0)
+    {
+        if (z_value == 0) z_value = depth_map_.coeff(int(point.y()), int(point.x()));
+        return Eigen::Vector3d((point.x() - c_x_) * 1.0 / f_x_, (point.y() - c_y_) * 1.0 / f_y_, 1.0) * z_value;
+    }
+    Eigen::Vector3d worldToCameraFrame(const Eigen::Vector3d &Point, const int scanlineNr, bool useRelative = true)
+    {
+        const Scanline &s = scanlines_[(size_t)scanlineNr];
+        const Eigen::Matrix3d &R = useRelative ? s.getRelativeRotation() : s.getRotation();
+        const Eigen::Vector3d &t = useRelative ? s.getRelativeTranslation() : s.getTranslation();
+        return R * Point + t;
+    }
+    Eigen::Vector3d cameraToWorldFrame(const Eigen::Vector3d &Point, const int scanlineNr, bool useRelative = true)
+    {
+        const Scanline &s = scanlines_[(size_t)scanlineNr];
+        const Eigen::Matrix3d Rt = (useRelative ? s.getRelativeRotation() : s.getRotation()).transpose();
+        const Eigen::Vector3d &t = useRelative ? s.getRelativeTranslation() : s.getTranslation();
+        return Rt * Point - Rt * t;
+    }
+
+    // rsframe.cc:803-839 / :842-878
+    void backProject() { backProjectImpl(0); }
+    void backProjectGs() { backProjectImpl(1); }
+
+private:
+    void backProjectImpl(int gs_mode)
+    {
+        std::vector<double> R((size_t)9 * rows_), t((size_t)3 * rows_);
+        for (int i = 0; i < rows_; ++i) {
+            const Eigen::Matrix3d &Ri = scanlines_[(size_t)i].getRelativeRotation();
+            const Eigen::Vector3d &ti = scanlines_[(size_t)i].getRelativeTranslation();
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[(size_t)9 * i + 3 * r + c] = Ri(r, c);
+            for (int a = 0; a < 3; ++a) t[(size_t)3 * i + a] = ti(a);
+        }
+        const double K4[4] = {f_x_, f_y_, c_x_, c_y_};
+        cv::Mat gs_image = image_.clone();
+        cv::Mat coordinates_3d(rows_, cols_, CV_32FC3);
+        rsdsfm_host::check(rsdsfm_backproject(rsdsfm_host::context(), RSDSFM_HOST, image_.data, depth_map_.data(), RSDSFM_DEPTH_COLMAJOR,
+                                              rows_, cols_, K4, R.data(), t.data(), gs_mode, gs_image.data,
+                                              reinterpret_cast<float *>(coordinates_3d.data)),
+                           "backProject");
+        coordinates_3d_ = coordinates_3d;       // rsframe.cc:837-838: both members are replaced (Q20)
+        gs_image_ = gs_image;
+    }
+
+    int rows_ = 0, cols_ = 0;
+    double f_x_ = 0, f_y_ = 0, c_x_ = 0, c_y_ = 0, gamma_ = 0;
+    cv::Mat image_, gs_image_, coordinates_3d_;
+    Eigen::MatrixXd depth_map_;
+    std::vector<Scanline> scanlines_;
+};
+
+// ---------------------------------------------------------------------------- camera.h:33-340 (hot-path slice)
+class Camera {
+public:
+    Eigen::Matrix3d getIntrinsics() { return K_; }
+    void addFrameReal(cv::Mat rs_image)
+    {   // camera.cc:39-46
+        RsFrame frame;
+        frame.setIntrinsics(K_);
+        frame.setImage(rs_image);
+        frames_.push_back(frame);
+    }
+    void setIntrinsics(const Eigen::Matrix3d &intrinsics) { K_ = intrinsics; }
+    // camera.cc:179-206: the five hard-coded phone calibrations
+    void setIntrinsics(const std::string source_camera)
+    {
+        double fx = 0, fy = 0, cx = 0, cy = 0;
+        if (source_camera == "iphone") { fx = 1505.1283359786307; fy = 1513.7789208311444; cx = 657.81734686405991; cy = 349.91807538147589; }
+        else if (source_camera == "galaxy_stabil") { fx = 1803.29785922382; fy = 1799.35406531529; cx = 945.304708272490; cy = 544.684292978344; }
+        else if (source_camera == "galaxy") { fx = 1492.41306997746; fy = 1491.09286590722; cx = 949.571146410704; cy = 554.675409391795; }
+        else if (source_camera == "galaxy_old") { fx = 3154.53208221173; fy = 3152.28696217577; cx = 1969.87107268891; cy = 1521.27056048818; }
+        else if (source_camera == "galaxy_vga") { fx = 484.450845764569; fy = 485.345469134313; cx = 313.442094604855; cy = 241.383116350144; }
+        else std::cerr << "No valid source camera specified";
+        Eigen::Matrix3d K;
+        K(0, 0) = fx; K(1, 1) = fy; K(0, 2) = cx; K(1, 2) = cy; K(2, 2) = 1.0;
+        K_ = K;
+    }
+    RsFrame getFrame(const int frameNr) { return frames_[(size_t)frameNr - 1]; }          // 1-based, deep copy
+    void setPose(const int frameNr, const double k, const Eigen::Vector3d &linear_velocity, const Eigen::Vector3d &angular_velocity)
+    {
+        frames_[(size_t)frameNr - 1].setRelativePose(linear_velocity, angular_velocity, k);
+    }
+    void setGamma(const double gamma) { for (auto &f : frames_) f.setGamma(gamma); }
+    void backProject(const int frameNr) { frames_[(size_t)frameNr - 1].backProject(); }
+    void backProjectGs(const int frameNr) { frames_[(size_t)frameNr - 1].backProjectGs(); }
+    void setDepthMap(const int frameNr, Eigen::MatrixXd depth_map) { frames_[(size_t)frameNr - 1].setDepthMap(depth_map); }
+
+    // camera.cc:253-277 computes DeepFlow with OpenCV's optflow module; flow production is upstream
+    // of this path (both sides consume a cached flow field), so the flow is attached instead.
+    void setCachedFlow(const cv::Mat_<cv::Point_<double>> &flow) { cached_flow_ = flow; }
+    cv::Mat_<cv::Point_<double>> calculateDeepFlow(const int, const int) { return cached_flow_; }
+    cv::Mat_<cv::Point_<double>> calculateTrueFlow(const int, const int) { return cached_flow_; }
+
+    // camera.cc:753-774
+    cv::Mat interpolateCrackyImage(cv::Mat image_in, const unsigned offset)
+    {
+        cv::Mat image_out = image_in.clone();
+        rsdsfm_host::check(rsdsfm_fill_cracks(rsdsfm_host::context(), RSDSFM_HOST, image_in.data, image_in.rows, image_in.cols, offset,
+                                              image_out.data),
+                           "interpolateCrackyImage");
+        return image_out;
+    }
+
+private:
+    std::vector<RsFrame> frames_;
+    Eigen::Matrix3d K_;
+    cv::Mat_<cv::Point_<double>> cached_flow_;
+};
+
+// ---------------------------------------------------------------------------- errorMeasure.h:18-64
+namespace error_measure {
+
+struct TrueValues {
+    Eigen::Vector3d v, w;
+    double k;
+    TrueValues(Eigen::Vector3d v_init, Eigen::Vector3d w_init, double k_init) : v(v_init), w(w_init), k(k_init) {}
+};
+
+struct VelocityErrors {
+    std::vector<Eigen::Vector3d> w, v;          // per evaluation
+    Eigen::ArrayXd k, mean_error, v_error, w_error;   // stored as ArrayXd (Q23)
+    double average_w_error = 0, average_v_error = 0, average_mean_error = 0;
+};
+
+// The flatten + normalise glue both reference drivers share (main.cc:398-432, errorMeasure.cpp:66-97).
+struct Flattened {
+    Eigen::Matrix2Xd coord, flow, coord_pixel, flow_pixel;
+    int n = 0;
+};
+inline Flattened flattenFlow(const cv::Mat_<cv::Point_<double>> &flow_image, const Eigen::Matrix3d &K, double gamma,
+                             double flow_threshold, bool truncate)
+{
+    const int rows = flow_image.rows, cols = flow_image.cols;
+    Flattened F;
+    F.coord = Eigen::Matrix2Xd(2, (std::ptrdiff_t)rows * cols); F.flow = F.coord; F.coord_pixel = F.coord; F.flow_pixel = F.coord;
+    const double K4[4] = {K(0, 0), K(1, 1), K(0, 2), K(1, 2)};
+    rsdsfm_host::check(rsdsfm_flatten(rsdsfm_host::context(), RSDSFM_HOST, reinterpret_cast<const double *>(flow_image.data), rows, cols,
+                                      K4, gamma, flow_threshold, F.coord.data(), F.flow.data(), F.coord_pixel.data(),
+                                      F.flow_pixel.data(), nullptr, &F.n),
+                       "flatten");
+    if (truncate) { F.coord.conservativeResize(2, F.n); F.flow.conservativeResize(2, F.n); }   // errorMeasure.cpp:96-97
+    return F;
+}
+
+// errorMeasure.cpp:41-254 with the GT reprojection metric (section 8f, not on the hot path) left out:
+// mean_error entries are NaN.
+inline VelocityErrors evaluateVelocities(Camera camera, TrueValues true_values, double gamma, int ransac_trials, int num_evaluations,
+                                         bool use_deep_flow, bool constant_acceleration, bool global_shutter,
+                                         bool optimize_results, bool show_messages, std::string /*image_path*/)
+{
+    const double THRESHOLD_FLOW = 0.0000000001, TOL_RANSAC = 0.05;
+    cv::Mat_<cv::Point_<double>> flow_image = use_deep_flow ? camera.calculateDeepFlow(1, 2) : camera.calculateTrueFlow(1, 2);
+    const int rows = flow_image.rows, cols = flow_image.cols;
+    Eigen::Matrix3d K = camera.getIntrinsics();
+    const double f_x = K(0, 0), f_y = K(1, 1), c_x = K(0, 2), c_y = K(1, 2);
+    camera.setGamma(gamma);
+    Flattened F = flattenFlow(flow_image, K, gamma, THRESHOLD_FLOW, true);
+    Eigen::ArrayXd alpha = minimal::getAlpha(F.flow_pixel, rows, gamma);
+    Eigen::ArrayXd alphaK = minimal::getAlphaK(F.coord_pixel, F.flow_pixel, rows, gamma);
+    if (global_shutter) { alpha *= 0; alpha += 1; constant_acceleration = false; }
+    VelocityErrors E;
+    E.k = Eigen::ArrayXd::Zero(num_evaluations); E.mean_error = E.k; E.v_error = E.k; E.w_error = E.k;
+    const double true_v_norm = true_values.v.norm();
+    for (int eval_num = 0; eval_num < num_evaluations; eval_num++) {
+        RansacValues ransac_results = minimal::ransac(F.coord, F.flow, alpha, alphaK, constant_acceleration, ransac_trials, TOL_RANSAC, show_messages);
+        RansacValues results = ransac_results;
+        if (optimize_results) results = nonlinear_refinement::nonLinearRefinement(F.flow, ransac_results, constant_acceleration, show_messages);
+        double z_count = 0;
+        for (int i = 0; i < results.num_inliers; i++) z_count += results.inliers(2, i);
+        if (z_count * 1.0 / results.num_inliers < 0) { results.inliers.row(2) *= -1.0; results.v *= -1.0; }
+        E.w.push_back(results.w); E.v.push_back(results.v); E.k(eval_num) = results.k;
+        // rotation error |vee(R_est R_true^T)|, translation angle (errorMeasure.cpp:173-186)
+        auto rot = [](const Eigen::Vector3d &w) {
+            Eigen::Matrix3d R = Eigen::Matrix3d::Identity();
+            R(0, 1) = -w(2); R(0, 2) = w(1); R(1, 0) = w(2); R(1, 2) = -w(0); R(2, 0) = -w(1); R(2, 1) = w(0);
+            return R;
+        };
+        const Eigen::Matrix3d Re = rot(results.w), Rt = rot(true_values.w).transpose();
+        auto mm = [&](int r, int c) { return Re(r, 0) * Rt(0, c) + Re(r, 1) * Rt(1, c) + Re(r, 2) * Rt(2, c); };
+        E.w_error(eval_num) = Eigen::Vector3d(mm(2, 1), mm(0, 2), mm(1, 0)).norm();
+        E.v_error(eval_num) = std::acos(results.v.dot(true_values.v) / (results.v.norm() * true_v_norm));
+        Eigen::MatrixXd depth_map = Eigen::MatrixXd::Zero(rows, cols);
+        for (int i = 0; i < results.num_inliers; i++) {
+            const int x = int(f_x * results.inliers(0, i) + c_x + 0.5), y = int(f_y * results.inliers(1, i) + c_y + 0.5);
+            if (x >= 0 && x < cols && y >= 0 && y < rows) depth_map(y, x) = results.inliers(2, i);
+        }
+        camera.setPose(1, results.k, results.v, results.w);
+        camera.setDepthMap(1, depth_map);
+        if (global_shutter) camera.backProjectGs(1); else camera.backProject(1);
+        E.mean_error(eval_num) = std::nan("");
+    }
+    E.average_v_error = E.v_error.mean(); E.average_w_error = E.w_error.mean(); E.average_mean_error = std::nan("");
+    return E;
+}
+
+}  // namespace error_measure

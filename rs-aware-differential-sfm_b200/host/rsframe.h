@@ -1,0 +1,3 @@
+// rsframe.h -- same header name as the reference's src/rsframe.h: the declarations live in rsdsfm_host.h.
+#pragma once
+#include "rsdsfm_host.h"

@@ -236,3 +236,23 @@ def test_refine_rectify_pair(ctx, oracle, case_cv, case_ca, which):
     _depth_close(got["depth_map"][nz], ref["depth_map"][nz])
     diff = np.abs(got["rectified"].astype(np.int32) - ref["rectified"].astype(np.int32)).max(axis=2)
     assert (diff <= 1).mean() >= 0.999, "rectified image: %.5f of pixels within 1 grey level" % (diff <= 1).mean()
+
+
+# ---------------------------------------------------------------------------- C++ host shim (reference class surface)
+def test_cpp_host_shim_single_run(capi):
+    """Builds rs-aware-differential-sfm_b200/host/example_single_run.cc (the glue of main.cc:398-523
+    written against Camera / minimal::ransac / nonLinearRefinement / interpolateCrackyImage) with g++,
+    links it with librsdsfm.so and runs it: exact constant-velocity data must give back w and the
+    direction of v."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "rs-aware-differential-sfm_b200", "host")
+    exe = os.path.join(host, "example_single_run")
+    cmd = ["g++", "-std=c++17", "-O2", "-I", os.path.join(root, "include"), "-I", host, os.path.join(host, "example_single_run.cc"),
+           "-L", os.path.dirname(capi.LIB_PATH), "-lrsdsfm", "-Wl,-rpath," + os.path.dirname(capi.LIB_PATH), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rectified image" in r.stdout
