@@ -16,20 +16,29 @@
 
 namespace rsdsfm {
 
-// out[j] = reduce over CTA rows b of partials[b*(ns+nm)+j]; sums in ascending row order
-__global__ void k_final_reduce(const double *__restrict__ partials, int nblocks, int ns, int nm, double *out)
+// out[j] = reduce over CTA rows b of partials[b*(ns+nm)+j] for up to 8 columns: warp c handles
+// column c; lane l combines rows l, l+32, ... in ascending order, then a butterfly over the lanes
+// (fixed order => bit-reproducible for a given number of rows).
+__global__ void __launch_bounds__(256) k_final_reduce(const double *__restrict__ partials, int nblocks, int ns, int nm, double *out)
 {
-    const int j = threadIdx.x;
-    if (j >= ns + nm) return;
-    double v = partials[j];
-    if (j < ns) for (int b = 1; b < nblocks; ++b) v += partials[(size_t)b * (ns + nm) + j];
-    else        for (int b = 1; b < nblocks; ++b) v = fmax(v, partials[(size_t)b * (ns + nm) + j]);
-    out[j] = v;
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31, nv = ns + nm;
+    if (c >= nv) return;
+    const bool is_sum = c < ns;
+    double v = is_sum ? 0.0 : -INFINITY;
+    for (int b = lane; b < nblocks; b += 32) {
+        const double x = partials[(size_t)b * nv + c];
+        v = is_sum ? v + x : fmax(v, x);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double y = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_sum ? v + y : fmax(v, y);
+    }
+    if (lane == 0) out[c] = v;
 }
 
 void launch_final_reduce(rsdsfm_ctx *ctx, const double *partials, int nblocks, int ns, int nm, double *out)
 {
-    k_final_reduce<<<1, 64, 0, ctx->stream>>>(partials, nblocks, ns, nm, out);
+    k_final_reduce<<<1, 256, 0, ctx->stream>>>(partials, nblocks, ns, nm, out);   // ns + nm <= 8
     ctx->launches++;
 }
 

@@ -50,7 +50,7 @@ struct ExcEntry {            // a pixel whose LM diagonal is (possibly) clamped,
 
 // Broadcast block: written by the controller CTA, read by every CTA at the start of a phase.
 struct Bcast {
-    int next, which_x, first, pad0;
+    int next, which_x, first, cur_list;   // cur_list: which exception list belongs to the current point
     Motion mot, cand;
     double delta_f[kMaxNF];
     double radius;
@@ -67,7 +67,7 @@ struct LmShared {
     unsigned long long t_phase[12];
     // ---- grid synchronisation
     unsigned int arrive, generation;
-    unsigned int n_exc, exc_overflow;
+    unsigned int n_exc[2], exc_overflow, pad1;   // two exception lists: current point / speculative candidate
     int error;
     int nonfinite_input;     // LAST field: raised by the gather kernel, preserved by the control-block upload
 };
@@ -169,7 +169,7 @@ __device__ __forceinline__ void fence_proxy_async()
 }
 
 struct PhaseParams {           // shared-memory copy of the broadcast block (+ options, start point)
-    int next, which_x, first, pad0;
+    int next, which_x, first, cur_list;
     Motion mot, cand;
     double delta_f[kMaxNF];
     double radius;
@@ -180,7 +180,7 @@ struct PhaseParams {           // shared-memory copy of the broadcast block (+ o
 };
 static_assert(offsetof(PhaseParams, ee_fast_min) == offsetof(Bcast, ee_fast_min), "PhaseParams must start with Bcast");
 
-constexpr int kStages = 5;                      // tiles in flight per CTA (5 x 28 KB)
+constexpr int kStages = 7;                      // tiles in flight per CTA (7 x 28 KB of the 227 KB shared memory)
 struct Stage {
     double2 xy[kTile], uu[kTile], aa[kTile];
     double d[kTile];
@@ -193,56 +193,47 @@ struct Loaded {
 };
 
 // ------------------------------------------------------------------------------------------
-// Pass A layout: NS = 2 + 2*TRI + 2*NF sums (cost2, sum d^2, G1, G2, h1, h2), NM = 3 maxima
+// Per-thread accumulator layout.  Sums: [0] sum r^2 and [1] sum d^2 at the evaluation point,
+// G1, G2 (packed upper triangles), h1, h2, then the candidate-step sums mcc and |step|^2.
+// Maxima (all >= 0): max|e^T r|, bad evaluation, max e^Te, bad step, bad residual.
 // ------------------------------------------------------------------------------------------
 template <int NF>
-struct PassA {
+struct Acc {
     static constexpr int TRI = NF * (NF + 1) / 2;
-    static constexpr int oG1 = 2, oG2 = oG1 + TRI, oH1 = oG2 + TRI, oH2 = oH1 + NF;
-    static constexpr int NS = oH2 + NF, NM = 3, NV = NS + NM;
-    static constexpr int iGMAX = NS, iBAD = NS + 1, iEEMAX = NS + 2;
+    static constexpr int oG1 = 2, oG2 = oG1 + TRI, oH1 = oG2 + TRI, oH2 = oH1 + NF, oMCC = oH2 + NF, oSTEP = oMCC + 1;
+    static constexpr int NS = oSTEP + 1, NM = 5, NV = NS + NM;
+    static constexpr int iGMAX = NS, iBAD = NS + 1, iEEMAX = NS + 2, iBADSTEP = NS + 3, iBADRES = NS + 4;
 };
-constexpr int kNB = 5;                          // pass B: 3 sums (mcc, step^2, cost2) + 2 maxima
+constexpr int kExcVals = kTri + kMaxNF;          // exception sums: S triangle + rhs
+template <int NF> constexpr int kRowVals = (Acc<NF>::NV > kExcVals) ? Acc<NF>::NV : kExcVals;
+static_assert(kRowVals<7> <= 96, "the final reduce covers three 32-lane column chunks");
 
-template <int NF> constexpr int red_rows()
-{   // rows of the shared reduction scratch: pass A values, pass B values, exception sums
-    int r = PassA<NF>::NV;
-    if (r < kNB) r = kNB;
-    if (NF > 0 && r < kTri + kMaxNF) r = kTri + kMaxNF;
-    return r;
-}
-template <int NF> constexpr int kRedRows = red_rows<NF>();
-template <int NF> constexpr size_t smem_bytes()
-{
-    size_t a = sizeof(double) * (size_t)kRedRows<NF> * kThreads, b = sizeof(Stage) * (size_t)kStages;
-    return a > b ? a : b;
-}
-
-// NV values per thread (first NS sums, then NM maxima, all maxima >= 0) -> one row of NV doubles.
-// red: shared scratch of NV * kThreads doubles.  Fixed order => bit-reproducible.
-template <int NS, int NM>
-__device__ __forceinline__ void cta_reduce(const double (&v)[NS + NM], double *red, double *row)
+// NV values per thread (first NS sums, then maxima >= 0) -> one row of NV doubles: butterfly
+// shuffles inside each warp, then the 8 warp results are combined in warp order.  No large
+// shared scratch (the TMA ring owns the dynamic shared memory); fixed order => bit-reproducible.
+template <int NS, int NM, int LD>
+__device__ __forceinline__ void cta_reduce(const double (&v)[NS + NM], double (*wpart)[LD], double *row)
 {
     constexpr int NV = NS + NM;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) red[j * kThreads + tid] = v[j];
-    __syncthreads();
-    for (int j = warp; j < NV; j += kWarps) {
-        const double *c = red + j * kThreads + lane;
-        double s = c[0];
+    for (int j = 0; j < NV; ++j) {
+        double x = v[j];
         if (j < NS) {
 #pragma unroll
-            for (int k = 1; k < kWarps; ++k) s += c[32 * k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         } else {
 #pragma unroll
-            for (int k = 1; k < kWarps; ++k) s = fmax(s, c[32 * k]);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
+            for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
         }
-        if (lane == 0) row[j] = s;
+        if (lane == 0) wpart[warp][j] = x;
+    }
+    __syncthreads();
+    if (tid < NV) {
+        double x = wpart[0][tid];
+        if (tid < NS) { for (int w = 1; w < kWarps; ++w) x += wpart[w][tid]; }
+        else          { for (int w = 1; w < kWarps; ++w) x = fmax(x, wpart[w][tid]); }
+        row[tid] = x;
     }
     __syncthreads();
 }
@@ -270,7 +261,7 @@ __device__ __forceinline__ double depth_scale_at_start(const Loaded &L, const Mo
     return 1.0 / (1.0 + sqrt(fma(s0, s0, s1 * s1)));
 }
 
-// Common per-pixel quantities of both passes at the point (mot, d).
+// Common per-pixel quantities at the point (m, d).
 struct PxEval {
     double x, y, xy, xx1, yy1, ak, beta, p0, p1, r0, r1, e0, e1, ee;
 };
@@ -289,21 +280,22 @@ __device__ __forceinline__ void px_eval(const Loaded &L, const Motion &m, double
     E.ee = fma(E.e0, E.e0, E.e1 * E.e1);
 }
 
-// Rare path of pass A: a pixel whose LM diagonal may be clamped (|e| ~ 0, focus of expansion) or
-// whose values are not finite.  F^TF / F^Tr go to G1 / h1; the radius-dependent term
-// q (F^Te)(e^TF) is applied by the controller from the exception list.
+// Rare path of the evaluation: a pixel whose LM diagonal may be clamped (|e| ~ 0, focus of
+// expansion) or whose values are not finite.  F^TF / F^Tr go to G1 / h1; the radius-dependent
+// term q (F^Te)(e^TF) is applied by the controller from the exception list.
 template <int NF>
-__device__ __forceinline__ void pass_a_slow(const Loaded &L, const PhaseParams &P, double c2, double (&acc)[PassA<NF>::NV],
-                                         LmShared *sh, ExcEntry *exc, unsigned int exc_cap)
+__device__ __forceinline__ void eval_slow(const Loaded &L, double d, const Motion &mot, double c2, bool first, const Motion &base,
+                                          double (&acc)[Acc<NF>::NV], unsigned int *n_exc, unsigned int *overflow, ExcEntry *exc,
+                                          unsigned int exc_cap)
 {
-    using A = PassA<NF>;
+    using A = Acc<NF>;
     PxEval E;
-    px_eval(L, P.mot, c2, L.d, E);
+    px_eval(L, mot, c2, d, E);
     const double dbeta = (NF == 7) ? c2 * fma(-E.ak, 0.5 * c2, L.a.y) : 0.0;
-    const double se = P.first ? 1.0 / (1.0 + sqrt(E.ee)) : depth_scale_at_start(L, P.base);
+    const double se = first ? 1.0 / (1.0 + sqrt(E.ee)) : depth_scale_at_start(L, base);
     double F0[NF > 0 ? NF : 1], F1[NF > 0 ? NF : 1], fe[NF > 0 ? NF : 1];
-    ft_times<NF>(E.beta, dbeta, L.d, E.x, E.y, E.xy, E.xx1, E.yy1, E.p0, E.p1, 1.0, 0.0, F0);
-    ft_times<NF>(E.beta, dbeta, L.d, E.x, E.y, E.xy, E.xx1, E.yy1, E.p0, E.p1, 0.0, 1.0, F1);
+    ft_times<NF>(E.beta, dbeta, d, E.x, E.y, E.xy, E.xx1, E.yy1, E.p0, E.p1, 1.0, 0.0, F0);
+    ft_times<NF>(E.beta, dbeta, d, E.x, E.y, E.xy, E.xx1, E.yy1, E.p0, E.p1, 0.0, 1.0, F1);
     double bad = 0.0;
     int t = 0;
 #pragma unroll
@@ -315,7 +307,7 @@ __device__ __forceinline__ void pass_a_slow(const Loaded &L, const PhaseParams &
         for (int c = j; c < NF; ++c, ++t) acc[A::oG1 + t] += fma(F0[j], F0[c], F1[j] * F1[c]);
     }
     acc[A::iBAD] = fmax(acc[A::iBAD], bad);
-    const unsigned int slot = atomicAdd(&sh->n_exc, 1u);
+    const unsigned int slot = atomicAdd(n_exc, 1u);
     if (slot < exc_cap) {
         ExcEntry X;
         X.ees = E.ee * se * se; X.se2 = se * se; X.er = fma(E.e0, E.r0, E.e1 * E.r1);
@@ -323,24 +315,26 @@ __device__ __forceinline__ void pass_a_slow(const Loaded &L, const PhaseParams &
         for (int j = 0; j < kMaxNF; ++j) X.fe[j] = (j < NF) ? fe[j] : 0.0;
         exc[slot] = X;
     } else {
-        sh->exc_overflow = 1u;
+        *overflow = 1u;
     }
 }
 
-// Pass A on TWO residual blocks per thread: every stage of the computation is written for both
-// pixels side by side (no branches on the common path) so the two dependency chains interleave.
+// Evaluation (residual, Jacobian, Schur factors) of TWO residual blocks per thread at the point
+// (mot, d[p]): every stage is written for both pixels side by side, branch-free on the common
+// path, so the two dependency chains interleave.
 template <int NF>
-__device__ __forceinline__ void pass_a_pair(const Loaded (&L)[2], const bool (&valid)[2], const PhaseParams &P, double c2,
-                                            double (&acc)[PassA<NF>::NV], LmShared *sh, ExcEntry *exc, unsigned int exc_cap)
+__device__ __forceinline__ void eval_pair(const Loaded (&L)[2], const double (&dv)[2], const bool (&valid)[2], const Motion &mot,
+                                          double c2, bool first, const PhaseParams &P, double (&acc)[Acc<NF>::NV],
+                                          unsigned int *n_exc, unsigned int *overflow, ExcEntry *exc, unsigned int exc_cap)
 {
-    using A = PassA<NF>;
+    using A = Acc<NF>;
     PxEval E[2];
     double d[2], re[2], rn[2], mu[2];
-    bool slow[2];
+    bool slow[2] = {false, false};
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
-        d[p] = L[p].d;
-        px_eval(L[p], P.mot, c2, d[p], E[p]);
+        d[p] = dv[p];
+        px_eval(L[p], mot, c2, d[p], E[p]);
         if (!valid[p]) { E[p].r0 = 0.0; E[p].r1 = 0.0; E[p].e0 = 0.0; E[p].e1 = 0.0; E[p].ee = 0.0; d[p] = 0.0; }
     }
 #pragma unroll
@@ -351,7 +345,9 @@ __device__ __forceinline__ void pass_a_pair(const Loaded (&L)[2], const bool (&v
         rn[p] = fma(-E[p].e1, E[p].r0, E[p].e0 * E[p].r1);              // n^T r, n = (-e1, e0)
         acc[A::iGMAX] = fmax(acc[A::iGMAX], fabs(re[p]));
         acc[A::iEEMAX] = fmax(acc[A::iEEMAX], E[p].ee);
-        acc[A::iBAD] = fmax(acc[A::iBAD], bad_flag(E[p].r0 + E[p].r1 + E[p].ee));
+        const double br = bad_flag(E[p].r0 + E[p].r1);
+        acc[A::iBADRES] = fmax(acc[A::iBADRES], br);
+        acc[A::iBAD] = fmax(acc[A::iBAD], br + bad_flag(E[p].ee));
     }
     if (NF > 0) {
 #pragma unroll
@@ -359,7 +355,7 @@ __device__ __forceinline__ void pass_a_pair(const Loaded (&L)[2], const bool (&v
             // is the LM diagonal of this depth certainly not clamped?  (first evaluation: the Jacobi
             // scale is 1/(1+|e|) of this very point; later: global lower bound of the scales)
             bool fast;
-            if (P.first) {
+            if (first) {
                 const double se = 1.0 / (1.0 + sqrt(E[p].ee));
                 const double ees = E[p].ee * se * se;
                 fast = (ees >= P.min_diag && ees <= P.max_diag);
@@ -400,17 +396,19 @@ __device__ __forceinline__ void pass_a_pair(const Loaded (&L)[2], const bool (&v
         if (slow[0] || slow[1]) {
 #pragma unroll
             for (int p = 0; p < 2; ++p)
-                if (slow[p]) pass_a_slow<NF>(L[p], P, c2, acc, sh, exc, exc_cap);
+                if (slow[p]) eval_slow<NF>(L[p], dv[p], mot, c2, first, P.base, acc, n_exc, overflow, exc, exc_cap);
         }
     }
 }
 
-// Pass B on two residual blocks per thread.
+// Candidate step of two residual blocks at the current point: depth back-substitution
+// delta_d = -q e^T (r + F delta_f), model cost change, |step|^2; returns the candidate depths.
 template <int NF>
-__device__ __forceinline__ void pass_b_pair(const Loaded (&L)[2], const bool (&valid)[2], const int (&idx)[2],
-                                            const PhaseParams &P, double c2, double c2c, double rfac, double inv_radius,
-                                            double (&acc)[kNB], double *__restrict__ d_cand)
+__device__ __forceinline__ void step_pair(const Loaded (&L)[2], const bool (&valid)[2], const int (&idx)[2], const PhaseParams &P,
+                                          double c2, double rfac, double inv_radius, double (&acc)[Acc<NF>::NV],
+                                          double *__restrict__ d_cand, double (&dc)[2])
 {
+    using A = Acc<NF>;
     PxEval E[2];
     double q[2], m0[2], m1[2];
 #pragma unroll
@@ -447,29 +445,25 @@ __device__ __forceinline__ void pass_b_pair(const Loaded (&L)[2], const bool (&v
     for (int p = 0; p < 2; ++p) {
         const double delta_e = -q[p] * fma(E[p].e0, E[p].r0 + m0[p], E[p].e1 * (E[p].r1 + m1[p]));
         const double j0 = fma(E[p].e0, delta_e, m0[p]), j1 = fma(E[p].e1, delta_e, m1[p]);      // J delta
-        const double dc = L[p].d + delta_e;
-        const double dd = L[p].d - dc;
-        // candidate residual
-        const Motion &c = P.cand;
-        const double betac = c2c * fma(c.k, L[p].a.y, L[p].a.x);
-        const double ca0 = fma(-E[p].x, c.v[2], c.v[0]), ca1 = fma(-E[p].y, c.v[2], c.v[1]);
-        const double cb0 = fma(-E[p].xy, c.w[0], fma(E[p].xx1, c.w[1], -E[p].y * c.w[2]));
-        const double cb1 = fma(-E[p].yy1, c.w[0], fma(E[p].xy, c.w[1], E[p].x * c.w[2]));
-        const double s0 = fma(-betac, fma(dc, ca0, cb0), L[p].u.x), s1 = fma(-betac, fma(dc, ca1, cb1), L[p].u.y);
+        dc[p] = L[p].d + delta_e;
+        const double dd = L[p].d - dc[p];
         if (valid[p]) {
-            d_cand[idx[p]] = dc;
-            acc[0] += fma(j0, fma(0.5, j0, E[p].r0), j1 * fma(0.5, j1, E[p].r1));
-            acc[1] = fma(dd, dd, acc[1]);
-            acc[2] = fma(s0, s0, fma(s1, s1, acc[2]));
-            acc[3] = fmax(acc[3], bad_flag(delta_e));
-            acc[4] = fmax(acc[4], bad_flag(s0 + s1));
+            d_cand[idx[p]] = dc[p];
+            acc[A::oMCC] += fma(j0, fma(0.5, j0, E[p].r0), j1 * fma(0.5, j1, E[p].r1));
+            acc[A::oSTEP] = fma(dd, dd, acc[A::oSTEP]);
+            acc[A::iBADSTEP] = fmax(acc[A::iBADSTEP], bad_flag(delta_e));
+        } else {
+            dc[p] = 1.0;
         }
     }
 }
 
-
 // ------------------------------------------------------------------------------------------
-// The persistent kernel
+// The persistent kernel.  Phases: one INIT pass (evaluation at the start point), then one FUSED
+// pass per LM iteration: the candidate step at x (back substitution, model cost change) and,
+// speculatively, the complete evaluation at the candidate.  If the controller accepts the step the
+// speculative sums ARE the next iteration's system; if it rejects, it re-solves from the stored
+// radius-independent factors at a smaller radius -- either way the next phase is another FUSED pass.
 // ------------------------------------------------------------------------------------------
 constexpr unsigned long long kWatchdogNs = 4000000000ull;   // 4 s: a stuck grid barrier aborts the solve
 
@@ -487,17 +481,17 @@ __global__ void __launch_bounds__(kThreads, 1)
 k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *partials, ExcEntry *exc, unsigned int exc_cap,
                 const double *z_in, int z_stride, double *out, int invert_out)
 {
-    using A = PassA<NF>;
+    using A = Acc<NF>;
+    constexpr int LD = kRowVals<NF>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *red = reinterpret_cast<double *>(smem_raw);           // kRedRows<NF> * kThreads doubles, aliases the stages
     Stage *stages = reinterpret_cast<Stage *>(smem_raw);
     __shared__ __align__(8) uint64_t full[kStages];
     __shared__ PhaseParams P;
     __shared__ LmController s_ctl;
-    __shared__ double fin[kRedRows<NF>];
-    __shared__ double part[kWarps][kRedRows<NF>];
+    __shared__ double fin[LD];
+    __shared__ double part[kWarps][LD];
     __shared__ ExcSums s_exc;
-    __shared__ int s_flag[4];                                     // [0] is_last, [1] next, [2] n_exc
+    __shared__ int s_flag[6];                                     // [0] is_last, [1] next, [2] n_exc, [3] accepted, [4] cur_list
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x;
@@ -524,15 +518,19 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
         }
         __syncthreads();
         if (P.next == LM_DONE || P.error) break;
-        const bool run_a = (P.next == LM_RUN_A);
+        const bool run_init = (P.next == LM_RUN_A);
         double *dx = P.which_x ? d1 : d0;
         double *dcand = P.which_x ? d0 : d1;
         double *row = partials + (size_t)blockIdx.x * A::NV;
+        // exceptions of the evaluation point go to the current list (INIT) or to the speculative one (FUSED)
+        const int elist = run_init ? P.cur_list : (P.cur_list ^ 1);
+        unsigned int *n_exc = &sh->n_exc[elist];
+        ExcEntry *elist_p = exc + (size_t)elist * exc_cap;
         const unsigned long long t_begin = (blockIdx.x == 0 && tid == 0) ? globaltimer() : 0ull;
 
         // ---- prologue: fill the ring
         if (tid == 0) {
-            fence_proxy_async();                                   // the scratch was written through the generic proxy
+            fence_proxy_async();
             const int pre = n_my < kStages ? n_my : kStages;
             for (int k = 0; k < pre; ++k) {
                 const unsigned g = consumed + (unsigned)k;
@@ -540,10 +538,9 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
             }
         }
 
-        double accA[A::NV];
-        double accB[kNB] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        double acc[A::NV];
 #pragma unroll
-        for (int j = 0; j < A::NV; ++j) accA[j] = 0.0;
+        for (int j = 0; j < A::NV; ++j) acc[j] = 0.0;
         const double c2 = 2.0 / (2.0 + P.mot.k), c2c = 2.0 / (2.0 + P.cand.k);
         const double rfac = P.radius / (P.radius + 1.0), inv_radius = 1.0 / P.radius;
 
@@ -572,17 +569,22 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
                 fence_proxy_async();
                 issue_tile(D, dx, (int)blockIdx.x + (k + kStages) * G, &stages[s], &full[s]);
             }
-            if (run_a) pass_a_pair<NF>(L, valid, P, c2, accA, sh, exc, exc_cap);
-            else pass_b_pair<NF>(L, valid, idx, P, c2, c2c, rfac, inv_radius, accB, dcand);
+            if (run_init) {
+                const double dv[2] = {L[0].d, L[1].d};
+                eval_pair<NF>(L, dv, valid, P.mot, c2, P.first != 0, P, acc, n_exc, &sh->exc_overflow, elist_p, exc_cap);
+            } else {
+                double dc[2];
+                step_pair<NF>(L, valid, idx, P, c2, rfac, inv_radius, acc, dcand, dc);
+                eval_pair<NF>(L, dc, valid, P.cand, c2c, false, P, acc, n_exc, &sh->exc_overflow, elist_p, exc_cap);
+            }
         }
         consumed += (unsigned)n_my;
         __syncthreads();
         const unsigned long long t_loop = t_begin ? globaltimer() : 0ull;
-        if (run_a) cta_reduce<A::NS, A::NM>(accA, red, row);
-        else cta_reduce<3, 2>(accB, red, row);
+        cta_reduce<A::NS, A::NM, LD>(acc, part, row);
         if (t_begin) {
             const unsigned long long t2 = globaltimer();
-            sh->t_phase[run_a ? 4 : 7] += t_loop - t_begin; sh->t_phase[run_a ? 5 : 8] += t2 - t_loop;
+            sh->t_phase[run_init ? 4 : 7] += t_loop - t_begin; sh->t_phase[run_init ? 5 : 8] += t2 - t_loop;
         }
 
         // ---- grid barrier: the last CTA to arrive reduces the rows and runs the controller
@@ -595,7 +597,7 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
         if (s_flag[0]) {
             __threadfence();
             const unsigned long long t_ctl = (tid == 0) ? globaltimer() : 0ull;
-            const int nv = run_a ? A::NV : kNB, ns = run_a ? A::NS : 3;
+            constexpr int nv = A::NV, ns = A::NS;
             // final reduce: warp w sums rows w, w+8, ...; lanes cover the columns (coalesced); loads are
             // issued in batches of 8 rows before they are combined, in a fixed order
             {
@@ -627,15 +629,30 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
                 reinterpret_cast<int *>(&s_ctl)[w] = __ldcg(reinterpret_cast<const int *>(&sh->ctl) + w);
             __syncthreads();
             if (tid < nv) {
-                double s = part[0][tid];
-                if (tid < ns) for (int w = 1; w < kWarps; ++w) s += part[w][tid];
-                else          for (int w = 1; w < kWarps; ++w) s = fmax(s, part[w][tid]);
-                fin[tid] = s;
+                double x = part[0][tid];
+                if (tid < ns) for (int w = 1; w < kWarps; ++w) x += part[w][tid];
+                else          for (int w = 1; w < kWarps; ++w) x = fmax(x, part[w][tid]);
+                fin[tid] = x;
             }
             __syncthreads();
             const unsigned long long t_fin = (tid == 0) ? globaltimer() : 0ull;
-            if (run_a) {
-                // EvalSums in place (unused triangle / vector entries are zero)
+            // ---- FUSED: judge the candidate first
+            if (tid == 0) {
+                int accepted = run_init ? 1 : 0;
+                LmNext nx = LM_RUN_A;
+                if (!run_init) {
+                    CandSums c;
+                    c.mcc = fin[A::oMCC]; c.step_sq = fin[A::oSTEP]; c.cand_cost = 0.5 * fin[0];
+                    c.bad_step = fin[A::iBADSTEP]; c.bad_cand = fin[A::iBADRES];
+                    nx = s_ctl.on_candidate(c);
+                    accepted = (nx == LM_RUN_A) ? 1 : 0;
+                }
+                s_flag[1] = (int)nx;
+                s_flag[3] = accepted;
+            }
+            __syncthreads();
+            if (s_flag[3]) {
+                // the evaluation sums of this pass describe the (new) current point: EvalSums in place
                 if (tid < kTri) {
                     s_ctl.ev.G1[tid] = (tid < A::TRI) ? fin[A::oG1 + (tid < A::TRI ? tid : 0)] : 0.0;
                     s_ctl.ev.G2[tid] = (tid < A::TRI) ? fin[A::oG2 + (tid < A::TRI ? tid : 0)] : 0.0;
@@ -649,45 +666,41 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
                     s_ctl.ev.bad = fin[A::iBAD]; s_ctl.ev.ee_max = fin[A::iEEMAX];
                 }
                 __syncthreads();
+                if (tid == 0) s_flag[1] = (int)s_ctl.on_eval_stored();
             }
             if (tid == 0) {
-                LmNext nx;
-                if (run_a) {
-                    nx = s_ctl.on_eval_stored();
-                } else {
-                    CandSums c;
-                    c.mcc = fin[0]; c.step_sq = fin[1]; c.cand_cost = 0.5 * fin[2]; c.bad_step = fin[3]; c.bad_cand = fin[4];
-                    nx = s_ctl.on_candidate(c);
-                }
-                s_flag[1] = (int)nx;
-                const unsigned int ne = __ldcg(&sh->n_exc);
+                // exception lists: on acceptance the speculative list becomes the current one
+                const int cur = run_init ? P.cur_list : (s_flag[3] ? (P.cur_list ^ 1) : P.cur_list);
+                s_flag[4] = cur;
+                const unsigned int ne = __ldcg(&sh->n_exc[cur]);
                 s_flag[2] = (int)(ne < exc_cap ? ne : exc_cap);
+                sh->n_exc[cur ^ 1] = 0u;                       // the other list is rebuilt by the next pass
             }
             __syncthreads();
             // ---- (re)solve at the current radius; the clamped-pixel correction is summed by the whole CTA
             while (s_flag[1] == (int)LM_SOLVE) {
                 const int ne = s_flag[2];
                 if constexpr (NF > 0) if (ne > 0) {
+                    const ExcEntry *cur_exc = exc + (size_t)s_flag[4] * exc_cap;
                     const double R = s_ctl.radius, lo = s_ctl.opt.min_lm_diagonal, hi = s_ctl.opt.max_lm_diagonal;
-                    double a[kTri + kMaxNF];
+                    double a[kExcVals];
 #pragma unroll
-                    for (int j = 0; j < kTri + kMaxNF; ++j) a[j] = 0.0;
+                    for (int j = 0; j < kExcVals; ++j) a[j] = 0.0;
                     for (int k = tid; k < ne; k += kThreads) {
-                        ExcEntry E;
+                        ExcEntry X;
                         for (int w = 0; w < (int)(sizeof(ExcEntry) / sizeof(double)); ++w)
-                            reinterpret_cast<double *>(&E)[w] = __ldcg(reinterpret_cast<const double *>(exc + k) + w);
-                        const double q = E.se2 / (E.ees + fmin(fmax(E.ees, lo), hi) / R);
+                            reinterpret_cast<double *>(&X)[w] = __ldcg(reinterpret_cast<const double *>(cur_exc + k) + w);
+                        const double q = X.se2 / (X.ees + fmin(fmax(X.ees, lo), hi) / R);
                         int t = 0;
 #pragma unroll
                         for (int j = 0; j < NF; ++j) {
-                            const double qf = q * E.fe[j];
-                            a[kTri + j] = fma(qf, E.er, a[kTri + j]);
+                            const double qf = q * X.fe[j];
+                            a[kTri + j] = fma(qf, X.er, a[kTri + j]);
 #pragma unroll
-                            for (int c = j; c < NF; ++c, ++t) a[t] = fma(qf, E.fe[c], a[t]);
+                            for (int c = j; c < NF; ++c, ++t) a[t] = fma(qf, X.fe[c], a[t]);
                         }
                     }
-                    // a[] is packed with the NF-triangle first; spread into the kMaxNF layout the controller uses
-                    cta_reduce<kTri + kMaxNF, 0>(a, red, fin);
+                    cta_reduce<kExcVals, 0, LD>(a, part, fin);
                     if (tid < kTri) s_exc.S[tid] = fin[tid];
                     if (tid < kMaxNF) s_exc.rhs[tid] = fin[kTri + tid];
                     __syncthreads();
@@ -698,9 +711,9 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
             // ---- publish the next phase
             if (tid == 0) {
                 const unsigned long long t_solved = globaltimer();
-                sh->t_phase[run_a ? 10 : 11] += t_solved - t_fin;     // controller logic only (after the row reduction)
-                const LmNext nx = (LmNext)s_flag[1];
-                if (s_ctl.accepted_last && nx == LM_RUN_A) sh->bc.which_x = P.which_x ^ 1;
+                sh->t_phase[run_init ? 10 : 11] += t_solved - t_fin;     // controller logic only (after the row reduction)
+                const LmNext nx = (LmNext)s_flag[1];                     // LM_RUN_B (another fused pass) or LM_DONE
+                if (!run_init && s_flag[3]) sh->bc.which_x = P.which_x ^ 1;   // the candidate became x
                 Motion mo = P.base, ca = P.base;
                 if (NF >= 6) for (int j = 0; j < 3; ++j) {
                     mo.v[j] = s_ctl.f[j]; mo.w[j] = s_ctl.f[3 + j];
@@ -713,18 +726,18 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
                 sh->bc.radius = s_ctl.radius;
                 sh->bc.ee_fast_min = s_ctl.ee_fast_min;
                 sh->bc.first = 0;
+                sh->bc.cur_list = s_flag[4];
                 sh->bc.next = (int)nx;
-                if (nx == LM_RUN_A) sh->n_exc = 0u;       // a new evaluation rebuilds the exception list
                 if (t_begin) {
                     const unsigned long long dt = globaltimer() - t_begin;
-                    sh->t_phase[run_a ? 0 : 2] += dt; sh->t_phase[run_a ? 1 : 3] += 1ull;
+                    sh->t_phase[run_init ? 0 : 2] += dt; sh->t_phase[run_init ? 1 : 3] += 1ull;
                 }
             }
             for (int w = tid; w < (int)(sizeof(LmController) / sizeof(int)); w += kThreads)
                 reinterpret_cast<int *>(&sh->ctl)[w] = reinterpret_cast<const int *>(&s_ctl)[w];
             __syncthreads();
             if (tid == 0) {
-                sh->t_phase[run_a ? 6 : 9] += globaltimer() - t_ctl;
+                sh->t_phase[run_init ? 6 : 9] += globaltimer() - t_ctl;
                 __threadfence();
                 st_release(&sh->generation, gen + 1u);
             }
@@ -738,7 +751,7 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
             }
             if (t_begin && !s_flag[0]) {
                 const unsigned long long dt = globaltimer() - t_begin;
-                sh->t_phase[run_a ? 0 : 2] += dt; sh->t_phase[run_a ? 1 : 3] += 1ull;
+                sh->t_phase[run_init ? 0 : 2] += dt; sh->t_phase[run_init ? 1 : 3] += 1ull;
             }
         }
         __syncthreads();
@@ -765,7 +778,7 @@ static int launch_persistent(rsdsfm_ctx *ctx, RefineData D, double *d0, double *
                              ExcEntry *exc, unsigned int exc_cap, const double *z_in, int z_stride, double *out,
                              int invert_out, int grid)
 {
-    const size_t smem = smem_bytes<NF>();
+    const size_t smem = sizeof(Stage) * (size_t)kStages;
     RS_CUDA(ctx, cudaFuncSetAttribute(k_lm_persistent<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void *args[] = {&D, &d0, &d1, &sh, &partials, &exc, &exc_cap, &z_in, &z_stride, &out, &invert_out};
     if (ctx->profile) cudaEventRecord(ctx->pe0, ctx->stream);
@@ -793,10 +806,10 @@ static int lm_solve_async(rsdsfm_ctx *ctx, const RefineData &D, double *d0, doub
     RS_TRY(ensure(ctx, ctx->lm_shared, sizeof(LmShared)));
     LmShared *sh = (LmShared *)ctx->lm_shared.p;
     const int grid = ctx->num_sms;                      // one persistent CTA per SM
-    const int nv = (nf == 0) ? PassA<0>::NV : (nf == 6 ? PassA<6>::NV : PassA<7>::NV);
+    const int nv = (nf == 0) ? Acc<0>::NV : (nf == 6 ? Acc<6>::NV : Acc<7>::NV);
     RS_TRY(ensure(ctx, ctx->partials, sizeof(double) * (size_t)grid * nv));
     if (ctx->exc_cap < 4096) ctx->exc_cap = 4096;
-    RS_TRY(ensure(ctx, ctx->exc, sizeof(ExcEntry) * (size_t)ctx->exc_cap));
+    RS_TRY(ensure(ctx, ctx->exc, sizeof(ExcEntry) * 2 * (size_t)ctx->exc_cap));   // current + speculative list
     RS_TRY(ensure_pinned(ctx, sizeof(LmShared) * 2 + 1024));
 
     // initial control block, staged through pinned memory (second half; the first half receives results)
