@@ -43,9 +43,10 @@ struct RefineData {
 };
 __host__ __device__ inline size_t blk_index(int i, int field) { return (size_t)(i / kTile) * (3 * kTile) + (size_t)field * kTile + (size_t)(i % kTile); }
 
-struct ExcEntry {            // a pixel whose LM diagonal is (possibly) clamped, or whose e-column is degenerate
-    double ees, se2, er;     // s_e^2 e^Te, s_e^2, e^T r
-    double fe[kMaxNF];       // F^T e
+struct ExcEntry {            // a pixel whose LM diagonal is (possibly) clamped, or whose e-column is degenerate:
+    double ees, se2;         // s_e^2 e^Te, s_e^2     (the whole pixel is handled by the controller CTA)
+    double r0, r1, e0, e1;   // residual and depth column
+    double F0[kMaxNF], F1[kMaxNF];   // the two Jacobian rows of the free motion parameters
 };
 
 // Broadcast block: written by the controller CTA, read by every CTA at the start of a phase.
@@ -208,31 +209,76 @@ constexpr int kExcVals = kTri + kMaxNF;          // exception sums: S triangle +
 template <int NF> constexpr int kRowVals = (Acc<NF>::NV > kExcVals) ? Acc<NF>::NV : kExcVals;
 static_assert(kRowVals<7> <= 96, "the final reduce covers three 32-lane column chunks");
 
-// NV values per thread (first NS sums, then maxima >= 0) -> one row of NV doubles: butterfly
-// shuffles inside each warp, then the 8 warp results are combined in warp order.  No large
-// shared scratch (the TMA ring owns the dynamic shared memory); fixed order => bit-reproducible.
-template <int NS, int NM, int LD>
-__device__ __forceinline__ void cta_reduce(const double (&v)[NS + NM], double (*wpart)[LD], double *row)
+// Per-THREAD accumulators.  The two Schur factors are split across lane pairs: even lanes keep
+// K = G1 / H = h1 (the n-direction), odd lanes keep K = G2 / H = h2 (the e-direction); partners
+// swap the half they do not keep with one shuffle per value.  This halves the accumulator
+// registers (35 instead of 70 doubles for NF = 7), which is what lets two pixels per thread and the
+// fused candidate+evaluation pass run without spilling.
+template <int NF>
+struct TAcc {
+    static constexpr int TRI = NF * (NF + 1) / 2;
+    static constexpr int oK = 2, oH = oK + TRI, oMCC = oH + NF, oSTEP = oMCC + 1;
+    static constexpr int NS = oSTEP + 1, NM = 5, NV = NS + NM;
+    static constexpr int iGMAX = NS, iBAD = NS + 1, iEEMAX = NS + 2, iBADSTEP = NS + 3, iBADRES = NS + 4;
+};
+
+// Per-thread accumulators -> one CTA row in the Acc<NF> layout (G1, G2, h1, h2 separated again).
+// Butterfly shuffles inside each warp (K/H entries only over lanes of the same role), then the 8
+// warp results are combined in warp order.  Fixed order => bit-reproducible.
+template <int NF, int LD>
+__device__ __forceinline__ void cta_reduce_roles(const double (&v)[TAcc<NF>::NV], double (*wpart)[LD], double *row)
 {
-    constexpr int NV = NS + NM;
+    using T = TAcc<NF>;
+    using A = Acc<NF>;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
+    for (int j = 0; j < T::NV; ++j) {
         double x = v[j];
-        if (j < NS) {
+        const bool role_split = (j >= T::oK && j < T::oMCC);
+        if (j < T::NS) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            for (int o = 16; o > 1; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (!role_split) x += __shfl_xor_sync(0xffffffffu, x, 1);
         } else {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
         }
+        if (role_split) {
+            // lane 0: n-direction (G1 / h1), lane 1: e-direction (G2 / h2)
+            const int jj = j - T::oK;
+            const int dst = (jj < T::TRI) ? ((lane == 0 ? A::oG1 : A::oG2) + jj) : ((lane == 0 ? A::oH1 : A::oH2) + (jj - T::TRI));
+            if (lane < 2) wpart[warp][dst] = x;
+        } else if (lane == 0) {
+            const int dst = (j < T::oK) ? j : (j < T::NS ? (A::oMCC + (j - T::oMCC)) : (A::NS + (j - T::NS)));
+            wpart[warp][dst] = x;
+        }
+    }
+    __syncthreads();
+    if (tid < A::NV) {
+        double x = wpart[0][tid];
+        if (tid < A::NS) { for (int w = 1; w < kWarps; ++w) x += wpart[w][tid]; }
+        else             { for (int w = 1; w < kWarps; ++w) x = fmax(x, wpart[w][tid]); }
+        row[tid] = x;
+    }
+    __syncthreads();
+}
+
+// plain variant (all values reduced over all lanes): used for the exception sums
+template <int NS, int LD>
+__device__ __forceinline__ void cta_reduce_sums(const double (&v)[NS], double (*wpart)[LD], double *row)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        double x = v[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if (lane == 0) wpart[warp][j] = x;
     }
     __syncthreads();
-    if (tid < NV) {
+    if (tid < NS) {
         double x = wpart[0][tid];
-        if (tid < NS) { for (int w = 1; w < kWarps; ++w) x += wpart[w][tid]; }
-        else          { for (int w = 1; w < kWarps; ++w) x = fmax(x, wpart[w][tid]); }
+        for (int w = 1; w < kWarps; ++w) x += wpart[w][tid];
         row[tid] = x;
     }
     __syncthreads();
@@ -281,38 +327,27 @@ __device__ __forceinline__ void px_eval(const Loaded &L, const Motion &m, double
 }
 
 // Rare path of the evaluation: a pixel whose LM diagonal may be clamped (|e| ~ 0, focus of
-// expansion) or whose values are not finite.  F^TF / F^Tr go to G1 / h1; the radius-dependent
-// term q (F^Te)(e^TF) is applied by the controller from the exception list.
+// expansion) or whose values are not finite.  Nothing of its Jacobian is accumulated by the
+// thread: the pixel is listed and the controller CTA adds F^TF, F^Tr (radius independent) and
+// subtracts q (F^Te)(e^TF), q (F^Te)(e^Tr) (radius dependent) itself.
 template <int NF>
-__device__ __forceinline__ void eval_slow(const Loaded &L, double d, const Motion &mot, double c2, bool first, const Motion &base,
-                                          double (&acc)[Acc<NF>::NV], unsigned int *n_exc, unsigned int *overflow, ExcEntry *exc,
-                                          unsigned int exc_cap)
+__device__ __noinline__ void eval_slow(const Loaded &L, double d, const Motion &mot, double c2, bool first, const Motion &base,
+                                       unsigned int *n_exc, unsigned int *overflow, ExcEntry *exc, unsigned int exc_cap)
 {
-    using A = Acc<NF>;
     PxEval E;
     px_eval(L, mot, c2, d, E);
     const double dbeta = (NF == 7) ? c2 * fma(-E.ak, 0.5 * c2, L.a.y) : 0.0;
     const double se = first ? 1.0 / (1.0 + sqrt(E.ee)) : depth_scale_at_start(L, base);
-    double F0[NF > 0 ? NF : 1], F1[NF > 0 ? NF : 1], fe[NF > 0 ? NF : 1];
+    double F0[NF > 0 ? NF : 1], F1[NF > 0 ? NF : 1];
     ft_times<NF>(E.beta, dbeta, d, E.x, E.y, E.xy, E.xx1, E.yy1, E.p0, E.p1, 1.0, 0.0, F0);
     ft_times<NF>(E.beta, dbeta, d, E.x, E.y, E.xy, E.xx1, E.yy1, E.p0, E.p1, 0.0, 1.0, F1);
-    double bad = 0.0;
-    int t = 0;
-#pragma unroll
-    for (int j = 0; j < NF; ++j) {
-        fe[j] = fma(F0[j], E.e0, F1[j] * E.e1);
-        bad += bad_flag(fe[j]);
-        acc[A::oH1 + j] += fma(F0[j], E.r0, F1[j] * E.r1);
-#pragma unroll
-        for (int c = j; c < NF; ++c, ++t) acc[A::oG1 + t] += fma(F0[j], F0[c], F1[j] * F1[c]);
-    }
-    acc[A::iBAD] = fmax(acc[A::iBAD], bad);
     const unsigned int slot = atomicAdd(n_exc, 1u);
     if (slot < exc_cap) {
         ExcEntry X;
-        X.ees = E.ee * se * se; X.se2 = se * se; X.er = fma(E.e0, E.r0, E.e1 * E.r1);
+        X.ees = E.ee * se * se; X.se2 = se * se;
+        X.r0 = E.r0; X.r1 = E.r1; X.e0 = E.e0; X.e1 = E.e1;
 #pragma unroll
-        for (int j = 0; j < kMaxNF; ++j) X.fe[j] = (j < NF) ? fe[j] : 0.0;
+        for (int j = 0; j < kMaxNF; ++j) { X.F0[j] = (j < NF) ? F0[j] : 0.0; X.F1[j] = (j < NF) ? F1[j] : 0.0; }
         exc[slot] = X;
     } else {
         *overflow = 1u;
@@ -320,16 +355,17 @@ __device__ __forceinline__ void eval_slow(const Loaded &L, double d, const Motio
 }
 
 // Evaluation (residual, Jacobian, Schur factors) of TWO residual blocks per thread at the point
-// (mot, d[p]): every stage is written for both pixels side by side, branch-free on the common
-// path, so the two dependency chains interleave.
+// (mot, d[p]).  Branch-free on the common path; the lane pair (l, l^1) shares the rank-1 updates:
+// the even lane applies the n-direction update of both lanes' pixels, the odd lane the e-direction.
 template <int NF>
 __device__ __forceinline__ void eval_pair(const Loaded (&L)[2], const double (&dv)[2], const bool (&valid)[2], const Motion &mot,
-                                          double c2, bool first, const PhaseParams &P, double (&acc)[Acc<NF>::NV],
+                                          double c2, bool first, const PhaseParams &P, double (&acc)[TAcc<NF>::NV],
                                           unsigned int *n_exc, unsigned int *overflow, ExcEntry *exc, unsigned int exc_cap)
 {
-    using A = Acc<NF>;
+    using T = TAcc<NF>;
+    const bool e_role = (threadIdx.x & 1) != 0;
     PxEval E[2];
-    double d[2], re[2], rn[2], mu[2];
+    double d[2], mu[2];
     bool slow[2] = {false, false};
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
@@ -341,62 +377,59 @@ __device__ __forceinline__ void eval_pair(const Loaded (&L)[2], const double (&d
     for (int p = 0; p < 2; ++p) {
         acc[0] = fma(E[p].r0, E[p].r0, fma(E[p].r1, E[p].r1, acc[0]));
         acc[1] = fma(d[p], d[p], acc[1]);
-        re[p] = fma(E[p].e0, E[p].r0, E[p].e1 * E[p].r1);               // e^T r
-        rn[p] = fma(-E[p].e1, E[p].r0, E[p].e0 * E[p].r1);              // n^T r, n = (-e1, e0)
-        acc[A::iGMAX] = fmax(acc[A::iGMAX], fabs(re[p]));
-        acc[A::iEEMAX] = fmax(acc[A::iEEMAX], E[p].ee);
+        const double re = fma(E[p].e0, E[p].r0, E[p].e1 * E[p].r1);     // e^T r
+        acc[T::iGMAX] = fmax(acc[T::iGMAX], fabs(re));
+        acc[T::iEEMAX] = fmax(acc[T::iEEMAX], E[p].ee);
         const double br = bad_flag(E[p].r0 + E[p].r1);
-        acc[A::iBADRES] = fmax(acc[A::iBADRES], br);
-        acc[A::iBAD] = fmax(acc[A::iBAD], br + bad_flag(E[p].ee));
+        acc[T::iBADRES] = fmax(acc[T::iBADRES], br);
+        acc[T::iBAD] = fmax(acc[T::iBAD], br + bad_flag(E[p].ee));
+        // is the LM diagonal of this depth certainly not clamped?  (first evaluation: the Jacobi
+        // scale is 1/(1+|e|) of this very point; later: global lower bound of the scales)
+        bool fast;
+        if (first) {
+            const double se = 1.0 / (1.0 + sqrt(E[p].ee));
+            const double ees = E[p].ee * se * se;
+            fast = (ees >= P.min_diag && ees <= P.max_diag);
+        } else {
+            fast = (E[p].ee >= P.ee_fast_min && E[p].ee <= P.max_diag);
+        }
+        slow[p] = (NF > 0) && valid[p] && !fast;
+        const double r = fast_rcp(E[p].ee);
+        mu[p] = (valid[p] && fast) ? r : 0.0;
     }
     if (NF > 0) {
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            // is the LM diagonal of this depth certainly not clamped?  (first evaluation: the Jacobi
-            // scale is 1/(1+|e|) of this very point; later: global lower bound of the scales)
-            bool fast;
-            if (first) {
-                const double se = 1.0 / (1.0 + sqrt(E[p].ee));
-                const double ees = E[p].ee * se * se;
-                fast = (ees >= P.min_diag && ees <= P.max_diag);
-            } else {
-                fast = (E[p].ee >= P.ee_fast_min && E[p].ee <= P.max_diag);
-            }
-            slow[p] = valid[p] && !fast;
-            const double r = fast_rcp(E[p].ee);
-            mu[p] = (valid[p] && fast) ? r : 0.0;
-        }
-        // projector = (n n^T + e e^T/(radius+1)) / e^Te: accumulate the two radius-independent factors
-        double fn[2][NF > 0 ? NF : 1], fe[2][NF > 0 ? NF : 1];
+        // projector = (n n^T + e e^T/(radius+1)) / e^Te: two radius-independent rank-1 factors
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
             const double dbeta = (NF == 7) ? c2 * fma(-E[p].ak, 0.5 * c2, L[p].a.y) : 0.0;
-            ft_times<NF>(E[p].beta, dbeta, d[p], E[p].x, E[p].y, E[p].xy, E[p].xx1, E[p].yy1, E[p].p0, E[p].p1, -E[p].e1, E[p].e0, fn[p]);
-            ft_times<NF>(E[p].beta, dbeta, d[p], E[p].x, E[p].y, E[p].xy, E[p].xx1, E[p].yy1, E[p].p0, E[p].p1, E[p].e0, E[p].e1, fe[p]);
-        }
-        int t = 0;
+            double fn[NF > 0 ? NF : 1], fe[NF > 0 ? NF : 1];
+            ft_times<NF>(E[p].beta, dbeta, d[p], E[p].x, E[p].y, E[p].xy, E[p].xx1, E[p].yy1, E[p].p0, E[p].p1, -E[p].e1, E[p].e0, fn);
+            ft_times<NF>(E[p].beta, dbeta, d[p], E[p].x, E[p].y, E[p].xy, E[p].xx1, E[p].yy1, E[p].p0, E[p].p1, E[p].e0, E[p].e1, fe);
+            const double rn = fma(-E[p].e1, E[p].r0, E[p].e0 * E[p].r1);    // n^T r, n = (-e1, e0)
+            const double re = fma(E[p].e0, E[p].r0, E[p].e1 * E[p].r1);
+            // keep my direction, hand the other one to the partner lane
+            double kv[NF > 0 ? NF : 1], pv[NF > 0 ? NF : 1];
 #pragma unroll
-        for (int j = 0; j < NF; ++j) {
-            double gn[2], ge[2];
-#pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                gn[p] = mu[p] * fn[p][j]; ge[p] = mu[p] * fe[p][j];
-                acc[A::oH1 + j] = fma(gn[p], rn[p], acc[A::oH1 + j]);
-                acc[A::oH2 + j] = fma(ge[p], re[p], acc[A::oH2 + j]);
+            for (int j = 0; j < NF; ++j) {
+                kv[j] = e_role ? fe[j] : fn[j];
+                pv[j] = __shfl_xor_sync(0xffffffffu, e_role ? fn[j] : fe[j], 1);
             }
+            const double ks = e_role ? re : rn;
+            const double ps = __shfl_xor_sync(0xffffffffu, e_role ? rn : re, 1);
+            const double pmu = __shfl_xor_sync(0xffffffffu, mu[p], 1);
+            int t = 0;
 #pragma unroll
-            for (int c = j; c < NF; ++c, ++t) {
+            for (int j = 0; j < NF; ++j) {
+                const double g = mu[p] * kv[j], gp = pmu * pv[j];
+                acc[T::oH + j] = fma(g, ks, fma(gp, ps, acc[T::oH + j]));
 #pragma unroll
-                for (int p = 0; p < 2; ++p) {
-                    acc[A::oG1 + t] = fma(gn[p], fn[p][c], acc[A::oG1 + t]);
-                    acc[A::oG2 + t] = fma(ge[p], fe[p][c], acc[A::oG2 + t]);
-                }
+                for (int c = j; c < NF; ++c, ++t) acc[T::oK + t] = fma(g, kv[c], fma(gp, pv[c], acc[T::oK + t]));
             }
         }
         if (slow[0] || slow[1]) {
 #pragma unroll
             for (int p = 0; p < 2; ++p)
-                if (slow[p]) eval_slow<NF>(L[p], dv[p], mot, c2, first, P.base, acc, n_exc, overflow, exc, exc_cap);
+                if (slow[p]) eval_slow<NF>(L[p], dv[p], mot, c2, first, P.base, n_exc, overflow, exc, exc_cap);
         }
     }
 }
@@ -405,10 +438,10 @@ __device__ __forceinline__ void eval_pair(const Loaded (&L)[2], const double (&d
 // delta_d = -q e^T (r + F delta_f), model cost change, |step|^2; returns the candidate depths.
 template <int NF>
 __device__ __forceinline__ void step_pair(const Loaded (&L)[2], const bool (&valid)[2], const int (&idx)[2], const PhaseParams &P,
-                                          double c2, double rfac, double inv_radius, double (&acc)[Acc<NF>::NV],
+                                          double c2, double rfac, double inv_radius, double (&acc)[TAcc<NF>::NV],
                                           double *__restrict__ d_cand, double (&dc)[2])
 {
-    using A = Acc<NF>;
+    using A = TAcc<NF>;
     PxEval E[2];
     double q[2], m0[2], m1[2];
 #pragma unroll
@@ -538,9 +571,9 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
             }
         }
 
-        double acc[A::NV];
+        double acc[TAcc<NF>::NV];
 #pragma unroll
-        for (int j = 0; j < A::NV; ++j) acc[j] = 0.0;
+        for (int j = 0; j < TAcc<NF>::NV; ++j) acc[j] = 0.0;
         const double c2 = 2.0 / (2.0 + P.mot.k), c2c = 2.0 / (2.0 + P.cand.k);
         const double rfac = P.radius / (P.radius + 1.0), inv_radius = 1.0 / P.radius;
 
@@ -581,7 +614,7 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
         consumed += (unsigned)n_my;
         __syncthreads();
         const unsigned long long t_loop = t_begin ? globaltimer() : 0ull;
-        cta_reduce<A::NS, A::NM, LD>(acc, part, row);
+        cta_reduce_roles<NF, LD>(acc, part, row);
         if (t_begin) {
             const unsigned long long t2 = globaltimer();
             sh->t_phase[run_init ? 4 : 7] += t_loop - t_begin; sh->t_phase[run_init ? 5 : 8] += t2 - t_loop;
@@ -666,7 +699,6 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
                     s_ctl.ev.bad = fin[A::iBAD]; s_ctl.ev.ee_max = fin[A::iEEMAX];
                 }
                 __syncthreads();
-                if (tid == 0) s_flag[1] = (int)s_ctl.on_eval_stored();
             }
             if (tid == 0) {
                 // exception lists: on acceptance the speculative list becomes the current one
@@ -677,6 +709,33 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
                 sh->n_exc[cur ^ 1] = 0u;                       // the other list is rebuilt by the next pass
             }
             __syncthreads();
+            if (s_flag[3]) {
+                // listed pixels: their radius-independent part F^TF, F^Tr joins G1, h1 of the new point
+                if constexpr (NF > 0) if (s_flag[2] > 0) {
+                    const ExcEntry *cur_exc = exc + (size_t)s_flag[4] * exc_cap;
+                    double a[kExcVals];
+#pragma unroll
+                    for (int j = 0; j < kExcVals; ++j) a[j] = 0.0;
+                    for (int k = tid; k < s_flag[2]; k += kThreads) {
+                        ExcEntry X;
+                        for (int w = 0; w < (int)(sizeof(ExcEntry) / sizeof(double)); ++w)
+                            reinterpret_cast<double *>(&X)[w] = __ldcg(reinterpret_cast<const double *>(cur_exc + k) + w);
+                        int t = 0;
+#pragma unroll
+                        for (int j = 0; j < NF; ++j) {
+                            a[kTri + j] += fma(X.F0[j], X.r0, X.F1[j] * X.r1);
+#pragma unroll
+                            for (int c = j; c < NF; ++c, ++t) a[t] += fma(X.F0[j], X.F0[c], X.F1[j] * X.F1[c]);
+                        }
+                    }
+                    cta_reduce_sums<kExcVals, LD>(a, part, fin);
+                    if (tid < A::TRI) s_ctl.ev.G1[tid] += fin[tid];
+                    if (tid < NF) s_ctl.ev.h1[tid] += fin[kTri + tid];
+                    __syncthreads();
+                }
+                if (tid == 0) s_flag[1] = (int)s_ctl.on_eval_stored();
+                __syncthreads();
+            }
             // ---- (re)solve at the current radius; the clamped-pixel correction is summed by the whole CTA
             while (s_flag[1] == (int)LM_SOLVE) {
                 const int ne = s_flag[2];
@@ -691,16 +750,20 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
                         for (int w = 0; w < (int)(sizeof(ExcEntry) / sizeof(double)); ++w)
                             reinterpret_cast<double *>(&X)[w] = __ldcg(reinterpret_cast<const double *>(cur_exc + k) + w);
                         const double q = X.se2 / (X.ees + fmin(fmax(X.ees, lo), hi) / R);
+                        const double er = fma(X.e0, X.r0, X.e1 * X.r1);
+                        double fe[NF > 0 ? NF : 1];
+#pragma unroll
+                        for (int j = 0; j < NF; ++j) fe[j] = fma(X.F0[j], X.e0, X.F1[j] * X.e1);
                         int t = 0;
 #pragma unroll
                         for (int j = 0; j < NF; ++j) {
-                            const double qf = q * X.fe[j];
-                            a[kTri + j] = fma(qf, X.er, a[kTri + j]);
+                            const double qf = q * fe[j];
+                            a[kTri + j] = fma(qf, er, a[kTri + j]);
 #pragma unroll
-                            for (int c = j; c < NF; ++c, ++t) a[t] = fma(qf, X.fe[c], a[t]);
+                            for (int c = j; c < NF; ++c, ++t) a[t] = fma(qf, fe[c], a[t]);
                         }
                     }
-                    cta_reduce<kExcVals, 0, LD>(a, part, fin);
+                    cta_reduce_sums<kExcVals, LD>(a, part, fin);
                     if (tid < kTri) s_exc.S[tid] = fin[tid];
                     if (tid < kMaxNF) s_exc.rhs[tid] = fin[kTri + tid];
                     __syncthreads();
