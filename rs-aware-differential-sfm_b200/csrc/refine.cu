@@ -492,6 +492,159 @@ __device__ __forceinline__ void step_pair(const Loaded (&L)[2], const bool (&val
 }
 
 // ------------------------------------------------------------------------------------------
+// Warp-parallel controller steps.  The controller runs once per phase on the last CTA while the
+// whole grid waits, and its code is cold in the instruction cache every time (the pixel loops
+// evict it), so it is written as SMALL rolled loops executed by one warp on shared-memory data
+// (lanes work on matrix entries side by side) instead of a long unrolled scalar sequence.
+// Same arithmetic as LmController::on_eval_stored / solve_step (which the host-stepped RANSAC
+// solver keeps using for its f-block-free problems).
+// ------------------------------------------------------------------------------------------
+__constant__ unsigned char kLowR[28] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 6, 6};
+__constant__ unsigned char kLowC[28] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 6};
+
+template <int NF>
+__device__ __noinline__ int ctl_on_eval(LmController &c)
+{
+    const int lane = threadIdx.x & 31;
+    const bool bad = c.ev.bad > 0.0;
+    int done = -1;
+    if (c.phase == 0) {
+        // IterationZero: the Jacobi scaling is fixed here
+        if (bad) { if (lane == 0) { c.initial_cost = 0.0; c.finish(RSDSFM_FAILURE, RSDSFM_REASON_EVAL_FAILED); } done = LM_DONE; }
+        else {
+            if (lane < NF) {
+                const int t = lane * NF - (lane * (lane - 1)) / 2;
+                c.scale_f[lane] = 1.0 / (1.0 + sqrt(c.ev.G1[t] + c.ev.G2[t]));
+            }
+            if (lane == 0) {
+                c.x_cost = c.ev.cost; c.initial_cost = c.ev.cost;
+                const double t = 1.0 + sqrt(c.ev.ee_max);
+                c.ee_fast_min = c.opt.min_lm_diagonal * t * t;
+            }
+        }
+    } else {
+        // HandleSuccessfulStep: the evaluation at the new x
+        if (bad) { if (lane == 0) c.finish(RSDSFM_FAILURE, RSDSFM_REASON_EVAL_FAILED); done = LM_DONE; }
+        else if (lane == 0) { c.x_cost = c.ev.cost; c.step_is_successful = 1; }
+    }
+    __syncwarp();
+    if (done >= 0) return done;
+    // gradient max norm |x - Plus(x, -g)|_inf and |x|
+    double g = 0.0, xs = 0.0;
+    if (lane < NF) {
+        const double f = c.f[lane];
+        const double proj = f + (-(c.ev.h1[lane] + c.ev.h2[lane]));
+        g = fabs(f - proj);
+        xs = f * f;
+    }
+    for (int o = 16; o > 0; o >>= 1) { g = fmax(g, __shfl_xor_sync(0xffffffffu, g, o)); xs += __shfl_xor_sync(0xffffffffu, xs, o); }
+    int nx = 0;
+    if (lane == 0) {
+        c.gmax = fmax(c.ev.gmax_e, g);
+        c.x_norm = sqrt(c.ev.sumsq_d + xs);
+        nx = (int)c.begin_iteration();
+    }
+    return __shfl_sync(0xffffffffu, nx, 0);
+}
+
+__device__ __forceinline__ double fast_rsqrt(double x)
+{   // MUFU.RSQ64H seed + two Newton steps (x > 0, normal)
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double hx = 0.5 * x;
+    r = r * fma(-hx * r, r, 1.5);
+    r = r * fma(-hx * r, r, 1.5);
+    return r;
+}
+
+// LevenbergMarquardtStrategy::ComputeStep on the Schur-reduced system at the current radius.
+// One warp: lane i keeps row i of the lower triangle in registers; pivots / multipliers travel by
+// shuffle; the factor's columns are fetched once through the shared scratch Lm for the backward
+// substitution.  Eigen::LLT semantics: the solve fails on a non-positive or NaN pivot.
+template <int NF>
+__device__ __noinline__ int ctl_solve(LmController &c, const ExcSums *exc, double (*Lm)[8], double *y_unused)
+{
+    (void)y_unused;
+    const int lane = threadIdx.x & 31;
+    int nx = 0;
+    if (NF == 0) {
+        if (lane == 0) { c.reuse_diagonal = 1; nx = (int)LM_RUN_B; }
+        return __shfl_sync(0xffffffffu, nx, 0);
+    }
+    constexpr int N = NF > 0 ? NF : 1;
+    const int i = lane < N ? lane : N - 1;                       // lanes >= N shadow the last row (results unused)
+    const double radius = c.radius;
+    const double sci = c.scale_f[i];
+    if (!c.reuse_diagonal && lane < N) {
+        const int t = i * N - (i * (i - 1)) / 2;
+        c.diag_f[i] = LmController::clampd((c.ev.G1[t] + c.ev.G2[t]) * sci * sci, c.opt.min_lm_diagonal, c.opt.max_lm_diagonal);
+    }
+    __syncwarp();
+    const double eps = 1.0 / (radius + 1.0);
+    double a[N], invd[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const int jj = j <= i ? j : i;                           // row i only needs columns j <= i
+        const int t = jj * N - (jj * (jj - 1)) / 2 + (i - jj);   // tri_index(N, jj, i)
+        double sv = c.ev.G1[t] + c.ev.G2[t] * eps;
+        if (exc) sv -= exc->S[t];
+        a[j] = sv * (sci * c.scale_f[jj]);
+        invd[j] = 0.0;
+    }
+    {
+        const double dd = c.diag_f[i] / radius;                  // (sqrt(diag/radius))^2
+#pragma unroll
+        for (int j = 0; j < N; ++j) if (j == i) a[j] += dd;
+    }
+    double y = c.ev.h1[i] + c.ev.h2[i] * eps;
+    if (exc) y -= exc->rhs[i];
+    y *= sci;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double dk = __shfl_sync(0xffffffffu, a[k], k);      // pivot
+        if (!(dk > 0.0)) ok = false;
+        const double inv = fast_rsqrt(dk);
+        invd[k] = inv;
+        a[k] = (i == k) ? dk * inv : a[k] * inv;                  // l_kk = sqrt(d), l_ik = a_ik / l_kk
+#pragma unroll
+        for (int j = k + 1; j < N; ++j) {
+            const double ljk = __shfl_sync(0xffffffffu, a[k], j);
+            a[j] = fma(-a[k], ljk, a[j]);                         // only meaningful for i >= j
+        }
+    }
+    // forward substitution L z = rhs
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double zk = __shfl_sync(0xffffffffu, y, k) * invd[k];
+        if (i == k) y = zk; else if (i > k) y = fma(-a[k], zk, y);
+    }
+    // backward substitution L^T x = z: lane i needs column i of L
+    if (lane < N) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) if (j <= i) Lm[i][j] = a[j];
+    }
+    __syncwarp();
+    double col[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) col[k] = (k > i) ? Lm[k][i] : 0.0;
+#pragma unroll
+    for (int k = N - 1; k >= 0; --k) {
+        const double xk = __shfl_sync(0xffffffffu, y, k) * invd[k];
+        if (i == k) y = xk; else if (i < k) y = fma(-col[k], xk, y);
+    }
+    if (!isfinite(y)) ok = false;
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane < N) c.delta_f[i] = -y * sci;                        // step = -y ; delta = step o scale
+    __syncwarp();
+    if (lane == 0) {
+        c.reuse_diagonal = 1;
+        nx = ok ? (int)LM_RUN_B : (int)c.invalid_step();
+    }
+    return __shfl_sync(0xffffffffu, nx, 0);
+}
+
+// ------------------------------------------------------------------------------------------
 // The persistent kernel.  Phases: one INIT pass (evaluation at the start point), then one FUSED
 // pass per LM iteration: the candidate step at x (back substitution, model cost change) and,
 // speculatively, the complete evaluation at the candidate.  If the controller accepts the step the
@@ -524,6 +677,7 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
     __shared__ double fin[LD];
     __shared__ double part[kWarps][LD];
     __shared__ ExcSums s_exc;
+    __shared__ double s_L[7][8], s_y[8];                          // controller solve scratch
     __shared__ int s_flag[6];                                     // [0] is_last, [1] next, [2] n_exc, [3] accepted, [4] cur_list
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -733,7 +887,10 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
                     if (tid < NF) s_ctl.ev.h1[tid] += fin[kTri + tid];
                     __syncthreads();
                 }
-                if (tid == 0) s_flag[1] = (int)s_ctl.on_eval_stored();
+                if (warp == 0) {
+                    const int nx = ctl_on_eval<NF>(s_ctl);
+                    if (lane == 0) s_flag[1] = nx;
+                }
                 __syncthreads();
             }
             // ---- (re)solve at the current radius; the clamped-pixel correction is summed by the whole CTA
@@ -768,7 +925,10 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
                     if (tid < kMaxNF) s_exc.rhs[tid] = fin[kTri + tid];
                     __syncthreads();
                 }
-                if (tid == 0) s_flag[1] = (int)s_ctl.solve_step((NF > 0 && ne > 0) ? &s_exc : nullptr);
+                if (warp == 0) {
+                    const int nx = ctl_solve<NF>(s_ctl, (NF > 0 && ne > 0) ? &s_exc : nullptr, s_L, s_y);
+                    if (lane == 0) s_flag[1] = nx;
+                }
                 __syncthreads();
             }
             // ---- publish the next phase
