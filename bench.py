@@ -170,6 +170,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL's version banner goes to stdout by default; stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import __graft_entry__ as ge
     if rank == 0:
@@ -243,7 +245,13 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "lm_kernel_traffic.json")     # dram bytes per launch from the committed ncu capture
     if os.path.exists(tp) and CONST_ACC:
         with open(tp) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        # the captured launch ran `lm_iterations_in_captured_launch` iterations; scale to this run's average
+        it_cap = float(tj.get("lm_iterations_in_captured_launch", 0)) or None
+        it_now = prof["pass_b_launches"] / n_launch
+        traffic = tj.get("dram_bytes_per_launch")
+        if traffic is not None and it_cap:
+            traffic = traffic * (it_now + 0.45) / (it_cap + 0.45)   # initial evaluation streams 24/56 of an iteration
     # FP64 side of the roofline: ~218 double-precision instructions per residual block per fused
     # iteration (SASS count), 64 FP64 lanes/SM -> 148 * 64 * 2 * 1.965 GHz = 37.2 TFLOP/s
     fp64_instr = 218.0
