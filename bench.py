@@ -211,11 +211,41 @@ def run_ours(args):
             ms = float(t.item())
         return ms, ctx.launch_count() - l0, its
 
+    def seq_entries(i0, count, host):
+        out = []
+        for i in range(count):
+            p = pairs[(i0 + i) % N_PAIRS]
+            src = p["host"] if host else p
+            out.append(dict(flow=src["flow"], inliers3=src["inliers3"], alpha=src["alpha"], alpha_k=src["alpha_k"], image=src["image"],
+                            m=p["m"], v=p["v"], w=p["w"], k=p["k"], out=src["out"]))
+        return out
+
+    def timed_sequence(host, steps, warmup):
+        """K steps = one rsdsfm_refine_rectify_sequence call over K frame pairs (upload i+1 | compute i |
+        download i-1 on three streams; with device buffers only the result collection is deferred)."""
+        p0 = pairs[0]
+        run = lambda ent: ctx.refine_rectify_sequence(ent, CONST_ACC, False, p0["K4"], p0["gamma"], layout=capi.DEPTH_ROWMAJOR)
+        run(seq_entries(0, warmup, host))
+        ent = seq_entries(warmup, steps, host)
+        barrier()
+        l0 = ctx.launch_count()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        res = run(ent)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ctx.launch_count() - l0, sum(r["summary"]["iterations"] for r in res)
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ctx.profile_enable(True)
-    ms, launches, its = timed(step_device, args.steps, args.warmup)
+    ms, launches, its = timed_sequence(False, args.steps, args.warmup)
     prof = ctx.profile_read()
     ctx.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
@@ -224,7 +254,10 @@ def run_ours(args):
         r = step_device(ctx, capi, pairs[i])
         lm_ms += r["summary"]["device_ms"] / max(r["summary"]["iterations"], 1)
     lm_ms /= min(args.steps, N_PAIRS)
-    ms_e2e, _, _ = timed(step_host, args.steps, max(3, min(args.warmup, 3)))
+    ms_e2e, _, _ = timed_sequence(True, args.steps, max(3, min(args.warmup, 3)))
+    # the same step through one synchronous rsdsfm_refine_rectify call per pair (no overlap between pairs)
+    ms_single, _, _ = timed(step_device, args.steps, 3)
+    ms_single_host, _, _ = timed(step_host, args.steps, 3)
 
     p0 = pairs[0]
     h2d = sum(p0["host"][k].nbytes for k in ("flow", "inliers3", "alpha", "alpha_k", "image"))
@@ -273,7 +306,12 @@ def run_ours(args):
                 "kernel_ms_per_solve": prof["kernel_ms"] / max(prof["kernel_launches"], 1)},
             "clocks": clocks,
             "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
+                    "api": "rsdsfm_refine_rectify_sequence, pinned host buffers: upload of pair i+1 and download of pair i-1 "
+                           "overlap the compute of pair i",
+                    "single_call_ms_per_step": ms_single_host / args.steps},
+            "api": "rsdsfm_refine_rectify_sequence over `steps` pairs, device buffers",
+            "single_call_ms_per_step": ms_single / args.steps,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm",
                          "kernel": "k_lm_persistent<%d> (persistent LM solve: fused candidate-step + residual/Jacobian/Schur "

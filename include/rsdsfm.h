@@ -206,6 +206,74 @@ RSDSFM_API int rsdsfm_refine_rectify(rsdsfm_ctx *ctx, int mem, const double *flo
                           const double *K4, double gamma, int layout, double *z_out, double *depth_map,
                           uint8_t *rectified, rsdsfm_lm_summary *summary);
 
+/* ---- the same step over a sequence of frame pairs, software-pipelined ---------------------- */
+/* One entry per frame pair: the arguments of rsdsfm_refine_rectify that change from pair to
+ * pair.  v,w,k are in/out (start motion = the RANSAC winner; refined and sign-fixed on return). */
+typedef struct rsdsfm_pair_io {
+    const double *flow, *inliers3, *alpha, *alpha_k;   /* as in rsdsfm_refine_rectify */
+    const uint8_t *image;                              /* rows*cols*3 */
+    int m;
+    int status;                                        /* out: RSDSFM_OK or the pair's error code */
+    double v[3], w[3], k;
+    double *z_out, *depth_map;                         /* m, rows*cols */
+    uint8_t *rectified;                                /* rows*cols*3 */
+    rsdsfm_lm_summary summary;                         /* out */
+} rsdsfm_pair_io;
+
+/* The reference handles one frame pair per run (evaluateSingleRun, main.cc:302-560; the sweep in
+ * main.cc:148-300 and errorMeasure.cpp:99-226 repeat it); pairs are independent, so this entry point runs
+ * them as a three-stage pipeline on one GPU: while pair i computes, pair i+1's inputs upload on a
+ * copy stream and pair i-1's outputs download on another (mem = RSDSFM_HOST; use pinned host
+ * memory for the copies to overlap).  With RSDSFM_DEVICE buffers only the result collection is
+ * deferred, so that the GPU never waits for the host between pairs.  Results are identical to
+ * n_pairs calls of rsdsfm_refine_rectify.  Returns the first failing pair's code (all pairs are
+ * attempted; see rsdsfm_pair_io.status). */
+RSDSFM_API int rsdsfm_refine_rectify_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm_pair_io *pairs,
+                          int const_acceleration, int gs_mode, int rows, int cols, const double *K4,
+                          double gamma, int layout);
+
+/* ---- a2..a15 in one call: evaluateSingleRun's compute (main.cc:398-523) --------------------- */
+typedef struct rsdsfm_pipeline_params {
+    int rows, cols;
+    double K4[4];               /* fx, fy, cx, cy */
+    double gamma;               /* readout ratio (main.cc:321) */
+    double flow_threshold;      /* 1e-10 in the reference (main.cc:311) */
+    double ransac_tolerance;    /* main.cc:310 */
+    int num_hypotheses;         /* RANSAC trials H (main.cc:304) */
+    int const_acceleration;     /* use_acceleration_mode */
+    int gs_mode;                /* use_global_shutter_mode: alpha := 1 (main.cc:441-444), backProjectGs */
+    int use_refinement;         /* main.cc:457 */
+    int repair_pairing;         /* 0 = reference behaviour (residual i reads flow(:, i));
+                                 * 1 = residual i reads the flow of inlier i */
+    int layout;                 /* depth_map layout, RSDSFM_DEPTH_* */
+} rsdsfm_pipeline_params;
+
+typedef struct rsdsfm_pipeline_io {
+    const double *flow_img;     /* rows*cols*2 (dx, dy) row-major, in `mem` */
+    const uint8_t *image;       /* rows*cols*3 BGR, in `mem` */
+    const int32_t *samples;     /* host, H*9 indices into the flattened order, or NULL */
+    const uint32_t *draws;      /* host, H*9 raw rand() values mapped to indices exactly like
+                                 * minimal.cc:226-244 (rand() % n_temp on a persistent index vector);
+                                 * used when samples == NULL */
+    double *depth_map;          /* out, rows*cols, in `mem` */
+    uint8_t *rectified;         /* out, rows*cols*3, in `mem` */
+    /* results (host) */
+    int status;
+    int n, m, best_idx;         /* valid flow vectors, consensus-set size, winning trial */
+    double ransac_motion[7];    /* v, w, k of the winning hypothesis */
+    double v[3], w[3], k;       /* final motion (refined when use_refinement), sign-fixed */
+    rsdsfm_lm_summary summary;
+} rsdsfm_pipeline_io;
+
+/* flatten -> alpha -> RANSAC (fit + score + gather) -> [refine] -> sign fix -> depth raster ->
+ * setPose -> backProject(Gs) -> interpolateCrackyImage, intermediates never leave the device. */
+RSDSFM_API int rsdsfm_pipeline_pair(rsdsfm_ctx *ctx, int mem, const rsdsfm_pipeline_params *params,
+                          rsdsfm_pipeline_io *io);
+/* The same over a sequence; with RSDSFM_HOST buffers the next pair's flow/image upload and the
+ * previous pair's download overlap the current pair's compute. */
+RSDSFM_API int rsdsfm_pipeline_sequence(rsdsfm_ctx *ctx, int mem, const rsdsfm_pipeline_params *params, int n_pairs,
+                          rsdsfm_pipeline_io *pairs);
+
 #ifdef __cplusplus
 }
 #endif

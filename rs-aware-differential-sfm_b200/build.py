@@ -16,12 +16,13 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 # reference's scalar IEEE arithmetic (RANSAC inlier sets, integer splat targets, alpha factors).
 UNITS = [
     ("api.cu", []),
+    ("pipeline.cu", []),
     ("refine.cu", []),
     ("ransac.cu", ["--fmad=false"]),
     ("rectify.cu", ["--fmad=false"]),
     ("preproc.cu", ["--fmad=false"]),
 ]
-HEADERS = ["common.cuh", "lm_controller.h", "rs_math.cuh", "solve9.h", os.path.join("..", "..", "include", "rsdsfm.h")]
+HEADERS = ["common.cuh", "stages.h", "lm_controller.h", "rs_math.cuh", "solve9.h", os.path.join("..", "..", "include", "rsdsfm.h")]
 
 
 def _nvcc():

@@ -20,7 +20,7 @@ EXPORTS = [
     "rsdsfm_synchronize", "rsdsfm_launch_count", "rsdsfm_profile_enable", "rsdsfm_profile_read", "rsdsfm_profile_detail", "rsdsfm_flatten", "rsdsfm_alpha", "rsdsfm_solve9",
     "rsdsfm_ransac_score", "rsdsfm_ransac", "rsdsfm_gather_inliers", "rsdsfm_estimate_inverse_depths",
     "rsdsfm_refine", "rsdsfm_depth_glue", "rsdsfm_set_relative_pose", "rsdsfm_backproject", "rsdsfm_fill_cracks",
-    "rsdsfm_refine_rectify",
+    "rsdsfm_refine_rectify", "rsdsfm_refine_rectify_sequence", "rsdsfm_pipeline_pair", "rsdsfm_pipeline_sequence",
 ]
 
 
@@ -41,6 +41,32 @@ class LmSummary(C.Structure):
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class PairIO(C.Structure):
+    """rsdsfm_pair_io (include/rsdsfm.h)."""
+    _fields_ = [("flow", C.c_void_p), ("inliers3", C.c_void_p), ("alpha", C.c_void_p), ("alpha_k", C.c_void_p),
+                ("image", C.c_void_p), ("m", C.c_int), ("status", C.c_int),
+                ("v", C.c_double * 3), ("w", C.c_double * 3), ("k", C.c_double),
+                ("z_out", C.c_void_p), ("depth_map", C.c_void_p), ("rectified", C.c_void_p),
+                ("summary", LmSummary)]
+
+
+class PipelineParams(C.Structure):
+    """rsdsfm_pipeline_params (include/rsdsfm.h)."""
+    _fields_ = [("rows", C.c_int), ("cols", C.c_int), ("K4", C.c_double * 4), ("gamma", C.c_double),
+                ("flow_threshold", C.c_double), ("ransac_tolerance", C.c_double), ("num_hypotheses", C.c_int),
+                ("const_acceleration", C.c_int), ("gs_mode", C.c_int), ("use_refinement", C.c_int),
+                ("repair_pairing", C.c_int), ("layout", C.c_int)]
+
+
+class PipelineIO(C.Structure):
+    """rsdsfm_pipeline_io (include/rsdsfm.h)."""
+    _fields_ = [("flow_img", C.c_void_p), ("image", C.c_void_p), ("samples", C.c_void_p), ("draws", C.c_void_p),
+                ("depth_map", C.c_void_p), ("rectified", C.c_void_p),
+                ("status", C.c_int), ("n", C.c_int), ("m", C.c_int), ("best_idx", C.c_int),
+                ("ransac_motion", C.c_double * 7), ("v", C.c_double * 3), ("w", C.c_double * 3), ("k", C.c_double),
+                ("summary", LmSummary)]
 
 
 _lib = None
@@ -340,6 +366,120 @@ class Context:
                                                 _ptr(K4), C.c_double(gamma), int(layout), _ptr(z), _ptr(dm), _ptr(rect),
                                                 C.byref(S)))
         return dict(v=v, w=w, k=kk.value, z=z, depth_map=dm, rectified=rect, summary=S.as_dict())
+
+    def refine_rectify_sequence(self, pairs, const_acc, gs_mode, K4, gamma, layout=DEPTH_COLMAJOR):
+        """rsdsfm_refine_rectify_sequence.  `pairs`: list of dicts with flow, inliers3, alpha, alpha_k,
+        image, m, v, w, k and optionally out=(z, depth_map, rectified) (pinned numpy or torch CUDA; all
+        pairs host or all device).  Returns one dict per pair like refine_rectify (+ status)."""
+        n = len(pairs)
+        arr = (PairIO * max(n, 1))()
+        keep, outs, mems = [], [], set()
+        rows = cols = 0
+        for i, p in enumerate(pairs):
+            flow = _f64(p["flow"]); inl = _f64(p["inliers3"]); a = _f64(p["alpha"]); ak = _f64(p["alpha_k"])
+            image = p["image"]
+            m = int(p["m"])
+            rows, cols = int(image.shape[0]), int(image.shape[1])
+            if p.get("out") is not None:
+                z, dm, rect = p["out"]
+            elif _is_torch(flow):
+                import torch
+                z = torch.empty(m, dtype=torch.float64, device=flow.device)
+                dm = torch.empty(rows * cols, dtype=torch.float64, device=flow.device)
+                rect = torch.empty_like(image)
+            else:
+                image = np.ascontiguousarray(image, dtype=np.uint8)
+                z = np.empty(m); dm = np.empty(rows * cols); rect = np.empty_like(image)
+            mems.add(_mem(flow, inl, a, ak, image, z, dm, rect))
+            keep.append((flow, inl, a, ak, image))
+            outs.append((z, dm, rect))
+            e = arr[i]
+            e.flow, e.inliers3, e.alpha, e.alpha_k, e.image = (_ptr(x).value for x in (flow, inl, a, ak, image))
+            e.m = m
+            e.v[:] = list(_small(p["v"], 3)); e.w[:] = list(_small(p["w"], 3)); e.k = float(p["k"])
+            e.z_out, e.depth_map, e.rectified = _ptr(z).value, _ptr(dm).value, _ptr(rect).value
+        if len(mems) > 1:
+            raise ValueError("mixing host and device pairs in one sequence")
+        K4 = _small(K4, 4)
+        rc = self.lib.rsdsfm_refine_rectify_sequence(self.h, mems.pop() if mems else HOST, n, arr, int(const_acc), int(gs_mode),
+                                                     rows, cols, _ptr(K4), C.c_double(gamma), int(layout))
+        res = []
+        for i in range(n):
+            e = arr[i]
+            z, dm, rect = outs[i]
+            res.append(dict(v=np.array(e.v[:]), w=np.array(e.w[:]), k=float(e.k), z=z, depth_map=dm, rectified=rect,
+                            summary=e.summary.as_dict(), status=int(e.status)))
+        self._ck(rc)
+        return res
+
+    # ---- a2..a15 in one call
+    @staticmethod
+    def _pipeline_params(rows, cols, K4, gamma, H, tol, const_acc, gs_mode, use_refinement, repair_pairing, layout, thr):
+        P = PipelineParams()
+        P.rows, P.cols = int(rows), int(cols)
+        P.K4[:] = list(_small(K4, 4))
+        P.gamma, P.flow_threshold, P.ransac_tolerance = float(gamma), float(thr), float(tol)
+        P.num_hypotheses = int(H)
+        P.const_acceleration, P.gs_mode, P.use_refinement = int(const_acc), int(gs_mode), int(use_refinement)
+        P.repair_pairing, P.layout = int(repair_pairing), int(layout)
+        return P
+
+    def pipeline_sequence(self, pairs, K4, gamma, tol, const_acc, gs_mode=False, use_refinement=True, repair_pairing=False,
+                          layout=DEPTH_COLMAJOR, thr=1e-10):
+        """rsdsfm_pipeline_sequence (len(pairs) == 1: rsdsfm_pipeline_pair).  `pairs`: list of dicts with
+        flow_img (rows x cols x 2 f64), image (rows x cols x 3 u8), and samples (H x 9 int32) or draws
+        (H x 9 uint32); optionally out=(depth_map, rectified).  Returns one dict per pair."""
+        n = len(pairs)
+        arr = (PipelineIO * max(n, 1))()
+        keep, outs, mems = [], [], set()
+        rows = cols = H = 0
+        for i, p in enumerate(pairs):
+            fi = _f64(p["flow_img"]); image = p["image"]
+            rows, cols = int(image.shape[0]), int(image.shape[1])
+            smp = drw = None
+            if p.get("samples") is not None:
+                smp = np.ascontiguousarray(p["samples"], dtype=np.int32).reshape(-1, 9); H = smp.shape[0]
+            else:
+                drw = np.ascontiguousarray(p["draws"], dtype=np.uint32).reshape(-1, 9); H = drw.shape[0]
+            if p.get("out") is not None:
+                dm, rect = p["out"]
+            elif _is_torch(fi):
+                import torch
+                dm = torch.empty(rows * cols, dtype=torch.float64, device=fi.device)
+                rect = torch.empty_like(image)
+            else:
+                image = np.ascontiguousarray(image, dtype=np.uint8)
+                dm = np.empty(rows * cols); rect = np.empty_like(image)
+            mems.add(_mem(fi, image, dm, rect))
+            keep.append((fi, image, smp, drw))
+            outs.append((dm, rect))
+            e = arr[i]
+            e.flow_img, e.image = _ptr(fi).value, _ptr(image).value
+            e.samples = _ptr(smp).value if smp is not None else None
+            e.draws = _ptr(drw).value if drw is not None else None
+            e.depth_map, e.rectified = _ptr(dm).value, _ptr(rect).value
+        if len(mems) > 1:
+            raise ValueError("mixing host and device pairs in one sequence")
+        mem = mems.pop() if mems else HOST
+        P = self._pipeline_params(rows, cols, K4, gamma, H, tol, const_acc, gs_mode, use_refinement, repair_pairing, layout, thr)
+        if n == 1:
+            rc = self.lib.rsdsfm_pipeline_pair(self.h, mem, C.byref(P), C.byref(arr[0]))
+        else:
+            rc = self.lib.rsdsfm_pipeline_sequence(self.h, mem, C.byref(P), n, arr)
+        res = []
+        for i in range(n):
+            e = arr[i]
+            dm, rect = outs[i]
+            rm = np.array(e.ransac_motion[:])
+            res.append(dict(status=int(e.status), n=int(e.n), m=int(e.m), best_idx=int(e.best_idx), ransac_v=rm[0:3], ransac_w=rm[3:6],
+                            ransac_k=float(rm[6]), v=np.array(e.v[:]), w=np.array(e.w[:]), k=float(e.k), depth_map=dm,
+                            rectified=rect, summary=e.summary.as_dict()))
+        self._ck(rc)
+        return res
+
+    def pipeline_pair(self, flow_img, image, K4, gamma, tol, const_acc, samples=None, draws=None, **kw):
+        return self.pipeline_sequence([dict(flow_img=flow_img, image=image, samples=samples, draws=draws, out=kw.pop("out", None))],
+                                      K4, gamma, tol, const_acc, **kw)[0]
 
 
 def solve9(q9, u9, alpha9, alpha_k9, use_alpha_k):

@@ -1,39 +1,12 @@
-// api.cu -- the extern "C" layer of include/rsdsfm.h: context management, host<->device staging
-// and the fused "refine + rectify" driver.  No CPU fallback: every compute entry point needs a
-// usable CUDA device and fails with RSDSFM_ERR_CUDA otherwise.
-#include "common.cuh"
-#include "lm_controller.h"
-#include "rs_math.cuh"
+// api.cu -- the extern "C" layer of include/rsdsfm.h: context management and the per-stage entry
+// points with host<->device staging (the fused drivers live in pipeline.cu).  No CPU fallback:
+// every compute entry point needs a usable CUDA device and fails with RSDSFM_ERR_CUDA otherwise.
+#include "stages.h"
 #include "solve9.h"
 
 namespace rsdsfm {
 
 thread_local std::string g_create_error;
-
-// implemented in the other translation units (device pointers, context stream)
-int refine_device(rsdsfm_ctx *, const double *, const double *, const double *, const double *, int, double *, double *,
-                  double *, int, const int32_t *, const rsdsfm_lm_options *, double *, rsdsfm_lm_summary *);
-int refine_async(rsdsfm_ctx *, const double *, const double *, const double *, const double *, int, const double *,
-                 const double *, double, int, const int32_t *, const rsdsfm_lm_options *, double *);
-int lm_collect(rsdsfm_ctx *, int, int, Motion *, rsdsfm_lm_summary *, bool *);
-const double *lm_motion_device(rsdsfm_ctx *);
-int estimate_inverse_depths_device(rsdsfm_ctx *, const double *, const double *, int, const double *, const double *, double,
-                                   const double *, const double *, double *, rsdsfm_lm_summary *);
-int glue_device(rsdsfm_ctx *, double *, int, const double *, int, int, const double *, int, int, double, int, double *,
-                uint8_t *, double *);
-int poses_device(rsdsfm_ctx *, const double *, const double *, double, int, double *, double *);
-int backproject_device(rsdsfm_ctx *, const uint8_t *, const double *, int, int, int, const double *, const double *,
-                       const double *, int, uint8_t *, float *);
-int fill_cracks_device(rsdsfm_ctx *, const uint8_t *, int, int, unsigned, uint8_t *);
-int flatten_device(rsdsfm_ctx *, const double *, int, int, const double *, double, double, double *, double *, double *,
-                   double *, int32_t *, int *);
-int alpha_device(rsdsfm_ctx *, const double *, const double *, int, double, double, double *, double *);
-int gather_inliers_device(rsdsfm_ctx *, const double *, const double *, const double *, int, const uint8_t *,
-                          const double *, double *, double *, double *, int32_t *, int *);
-int ransac_score_device(rsdsfm_ctx *, const double *, const double *, const double *, const double *, int, const double *,
-                        int, double, int *, double *, int *, uint8_t *, double *);
-int ransac_fit_device(rsdsfm_ctx *, const double *, const double *, const double *, const double *, int, int,
-                      const int32_t *, int, double *);
 
 static int finish_host_call(rsdsfm_ctx *ctx, int mem)
 {
@@ -95,8 +68,10 @@ int rsdsfm_create(int device, void *cuda_stream, rsdsfm_ctx **out)
     }
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
-    cudaEventCreate(&ctx->pe0);
-    cudaEventCreate(&ctx->pe1);
+    for (int j = 0; j < 2; ++j) { cudaEventCreate(&ctx->pe0[j]); cudaEventCreate(&ctx->pe1[j]); }
+    e = cudaMallocHost(&ctx->pinned_io, 2 * kPinnedSlotBytes);
+    if (e != cudaSuccess) { rsdsfm_destroy(ctx); return fail(nullptr, RSDSFM_ERR_NOMEM, "cudaMallocHost", e); }
+    memset(ctx->pinned_io, 0, 2 * kPinnedSlotBytes);
     *out = ctx;
     return RSDSFM_OK;
 }
@@ -106,16 +81,25 @@ void rsdsfm_destroy(rsdsfm_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->s_in) { cudaStreamSynchronize(ctx->s_in); cudaStreamDestroy(ctx->s_in); }
+    if (ctx->s_out) { cudaStreamSynchronize(ctx->s_out); cudaStreamDestroy(ctx->s_out); }
+    for (int j = 0; j < 2; ++j) {
+        if (ctx->ev_in[j]) cudaEventDestroy(ctx->ev_in[j]);
+        if (ctx->ev_cdone[j]) cudaEventDestroy(ctx->ev_cdone[j]);
+        if (ctx->ev_out[j]) cudaEventDestroy(ctx->ev_out[j]);
+        if (ctx->pe0[j]) cudaEventDestroy(ctx->pe0[j]);
+        if (ctx->pe1[j]) cudaEventDestroy(ctx->pe1[j]);
+    }
+    if (ctx->pinned_io) cudaFreeHost(ctx->pinned_io);
     DevBuf *all[] = {&ctx->partials, &ctx->sums, &ctx->pix, &ctx->dA, &ctx->dB, &ctx->scale_e, &ctx->misc, &ctx->winner,
                      &ctx->tmp_img, &ctx->depth_rm, &ctx->poses, &ctx->hyp, &ctx->rpart, &ctx->flags, &ctx->scan,
                      &ctx->lm_shared, &ctx->exc};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (auto &b : ctx->stage) if (b.p) cudaFree(b.p);
+    for (auto &b : ctx->pipe) if (b.p) cudaFree(b.p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->pe0) cudaEventDestroy(ctx->pe0);
-    if (ctx->pe1) cudaEventDestroy(ctx->pe1);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -417,69 +401,6 @@ int rsdsfm_fill_cracks(rsdsfm_ctx *ctx, int mem, const uint8_t *in, int rows, in
     RS_TRY(fill_cracks_device(ctx, (const uint8_t *)d_in, rows, cols, offset, (uint8_t *)d_out));
     RS_TRY(stage_out(ctx, mem, out, d_out, tot * 3));
     return finish_host_call(ctx, mem);
-}
-
-int rsdsfm_refine_rectify(rsdsfm_ctx *ctx, int mem, const double *flow, const double *inliers3, const double *alpha,
-                          const double *alpha_k, int m, double *v, double *w, double *k, int const_acceleration,
-                          int gs_mode, const uint8_t *image, int rows, int cols, const double *K4, double gamma, int layout,
-                          double *z_out, double *depth_map, uint8_t *rectified, rsdsfm_lm_summary *summary)
-{
-    RS_ENTER(ctx);
-    if (m <= 0 || rows <= 0 || cols <= 0 || !flow || !inliers3 || !alpha || !alpha_k || !v || !w || !k || !image || !K4 ||
-        !z_out || !depth_map || !rectified)
-        return fail(ctx, RSDSFM_ERR_ARG, "rsdsfm_refine_rectify: bad argument");
-    const size_t mm = (size_t)m, tot = (size_t)rows * cols;
-    const void *d_f = nullptr, *d_i = nullptr, *d_a = nullptr, *d_ak = nullptr, *d_img = nullptr;
-    void *d_z = nullptr, *d_dm = nullptr, *d_out = nullptr;
-    RS_TRY(stage_in(ctx, mem, 0, flow, sizeof(double) * 2 * mm, &d_f));
-    RS_TRY(stage_in(ctx, mem, 1, inliers3, sizeof(double) * 3 * mm, &d_i));
-    RS_TRY(stage_in(ctx, mem, 2, alpha, sizeof(double) * mm, &d_a));
-    RS_TRY(stage_in(ctx, mem, 3, alpha_k, sizeof(double) * mm, &d_ak));
-    RS_TRY(stage_in(ctx, mem, 4, image, tot * 3, &d_img));
-    RS_TRY(stage_out_reserve(ctx, mem, 5, z_out, sizeof(double) * mm, &d_z));
-    RS_TRY(stage_out_reserve(ctx, mem, 6, depth_map, sizeof(double) * tot, &d_dm));
-    RS_TRY(stage_out_reserve(ctx, mem, 7, rectified, tot * 3, &d_out));
-    rsdsfm_lm_summary local;
-    if (!summary) summary = &local;
-    memset(summary, 0, sizeof *summary);
-    RS_TRY(ensure(ctx, ctx->misc, 256));
-    RS_TRY(ensure(ctx, ctx->poses, sizeof(double) * 12 * (size_t)rows));
-    RS_TRY(ensure(ctx, ctx->tmp_img, tot * 3));
-    double *stats = (double *)ctx->misc.p;
-    double *dR = (double *)ctx->poses.p, *dt = dR + 9 * (size_t)rows;
-    const int nf = const_acceleration ? 7 : 6;
-    // Everything below is queued on the context's stream without a host round trip: the refined
-    // motion stays in the solver's device control block and feeds the pose kernel directly.
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        // nonLinearRefinement (main.cc:457)
-        RS_TRY(refine_async(ctx, (const double *)d_f, (const double *)d_i, (const double *)d_a, (const double *)d_ak, m, v, w,
-                            *k, const_acceleration, nullptr, nullptr, (double *)d_z));
-        // sign fix + depth raster (main.cc:466-509)
-        RS_TRY(glue_device(ctx, (double *)d_z, 1, (const double *)d_i, 3, m, K4, rows, cols, INFINITY, layout, (double *)d_dm,
-                           nullptr, stats));
-        // setPose (main.cc:516) -> per-scanline poses, with the sign-fixed v
-        RS_TRY(poses_device(ctx, lm_motion_device(ctx), stats, gamma, rows, dR, dt));
-        // backProject / backProjectGs (main.cc:518-522) + interpolateCrackyImage (main.cc:523)
-        RS_TRY(backproject_device(ctx, (const uint8_t *)d_img, (const double *)d_dm, layout, rows, cols, K4, dR, dt, gs_mode,
-                                  (uint8_t *)ctx->tmp_img.p, nullptr));
-        RS_TRY(fill_cracks_device(ctx, (const uint8_t *)ctx->tmp_img.p, rows, cols, 1, (uint8_t *)d_out));
-        RS_TRY(stage_out(ctx, mem, z_out, d_z, sizeof(double) * mm));
-        RS_TRY(stage_out(ctx, mem, depth_map, d_dm, sizeof(double) * tot));
-        RS_TRY(stage_out(ctx, mem, rectified, d_out, tot * 3));
-        double *hstats = (double *)((char *)ctx->pinned + ctx->pinned_cap - 256);
-        RS_CUDA(ctx, cudaMemcpyAsync(hstats, stats, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        Motion mot;
-        for (int j = 0; j < 3; ++j) { mot.v[j] = v[j]; mot.w[j] = w[j]; }
-        mot.k = *k;
-        bool overflow = false;
-        RS_TRY(lm_collect(ctx, nf, m, &mot, summary, &overflow));      // the one synchronisation of the step
-        if (overflow) continue;                                         // exception list enlarged: run again
-        const double sign = (hstats[3] < 0) ? -1.0 : 1.0;
-        for (int j = 0; j < 3; ++j) { v[j] = mot.v[j] * sign; w[j] = mot.w[j]; }
-        *k = mot.k;
-        return RSDSFM_OK;
-    }
-    return fail(ctx, RSDSFM_ERR_INTERNAL, "refine_rectify: exception list overflow persisted");
 }
 
 }  // extern "C"

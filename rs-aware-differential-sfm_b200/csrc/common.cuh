@@ -38,12 +38,20 @@ struct rsdsfm_ctx {
     std::vector<rsdsfm::DevBuf *> bufs;
     rsdsfm::DevBuf partials, sums, pix, dA, dB, scale_e, misc, stage[16], winner, tmp_img, depth_rm, poses;
     rsdsfm::DevBuf hyp, rpart, flags, scan, lm_shared, exc;
+    rsdsfm::DevBuf pipe[16];  // intermediates of the fused a2-a15 driver (pipeline.cu)
     int exc_cap = 0;          // capacity (entries) of the clamped-pixel exception list
     void *pinned = nullptr;   // small pinned host buffer for reduced sums / scalars
     size_t pinned_cap = 0;
+    // Pipelined sequences (pipeline.cu): while pair i computes on `stream`, pair i+1 uploads on
+    // `s_in` and pair i-1 downloads on `s_out`.  Two I/O slots: staging buffers stage[8*slot+j]
+    // and a pinned slot area (LM control block in/out + depth statistics) each.
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cdone[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    int io_slot = 0;
+    void *pinned_io = nullptr;   // 2 x kPinnedSlotBytes, allocated with the context
     // per-kernel profiling (bench.py's roofline): CUDA events around the LM passes
     bool profile = false;
-    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    cudaEvent_t pe0[2] = {nullptr, nullptr}, pe1[2] = {nullptr, nullptr};   // per I/O slot
     double prof_detail[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // ms: pass A pixel loop / CTA reduce / controller, same for pass B
     double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // [0] pass A ms, [1] pass A phases, [2] pass A residual blocks,
                                                  // [3] pass B ms, [4] pass B phases, [5] pass B residual blocks,
@@ -53,6 +61,14 @@ struct rsdsfm_ctx {
 namespace rsdsfm {
 
 extern thread_local std::string g_create_error;
+
+// pinned slot area: [0, 8192) control block read back, [8192, 16128) initial control block,
+// [16128, 16384) depth statistics
+constexpr size_t kPinnedSlotBytes = 16384;
+inline char *pinned_slot(rsdsfm_ctx *ctx) { return (char *)ctx->pinned_io + kPinnedSlotBytes * (size_t)ctx->io_slot; }
+inline void *pinned_lm_result(rsdsfm_ctx *ctx) { return pinned_slot(ctx); }
+inline void *pinned_lm_init(rsdsfm_ctx *ctx) { return pinned_slot(ctx) + 8192; }
+inline double *pinned_stats(rsdsfm_ctx *ctx) { return (double *)(pinned_slot(ctx) + kPinnedSlotBytes - 256); }
 
 inline int fail(rsdsfm_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess)
 {
@@ -99,11 +115,12 @@ inline int ensure_pinned(rsdsfm_ctx *ctx, size_t bytes)
 }
 
 // Stage an input array: returns a device pointer holding `bytes` of `src` (which lives in `mem`).
-inline int stage_in(rsdsfm_ctx *ctx, int mem, int slot, const void *src, size_t bytes, const void **dev)
+inline int stage_in(rsdsfm_ctx *ctx, int mem, int slot, const void *src, size_t bytes, const void **dev,
+                    cudaStream_t on = nullptr)
 {
     if (mem == RSDSFM_DEVICE || src == nullptr) { *dev = src; return RSDSFM_OK; }
     RS_TRY(ensure(ctx, ctx->stage[slot], bytes));
-    RS_CUDA(ctx, cudaMemcpyAsync(ctx->stage[slot].p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    RS_CUDA(ctx, cudaMemcpyAsync(ctx->stage[slot].p, src, bytes, cudaMemcpyHostToDevice, on ? on : ctx->stream));
     *dev = ctx->stage[slot].p;
     return RSDSFM_OK;
 }
@@ -115,10 +132,10 @@ inline int stage_out_reserve(rsdsfm_ctx *ctx, int mem, int slot, void *dst, size
     *dev = ctx->stage[slot].p;
     return RSDSFM_OK;
 }
-inline int stage_out(rsdsfm_ctx *ctx, int mem, void *dst, const void *dev, size_t bytes)
+inline int stage_out(rsdsfm_ctx *ctx, int mem, void *dst, const void *dev, size_t bytes, cudaStream_t on = nullptr)
 {
     if (mem == RSDSFM_DEVICE || dst == nullptr || bytes == 0) return RSDSFM_OK;
-    RS_CUDA(ctx, cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    RS_CUDA(ctx, cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, on ? on : ctx->stream));
     return RSDSFM_OK;
 }
 

@@ -1,0 +1,483 @@
+// pipeline.cu -- the fused drivers behind include/rsdsfm.h:
+//   rsdsfm_refine_rectify            main.cc:457-523 for one frame pair, one host synchronisation
+//   rsdsfm_refine_rectify_sequence   the same over a sequence, three-stage software pipeline
+//                                    (upload i+1 | compute i | download i-1) on three streams
+//   rsdsfm_pipeline_pair / _sequence main.cc:398-523 (flatten .. crack fill) without leaving the device
+// Everything here composes the stage functions of stages.h; there is no arithmetic in this file
+// apart from the reference's sample draw (minimal.cc:226-244) on the host.
+#include <unordered_map>
+
+#include "stages.h"
+
+namespace rsdsfm {
+
+// ---- one "refine + rectify" step on device pointers --------------------------------------------
+struct StepArgs {
+    const double *flow, *inliers3, *alpha, *alpha_k;
+    const int32_t *flow_index;
+    const uint8_t *image;
+    int m, const_acc, gs_mode, rows, cols, layout;
+    const double *K4;
+    double gamma;
+    double *z, *depth_map;
+    uint8_t *rectified;
+};
+
+// Queues the whole step on ctx->stream, including the small read-backs (LM control block, depth
+// statistics) into the current I/O slot's pinned area.  No synchronisation.
+static int queue_step(rsdsfm_ctx *ctx, const StepArgs &a, const double *v, const double *w, double k)
+{
+    const size_t tot = (size_t)a.rows * a.cols;
+    RS_TRY(ensure(ctx, ctx->misc, 256));
+    RS_TRY(ensure(ctx, ctx->poses, sizeof(double) * 12 * (size_t)a.rows));
+    RS_TRY(ensure(ctx, ctx->tmp_img, tot * 3));
+    double *stats = (double *)ctx->misc.p;
+    double *dR = (double *)ctx->poses.p, *dt = dR + 9 * (size_t)a.rows;
+    // nonLinearRefinement (main.cc:457): the refined motion stays in the solver's device control
+    // block and feeds the pose kernel directly
+    RS_TRY(refine_async(ctx, a.flow, a.inliers3, a.alpha, a.alpha_k, a.m, v, w, k, a.const_acc, a.flow_index, nullptr, a.z));
+    // sign fix + depth raster (main.cc:466-509)
+    RS_TRY(glue_device(ctx, a.z, 1, a.inliers3, 3, a.m, a.K4, a.rows, a.cols, INFINITY, a.layout, a.depth_map, nullptr, stats));
+    // setPose (main.cc:516) -> per-scanline poses, with the sign-fixed v
+    RS_TRY(poses_device(ctx, lm_motion_device(ctx), stats, a.gamma, a.rows, dR, dt));
+    // backProject / backProjectGs (main.cc:518-522) + interpolateCrackyImage (main.cc:523)
+    RS_TRY(backproject_device(ctx, a.image, a.depth_map, a.layout, a.rows, a.cols, a.K4, dR, dt, a.gs_mode,
+                              (uint8_t *)ctx->tmp_img.p, nullptr));
+    RS_TRY(fill_cracks_device(ctx, (const uint8_t *)ctx->tmp_img.p, a.rows, a.cols, 1, a.rectified));
+    RS_CUDA(ctx, cudaMemcpyAsync(pinned_stats(ctx), stats, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    return lm_collect_enqueue(ctx);
+}
+
+// Parses the current I/O slot's read-backs (which must have completed).
+static int finish_step(rsdsfm_ctx *ctx, int nf, int m, double *v, double *w, double *k, rsdsfm_lm_summary *summary,
+                       bool *overflow)
+{
+    Motion mot;
+    for (int j = 0; j < 3; ++j) { mot.v[j] = v[j]; mot.w[j] = w[j]; }
+    mot.k = *k;
+    RS_TRY(lm_collect_finish(ctx, nf, m, &mot, summary, overflow));
+    if (*overflow) return RSDSFM_OK;
+    const double sign = (pinned_stats(ctx)[3] < 0) ? -1.0 : 1.0;      // z_mean < 0: v *= -1 (main.cc:475-478)
+    for (int j = 0; j < 3; ++j) { v[j] = mot.v[j] * sign; w[j] = mot.w[j]; }
+    *k = mot.k;
+    return RSDSFM_OK;
+}
+
+static int ensure_io(rsdsfm_ctx *ctx)
+{
+    if (ctx->s_in) return RSDSFM_OK;
+    RS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    RS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    for (int j = 0; j < 2; ++j) {
+        RS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[j], cudaEventDisableTiming));
+        RS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_cdone[j], cudaEventDisableTiming));
+        RS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_out[j], cudaEventDisableTiming));
+    }
+    return RSDSFM_OK;
+}
+
+static void drain(rsdsfm_ctx *ctx)
+{
+    if (ctx->s_in) cudaStreamSynchronize(ctx->s_in);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->s_out) cudaStreamSynchronize(ctx->s_out);
+}
+
+// Synchronous step with the caller's buffers in `mem` (I/O slot `slot`).
+static int step_sync(rsdsfm_ctx *ctx, int mem, int slot, const double *flow, const double *inliers3, const double *alpha,
+                     const double *alpha_k, int m, double *v, double *w, double *k, int const_acc, int gs_mode,
+                     const uint8_t *image, int rows, int cols, const double *K4, double gamma, int layout, double *z_out,
+                     double *depth_map, uint8_t *rectified, rsdsfm_lm_summary *summary)
+{
+    const size_t mm = (size_t)m, tot = (size_t)rows * cols;
+    const int b = 8 * slot;
+    ctx->io_slot = slot;
+    const void *d_f = nullptr, *d_i = nullptr, *d_a = nullptr, *d_ak = nullptr, *d_img = nullptr;
+    void *d_z = nullptr, *d_dm = nullptr, *d_out = nullptr;
+    RS_TRY(stage_in(ctx, mem, b + 0, flow, sizeof(double) * 2 * mm, &d_f));
+    RS_TRY(stage_in(ctx, mem, b + 1, inliers3, sizeof(double) * 3 * mm, &d_i));
+    RS_TRY(stage_in(ctx, mem, b + 2, alpha, sizeof(double) * mm, &d_a));
+    RS_TRY(stage_in(ctx, mem, b + 3, alpha_k, sizeof(double) * mm, &d_ak));
+    RS_TRY(stage_in(ctx, mem, b + 4, image, tot * 3, &d_img));
+    RS_TRY(stage_out_reserve(ctx, mem, b + 5, z_out, sizeof(double) * mm, &d_z));
+    RS_TRY(stage_out_reserve(ctx, mem, b + 6, depth_map, sizeof(double) * tot, &d_dm));
+    RS_TRY(stage_out_reserve(ctx, mem, b + 7, rectified, tot * 3, &d_out));
+    rsdsfm_lm_summary local;
+    if (!summary) summary = &local;
+    memset(summary, 0, sizeof *summary);
+    StepArgs a{(const double *)d_f, (const double *)d_i, (const double *)d_a, (const double *)d_ak, nullptr,
+               (const uint8_t *)d_img, m, const_acc, gs_mode, rows, cols, layout, K4, gamma,
+               (double *)d_z, (double *)d_dm, (uint8_t *)d_out};
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        RS_TRY(queue_step(ctx, a, v, w, *k));
+        RS_TRY(stage_out(ctx, mem, z_out, d_z, sizeof(double) * mm));
+        RS_TRY(stage_out(ctx, mem, depth_map, d_dm, sizeof(double) * tot));
+        RS_TRY(stage_out(ctx, mem, rectified, d_out, tot * 3));
+        RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));               // the one synchronisation of the step
+        bool overflow = false;
+        RS_TRY(finish_step(ctx, const_acc ? 7 : 6, m, v, w, k, summary, &overflow));
+        if (!overflow) return RSDSFM_OK;                                 // else: exception list enlarged, run again
+    }
+    return fail(ctx, RSDSFM_ERR_INTERNAL, "refine_rectify: exception list overflow persisted");
+}
+
+static bool pair_args_ok(const rsdsfm_pair_io &p)
+{
+    return p.m > 0 && p.flow && p.inliers3 && p.alpha && p.alpha_k && p.image && p.z_out && p.depth_map && p.rectified;
+}
+
+// ---- a2..a15 on device pointers ------------------------------------------------------------------
+// minimal.cc:226-244: every trial draws 9 indices with rand() % n_temp from an index vector that
+// persists (with its swaps) across trials.  The vector is kept sparse: only displaced entries.
+static void draws_to_samples(const uint32_t *draws, int H, int n, std::vector<int32_t> &samples)
+{
+    std::unordered_map<int, int> moved;
+    auto at = [&](int i) { auto it = moved.find(i); return it == moved.end() ? i : it->second; };
+    samples.resize((size_t)H * 9);
+    for (int t = 0; t < H; ++t) {
+        int n_temp = n;
+        for (int j = 0; j < 9; ++j) {
+            const int c = (int)(draws[(size_t)t * 9 + j] % (uint32_t)n_temp);
+            const int last = at(n_temp - 1), pick = at(c);
+            moved[n_temp - 1] = pick;                                    // std::swap(indices[n_temp-1], indices[c])
+            moved[c] = last;
+            samples[(size_t)t * 9 + j] = pick;
+            n_temp--;
+        }
+    }
+}
+
+__global__ void k_fill_double(double *p, int n, double val)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = val;
+}
+
+static int pipeline_device(rsdsfm_ctx *ctx, const rsdsfm_pipeline_params &P, const double *d_flow_img, const uint8_t *d_image,
+                           rsdsfm_pipeline_io *io, double *d_dm, uint8_t *d_out)
+{
+    const size_t tot = (size_t)P.rows * P.cols;
+    const int H = P.num_hypotheses;
+    io->n = io->m = 0; io->best_idx = -1;
+    memset(&io->summary, 0, sizeof io->summary);
+    DevBuf *B = ctx->pipe;
+    RS_TRY(ensure(ctx, B[0], sizeof(double) * 2 * tot));   // coord
+    RS_TRY(ensure(ctx, B[1], sizeof(double) * 2 * tot));   // flow
+    RS_TRY(ensure(ctx, B[2], sizeof(double) * 2 * tot));   // coord_px
+    RS_TRY(ensure(ctx, B[3], sizeof(double) * 2 * tot));   // flow_px
+    RS_TRY(ensure(ctx, B[4], sizeof(int32_t) * tot));      // pixel index
+    double *coord = (double *)B[0].p, *flow = (double *)B[1].p, *cpx = (double *)B[2].p, *fpx = (double *)B[3].p;
+    int n = 0;
+    RS_TRY(flatten_device(ctx, d_flow_img, P.rows, P.cols, P.K4, P.gamma, P.flow_threshold, coord, flow, cpx, fpx,
+                          (int32_t *)B[4].p, &n));
+    io->n = n;
+    if (n < 9) return fail(ctx, RSDSFM_ERR_ARG, "pipeline: fewer than 9 valid flow vectors");
+    const size_t nn = (size_t)n;
+    RS_TRY(ensure(ctx, B[5], sizeof(double) * nn));        // alpha
+    RS_TRY(ensure(ctx, B[6], sizeof(double) * nn));        // alpha_k
+    RS_TRY(ensure(ctx, B[7], nn));                         // consensus mask of the winner
+    RS_TRY(ensure(ctx, B[8], sizeof(double) * nn));        // its inverse depths
+    RS_TRY(ensure(ctx, B[9], sizeof(double) * 3 * nn));    // inliers3
+    RS_TRY(ensure(ctx, B[10], sizeof(double) * nn));       // alpha of the inliers
+    RS_TRY(ensure(ctx, B[11], sizeof(double) * nn));       // alpha_k of the inliers
+    RS_TRY(ensure(ctx, B[12], sizeof(int32_t) * nn));      // flattened index of the inliers
+    RS_TRY(ensure(ctx, B[13], sizeof(double) * nn));       // z
+    double *alpha = (double *)B[5].p, *alpha_k = (double *)B[6].p;
+    RS_TRY(alpha_device(ctx, fpx, cpx, n, (double)P.rows, P.gamma, alpha, alpha_k));
+    if (P.gs_mode) {                                       // alpha *= 0; alpha += 1 (main.cc:441-444)
+        k_fill_double<<<grid_for(ctx, n, 4), kThreads, 0, ctx->stream>>>(alpha, n, 1.0);
+        ctx->launches++;
+    }
+    std::vector<int32_t> samples;
+    const int32_t *smp = io->samples;
+    if (!smp) { draws_to_samples(io->draws, H, n, samples); smp = samples.data(); }
+    for (size_t i = 0; i < (size_t)H * 9; ++i)
+        if (smp[i] < 0 || smp[i] >= n) return fail(ctx, RSDSFM_ERR_ARG, "pipeline: sample index out of range");
+    std::vector<double> hyps((size_t)H * 7);
+    std::vector<int> counts((size_t)H);
+    std::vector<double> sumerr((size_t)H);
+    RS_TRY(ransac_fit_device(ctx, coord, flow, alpha, alpha_k, n, P.const_acceleration, smp, H, hyps.data()));
+    int best = -1;
+    RS_TRY(ransac_score_device(ctx, coord, flow, alpha, alpha_k, n, hyps.data(), H, P.ransac_tolerance, counts.data(),
+                               sumerr.data(), &best, (uint8_t *)B[7].p, (double *)B[8].p));
+    io->best_idx = best;
+    if (best < 0) return fail(ctx, RSDSFM_ERR_ARG, "pipeline: no RANSAC trial produced a consensus set");
+    // calculateVelocities returns (w, v, k); RansacValues stores v, w, k
+    double v[3], w[3], k;
+    for (int j = 0; j < 3; ++j) { w[j] = hyps[(size_t)best * 7 + j]; v[j] = hyps[(size_t)best * 7 + 3 + j]; }
+    k = hyps[(size_t)best * 7 + 6];
+    for (int j = 0; j < 3; ++j) { io->ransac_motion[j] = v[j]; io->ransac_motion[3 + j] = w[j]; }
+    io->ransac_motion[6] = k;
+    int m = 0;
+    double *inl = (double *)B[9].p;
+    RS_TRY(gather_inliers_device(ctx, coord, alpha, alpha_k, n, (const uint8_t *)B[7].p, (const double *)B[8].p, inl,
+                                 (double *)B[10].p, (double *)B[11].p, (int32_t *)B[12].p, &m));
+    io->m = m;
+    if (m <= 0) return fail(ctx, RSDSFM_ERR_ARG, "pipeline: empty consensus set");
+    if (P.use_refinement) {
+        StepArgs a{flow, inl, (const double *)B[10].p, (const double *)B[11].p,
+                   P.repair_pairing ? (const int32_t *)B[12].p : nullptr, d_image, m, P.const_acceleration, P.gs_mode,
+                   P.rows, P.cols, P.layout, P.K4, P.gamma, (double *)B[13].p, d_dm, d_out};
+        for (int attempt = 0;; ++attempt) {
+            RS_TRY(queue_step(ctx, a, v, w, k));
+            RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            bool overflow = false;
+            RS_TRY(finish_step(ctx, P.const_acceleration ? 7 : 6, m, v, w, &k, &io->summary, &overflow));
+            if (!overflow) break;
+            if (attempt == 1) return fail(ctx, RSDSFM_ERR_INTERNAL, "pipeline: exception list overflow persisted");
+        }
+    } else {
+        // results = ransac_results (main.cc:455): row 2 of the inliers is used as it is
+        RS_TRY(ensure(ctx, ctx->misc, 256));
+        RS_TRY(ensure(ctx, ctx->poses, sizeof(double) * 12 * (size_t)P.rows));
+        RS_TRY(ensure(ctx, ctx->tmp_img, tot * 3));
+        double *stats = (double *)ctx->misc.p, *dmot = stats + 16;
+        double *dR = (double *)ctx->poses.p, *dt = dR + 9 * (size_t)P.rows;
+        double *hm = (double *)pinned_lm_init(ctx);
+        for (int j = 0; j < 3; ++j) { hm[j] = v[j]; hm[3 + j] = w[j]; }
+        hm[6] = k;
+        RS_CUDA(ctx, cudaMemcpyAsync(dmot, hm, sizeof(double) * 7, cudaMemcpyHostToDevice, ctx->stream));
+        RS_TRY(glue_device(ctx, inl + 2, 3, inl, 3, m, P.K4, P.rows, P.cols, INFINITY, P.layout, d_dm, nullptr, stats));
+        RS_TRY(poses_device(ctx, dmot, stats, P.gamma, P.rows, dR, dt));
+        RS_TRY(backproject_device(ctx, d_image, d_dm, P.layout, P.rows, P.cols, P.K4, dR, dt, P.gs_mode,
+                                  (uint8_t *)ctx->tmp_img.p, nullptr));
+        RS_TRY(fill_cracks_device(ctx, (const uint8_t *)ctx->tmp_img.p, P.rows, P.cols, 1, d_out));
+        RS_CUDA(ctx, cudaMemcpyAsync(pinned_stats(ctx), stats, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (pinned_stats(ctx)[3] < 0) for (int j = 0; j < 3; ++j) v[j] *= -1.0;
+        io->summary.termination = RSDSFM_CONVERGENCE;
+    }
+    for (int j = 0; j < 3; ++j) { io->v[j] = v[j]; io->w[j] = w[j]; }
+    io->k = k;
+    return RSDSFM_OK;
+}
+
+static bool pipeline_args_ok(const rsdsfm_pipeline_params *P, const rsdsfm_pipeline_io *io)
+{
+    return P && io && P->rows > 0 && P->cols > 0 && P->num_hypotheses > 0 && io->flow_img && io->image &&
+           (io->samples || io->draws) && io->depth_map && io->rectified;
+}
+
+}  // namespace rsdsfm
+
+using namespace rsdsfm;
+
+#define RS_ENTER(ctx)                                                     \
+    if (!(ctx)) return RSDSFM_ERR_ARG;                                    \
+    RS_CUDA((ctx), cudaSetDevice((ctx)->device))
+
+extern "C" {
+
+int rsdsfm_refine_rectify(rsdsfm_ctx *ctx, int mem, const double *flow, const double *inliers3, const double *alpha,
+                          const double *alpha_k, int m, double *v, double *w, double *k, int const_acceleration,
+                          int gs_mode, const uint8_t *image, int rows, int cols, const double *K4, double gamma, int layout,
+                          double *z_out, double *depth_map, uint8_t *rectified, rsdsfm_lm_summary *summary)
+{
+    RS_ENTER(ctx);
+    if (m <= 0 || rows <= 0 || cols <= 0 || !flow || !inliers3 || !alpha || !alpha_k || !v || !w || !k || !image || !K4 ||
+        !z_out || !depth_map || !rectified)
+        return fail(ctx, RSDSFM_ERR_ARG, "rsdsfm_refine_rectify: bad argument");
+    return step_sync(ctx, mem, 0, flow, inliers3, alpha, alpha_k, m, v, w, k, const_acceleration, gs_mode, image, rows, cols,
+                     K4, gamma, layout, z_out, depth_map, rectified, summary);
+}
+
+int rsdsfm_refine_rectify_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm_pair_io *pairs, int const_acceleration,
+                                   int gs_mode, int rows, int cols, const double *K4, double gamma, int layout)
+{
+    RS_ENTER(ctx);
+    if (n_pairs < 0 || (n_pairs > 0 && !pairs) || rows <= 0 || cols <= 0 || !K4)
+        return fail(ctx, RSDSFM_ERR_ARG, "rsdsfm_refine_rectify_sequence: bad argument");
+    if (n_pairs == 0) return RSDSFM_OK;
+    RS_TRY(ensure_io(ctx));
+    const size_t tot = (size_t)rows * cols;
+    const int nf = const_acceleration ? 7 : 6;
+    const bool host = (mem == RSDSFM_HOST);
+    int first_err = RSDSFM_OK;
+    int max_m = 0;
+    for (int i = 0; i < n_pairs; ++i) {
+        pairs[i].status = pair_args_ok(pairs[i]) ? RSDSFM_OK : RSDSFM_ERR_ARG;
+        memset(&pairs[i].summary, 0, sizeof pairs[i].summary);
+        if (pairs[i].status == RSDSFM_OK && pairs[i].m > max_m) max_m = pairs[i].m;
+        else if (pairs[i].status != RSDSFM_OK && first_err == RSDSFM_OK)
+            first_err = fail(ctx, RSDSFM_ERR_ARG, "rsdsfm_refine_rectify_sequence: bad pair argument");
+    }
+    if (max_m == 0) return first_err;
+    // size every buffer once, before anything is in flight
+    drain(ctx);
+    RS_TRY(lm_reserve(ctx, max_m));
+    if (host)
+        for (int s = 0; s < 2; ++s) {
+            const size_t sz[8] = {sizeof(double) * 2 * (size_t)max_m, sizeof(double) * 3 * (size_t)max_m,
+                                  sizeof(double) * (size_t)max_m, sizeof(double) * (size_t)max_m, tot * 3,
+                                  sizeof(double) * (size_t)max_m, sizeof(double) * tot, tot * 3};
+            for (int j = 0; j < 8; ++j) RS_TRY(ensure(ctx, ctx->stage[8 * s + j], sz[j]));
+        }
+
+    // Pair `j` occupies I/O slot j&1.  In flight at any time: upload of pair i (s_in), compute of
+    // pairs <= i (stream, in order), download of pairs < i (s_out).  A pair is finished (results
+    // parsed on the host) one iteration after it was submitted.
+    int submitted[2] = {-1, -1};                 // pair occupying each slot, not yet finished
+    auto finish = [&](int slot) -> int {
+        const int j = submitted[slot];
+        if (j < 0) return RSDSFM_OK;
+        submitted[slot] = -1;
+        rsdsfm_pair_io &p = pairs[j];
+        RS_CUDA(ctx, cudaEventSynchronize(ctx->ev_out[slot]));
+        ctx->io_slot = slot;
+        bool overflow = false;
+        int rc = finish_step(ctx, nf, p.m, p.v, p.w, &p.k, &p.summary, &overflow);
+        if (rc == RSDSFM_OK && overflow) {
+            // Exception list too small for this pair (it has been enlarged): let everything in
+            // flight complete, keep the other slot's read-backs, and redo this pair synchronously.
+            drain(ctx);
+            rc = step_sync(ctx, mem, slot, p.flow, p.inliers3, p.alpha, p.alpha_k, p.m, p.v, p.w, &p.k, const_acceleration,
+                           gs_mode, p.image, rows, cols, K4, gamma, layout, p.z_out, p.depth_map, p.rectified, &p.summary);
+        }
+        p.status = rc;
+        return rc;
+    };
+
+    for (int i = 0; i < n_pairs; ++i) {
+        rsdsfm_pair_io &p = pairs[i];
+        if (p.status != RSDSFM_OK) continue;
+        const int s = i & 1, b = 8 * s;
+        int rc = finish(s);                       // the pair that used this slot two submissions ago
+        if (rc != RSDSFM_OK && first_err == RSDSFM_OK) first_err = rc;
+        const size_t mm = (size_t)p.m;
+        StepArgs a{p.flow, p.inliers3, p.alpha, p.alpha_k, nullptr, p.image, p.m, const_acceleration, gs_mode, rows, cols,
+                   layout, K4, gamma, p.z_out, p.depth_map, p.rectified};
+        rc = [&]() -> int {
+            if (host) {
+                // upload: the slot's staging buffers were last read by the compute of the pair finished above
+                const void *src[5] = {p.flow, p.inliers3, p.alpha, p.alpha_k, p.image};
+                const size_t sz[5] = {sizeof(double) * 2 * mm, sizeof(double) * 3 * mm, sizeof(double) * mm, sizeof(double) * mm, tot * 3};
+                for (int j = 0; j < 5; ++j)
+                    RS_CUDA(ctx, cudaMemcpyAsync(ctx->stage[b + j].p, src[j], sz[j], cudaMemcpyHostToDevice, ctx->s_in));
+                RS_CUDA(ctx, cudaEventRecord(ctx->ev_in[s], ctx->s_in));
+                RS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[s], 0));
+                a.flow = (const double *)ctx->stage[b + 0].p; a.inliers3 = (const double *)ctx->stage[b + 1].p;
+                a.alpha = (const double *)ctx->stage[b + 2].p; a.alpha_k = (const double *)ctx->stage[b + 3].p;
+                a.image = (const uint8_t *)ctx->stage[b + 4].p;
+                a.z = (double *)ctx->stage[b + 5].p; a.depth_map = (double *)ctx->stage[b + 6].p;
+                a.rectified = (uint8_t *)ctx->stage[b + 7].p;
+            }
+            ctx->io_slot = s;
+            RS_TRY(queue_step(ctx, a, p.v, p.w, p.k));
+            RS_CUDA(ctx, cudaEventRecord(ctx->ev_cdone[s], ctx->stream));
+            RS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_cdone[s], 0));
+            if (host) {
+                RS_CUDA(ctx, cudaMemcpyAsync(p.z_out, a.z, sizeof(double) * mm, cudaMemcpyDeviceToHost, ctx->s_out));
+                RS_CUDA(ctx, cudaMemcpyAsync(p.depth_map, a.depth_map, sizeof(double) * tot, cudaMemcpyDeviceToHost, ctx->s_out));
+                RS_CUDA(ctx, cudaMemcpyAsync(p.rectified, a.rectified, tot * 3, cudaMemcpyDeviceToHost, ctx->s_out));
+            }
+            RS_CUDA(ctx, cudaEventRecord(ctx->ev_out[s], ctx->s_out));
+            return RSDSFM_OK;
+        }();
+        if (rc != RSDSFM_OK) {
+            drain(ctx);
+            p.status = rc;
+            if (first_err == RSDSFM_OK) first_err = rc;
+            continue;
+        }
+        submitted[s] = i;
+    }
+    // finish in submission order (older pair first)
+    int order[2] = {0, 1};
+    if (submitted[0] >= 0 && submitted[1] >= 0 && submitted[1] < submitted[0]) { order[0] = 1; order[1] = 0; }
+    for (int q = 0; q < 2; ++q) {
+        int rc = finish(order[q]);
+        if (rc != RSDSFM_OK && first_err == RSDSFM_OK) first_err = rc;
+    }
+    drain(ctx);
+    ctx->io_slot = 0;
+    return first_err;
+}
+
+int rsdsfm_pipeline_pair(rsdsfm_ctx *ctx, int mem, const rsdsfm_pipeline_params *params, rsdsfm_pipeline_io *io)
+{
+    RS_ENTER(ctx);
+    if (!pipeline_args_ok(params, io)) return fail(ctx, RSDSFM_ERR_ARG, "rsdsfm_pipeline_pair: bad argument");
+    const size_t tot = (size_t)params->rows * params->cols;
+    ctx->io_slot = 0;
+    const void *d_fi = nullptr, *d_img = nullptr;
+    void *d_dm = nullptr, *d_out = nullptr;
+    RS_TRY(stage_in(ctx, mem, 0, io->flow_img, sizeof(double) * 2 * tot, &d_fi));
+    RS_TRY(stage_in(ctx, mem, 4, io->image, tot * 3, &d_img));
+    RS_TRY(stage_out_reserve(ctx, mem, 6, io->depth_map, sizeof(double) * tot, &d_dm));
+    RS_TRY(stage_out_reserve(ctx, mem, 7, io->rectified, tot * 3, &d_out));
+    io->status = pipeline_device(ctx, *params, (const double *)d_fi, (const uint8_t *)d_img, io, (double *)d_dm, (uint8_t *)d_out);
+    if (io->status != RSDSFM_OK) { cudaStreamSynchronize(ctx->stream); return io->status; }
+    RS_TRY(stage_out(ctx, mem, io->depth_map, d_dm, sizeof(double) * tot));
+    RS_TRY(stage_out(ctx, mem, io->rectified, d_out, tot * 3));
+    if (mem == RSDSFM_HOST) RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RSDSFM_OK;
+}
+
+int rsdsfm_pipeline_sequence(rsdsfm_ctx *ctx, int mem, const rsdsfm_pipeline_params *params, int n_pairs,
+                             rsdsfm_pipeline_io *pairs)
+{
+    RS_ENTER(ctx);
+    if (!params || n_pairs < 0 || (n_pairs > 0 && !pairs)) return fail(ctx, RSDSFM_ERR_ARG, "rsdsfm_pipeline_sequence: bad argument");
+    int first_err = RSDSFM_OK;
+    if (mem != RSDSFM_HOST) {                    // nothing to overlap: the stages synchronise for their counts anyway
+        for (int i = 0; i < n_pairs; ++i) {
+            int rc = rsdsfm_pipeline_pair(ctx, mem, params, &pairs[i]);
+            pairs[i].status = rc;
+            if (rc != RSDSFM_OK && first_err == RSDSFM_OK) first_err = rc;
+        }
+        return first_err;
+    }
+    RS_TRY(ensure_io(ctx));
+    const size_t tot = (size_t)params->rows * params->cols;
+    drain(ctx);
+    for (int s = 0; s < 2; ++s) {
+        RS_TRY(ensure(ctx, ctx->stage[8 * s + 0], sizeof(double) * 2 * tot));
+        RS_TRY(ensure(ctx, ctx->stage[8 * s + 4], tot * 3));
+        RS_TRY(ensure(ctx, ctx->stage[8 * s + 6], sizeof(double) * tot));
+        RS_TRY(ensure(ctx, ctx->stage[8 * s + 7], tot * 3));
+    }
+    // valid pairs, in order; position q in this list occupies I/O slot q&1
+    std::vector<int> idx;
+    for (int i = 0; i < n_pairs; ++i) {
+        if (pipeline_args_ok(params, &pairs[i])) { idx.push_back(i); continue; }
+        pairs[i].status = fail(ctx, RSDSFM_ERR_ARG, "rsdsfm_pipeline_sequence: bad pair argument");
+        if (first_err == RSDSFM_OK) first_err = RSDSFM_ERR_ARG;
+    }
+    auto upload = [&](size_t q) -> int {         // flow field and frame of list entry q -> its slot, on the upload stream
+        const int s = (int)(q & 1), b = 8 * s;
+        const rsdsfm_pipeline_io &p = pairs[idx[q]];
+        RS_CUDA(ctx, cudaMemcpyAsync(ctx->stage[b + 0].p, p.flow_img, sizeof(double) * 2 * tot, cudaMemcpyHostToDevice, ctx->s_in));
+        RS_CUDA(ctx, cudaMemcpyAsync(ctx->stage[b + 4].p, p.image, tot * 3, cudaMemcpyHostToDevice, ctx->s_in));
+        RS_CUDA(ctx, cudaEventRecord(ctx->ev_in[s], ctx->s_in));
+        return RSDSFM_OK;
+    };
+    bool out_pending[2] = {false, false};
+    if (!idx.empty()) RS_TRY(upload(0));
+    for (size_t q = 0; q < idx.size(); ++q) {
+        rsdsfm_pipeline_io &p = pairs[idx[q]];
+        const int s = (int)(q & 1), b = 8 * s;
+        // the other slot's previous occupant (entry q-1) has finished computing -- every pair ends
+        // synchronised -- so the next entry's inputs can go up while this one computes
+        if (q + 1 < idx.size()) RS_TRY(upload(q + 1));
+        RS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[s], 0));
+        if (out_pending[s]) RS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[s], 0));   // entry q-2's download
+        ctx->io_slot = s;
+        const int rc = pipeline_device(ctx, *params, (const double *)ctx->stage[b + 0].p, (const uint8_t *)ctx->stage[b + 4].p, &p,
+                                       (double *)ctx->stage[b + 6].p, (uint8_t *)ctx->stage[b + 7].p);
+        p.status = rc;
+        if (rc != RSDSFM_OK) {
+            cudaStreamSynchronize(ctx->stream);
+            if (first_err == RSDSFM_OK) first_err = rc;
+            continue;
+        }
+        // compute of this entry has completed: download on s_out while the next entry computes
+        RS_CUDA(ctx, cudaMemcpyAsync(p.depth_map, ctx->stage[b + 6].p, sizeof(double) * tot, cudaMemcpyDeviceToHost, ctx->s_out));
+        RS_CUDA(ctx, cudaMemcpyAsync(p.rectified, ctx->stage[b + 7].p, tot * 3, cudaMemcpyDeviceToHost, ctx->s_out));
+        RS_CUDA(ctx, cudaEventRecord(ctx->ev_out[s], ctx->s_out));
+        out_pending[s] = true;
+    }
+    drain(ctx);
+    ctx->io_slot = 0;
+    return first_err;
+}
+
+}  // extern "C"

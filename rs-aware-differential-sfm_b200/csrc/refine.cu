@@ -47,6 +47,8 @@ struct ExcEntry {            // a pixel whose LM diagonal is (possibly) clamped,
     double ees, se2;         // s_e^2 e^Te, s_e^2     (the whole pixel is handled by the controller CTA)
     double r0, r1, e0, e1;   // residual and depth column
     double F0[kMaxNF], F1[kMaxNF];   // the two Jacobian rows of the free motion parameters
+    double key;              // residual-block index: the controller sums the list in ascending key order, so
+                             // the result does not depend on the order the atomics handed out the slots
 };
 
 // Broadcast block: written by the controller CTA, read by every CTA at the start of a phase.
@@ -331,8 +333,9 @@ __device__ __forceinline__ void px_eval(const Loaded &L, const Motion &m, double
 // thread: the pixel is listed and the controller CTA adds F^TF, F^Tr (radius independent) and
 // subtracts q (F^Te)(e^TF), q (F^Te)(e^Tr) (radius dependent) itself.
 template <int NF>
-__device__ __noinline__ void eval_slow(const Loaded &L, double d, const Motion &mot, double c2, bool first, const Motion &base,
-                                       unsigned int *n_exc, unsigned int *overflow, ExcEntry *exc, unsigned int exc_cap)
+__device__ __noinline__ void eval_slow(const Loaded &L, double d, int index, const Motion &mot, double c2, bool first,
+                                       const Motion &base, unsigned int *n_exc, unsigned int *overflow, ExcEntry *exc,
+                                       unsigned int exc_cap)
 {
     PxEval E;
     px_eval(L, mot, c2, d, E);
@@ -345,7 +348,7 @@ __device__ __noinline__ void eval_slow(const Loaded &L, double d, const Motion &
     if (slot < exc_cap) {
         ExcEntry X;
         X.ees = E.ee * se * se; X.se2 = se * se;
-        X.r0 = E.r0; X.r1 = E.r1; X.e0 = E.e0; X.e1 = E.e1;
+        X.r0 = E.r0; X.r1 = E.r1; X.e0 = E.e0; X.e1 = E.e1; X.key = (double)index;
 #pragma unroll
         for (int j = 0; j < kMaxNF; ++j) { X.F0[j] = (j < NF) ? F0[j] : 0.0; X.F1[j] = (j < NF) ? F1[j] : 0.0; }
         exc[slot] = X;
@@ -358,7 +361,8 @@ __device__ __noinline__ void eval_slow(const Loaded &L, double d, const Motion &
 // (mot, d[p]).  Branch-free on the common path; the lane pair (l, l^1) shares the rank-1 updates:
 // the even lane applies the n-direction update of both lanes' pixels, the odd lane the e-direction.
 template <int NF>
-__device__ __forceinline__ void eval_pair(const Loaded (&L)[2], const double (&dv)[2], const bool (&valid)[2], const Motion &mot,
+__device__ __forceinline__ void eval_pair(const Loaded (&L)[2], const double (&dv)[2], const bool (&valid)[2],
+                                          const int (&idx)[2], const Motion &mot,
                                           double c2, bool first, const PhaseParams &P, double (&acc)[TAcc<NF>::NV],
                                           unsigned int *n_exc, unsigned int *overflow, ExcEntry *exc, unsigned int exc_cap)
 {
@@ -429,7 +433,7 @@ __device__ __forceinline__ void eval_pair(const Loaded (&L)[2], const double (&d
         if (slow[0] || slow[1]) {
 #pragma unroll
             for (int p = 0; p < 2; ++p)
-                if (slow[p]) eval_slow<NF>(L[p], dv[p], mot, c2, first, P.base, n_exc, overflow, exc, exc_cap);
+                if (slow[p]) eval_slow<NF>(L[p], dv[p], idx[p], mot, c2, first, P.base, n_exc, overflow, exc, exc_cap);
         }
     }
 }
@@ -662,6 +666,29 @@ __device__ __forceinline__ void issue_tile(const RefineData &D, const double *dx
     bulk_g2s(st->d, dx + (size_t)tile * kTile, (unsigned)(kTile * sizeof(double)), bar);
 }
 
+// Deterministic summation order for the listed pixels: bitonic sort (shared memory, whole CTA) of
+// keys[k] = (residual-block index << 32) | list slot.  false: the list does not fit (more than `cap`
+// listed pixels) and is summed in slot order -- correct, but then not bit-reproducible run to run.
+__device__ __forceinline__ bool sort_exceptions(const ExcEntry *list, int ne, unsigned long long *keys, int cap, int tid)
+{
+    int npad = 1;
+    while (npad < ne) npad <<= 1;
+    if (npad > cap) return false;
+    for (int k = tid; k < npad; k += kThreads)
+        keys[k] = (k < ne) ? ((unsigned long long)(unsigned int)(int)__ldcg(&list[k].key) << 32) | (unsigned int)k : ~0ull;
+    __syncthreads();
+    for (int size = 2; size <= npad; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < (npad >> 1); i += kThreads) {
+                const int lo = 2 * stride * (i / stride) + (i % stride), hi = lo + stride;
+                const unsigned long long a = keys[lo], b = keys[hi];
+                if ((a > b) == ((lo & size) == 0)) { keys[lo] = b; keys[hi] = a; }
+            }
+            __syncthreads();
+        }
+    return true;
+}
+
 template <int NF>
 __global__ void __launch_bounds__(kThreads, 1)
 k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *partials, ExcEntry *exc, unsigned int exc_cap,
@@ -758,11 +785,11 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
             }
             if (run_init) {
                 const double dv[2] = {L[0].d, L[1].d};
-                eval_pair<NF>(L, dv, valid, P.mot, c2, P.first != 0, P, acc, n_exc, &sh->exc_overflow, elist_p, exc_cap);
+                eval_pair<NF>(L, dv, valid, idx, P.mot, c2, P.first != 0, P, acc, n_exc, &sh->exc_overflow, elist_p, exc_cap);
             } else {
                 double dc[2];
                 step_pair<NF>(L, valid, idx, P, c2, rfac, inv_radius, acc, dcand, dc);
-                eval_pair<NF>(L, dc, valid, P.cand, c2c, false, P, acc, n_exc, &sh->exc_overflow, elist_p, exc_cap);
+                eval_pair<NF>(L, dc, valid, idx, P.cand, c2c, false, P, acc, n_exc, &sh->exc_overflow, elist_p, exc_cap);
             }
         }
         consumed += (unsigned)n_my;
@@ -863,6 +890,11 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
                 sh->n_exc[cur ^ 1] = 0u;                       // the other list is rebuilt by the next pass
             }
             __syncthreads();
+            // the pixel ring is idle during the controller section: its shared memory holds the sort keys
+            unsigned long long *xkeys = reinterpret_cast<unsigned long long *>(smem_raw);
+            bool xsorted = false;
+            if constexpr (NF > 0) if (s_flag[2] > 0)
+                xsorted = sort_exceptions(exc + (size_t)s_flag[4] * exc_cap, s_flag[2], xkeys, 16384, tid);
             if (s_flag[3]) {
                 // listed pixels: their radius-independent part F^TF, F^Tr joins G1, h1 of the new point
                 if constexpr (NF > 0) if (s_flag[2] > 0) {
@@ -871,9 +903,10 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
 #pragma unroll
                     for (int j = 0; j < kExcVals; ++j) a[j] = 0.0;
                     for (int k = tid; k < s_flag[2]; k += kThreads) {
+                        const int slot = xsorted ? (int)(unsigned int)(xkeys[k] & 0xffffffffull) : k;
                         ExcEntry X;
                         for (int w = 0; w < (int)(sizeof(ExcEntry) / sizeof(double)); ++w)
-                            reinterpret_cast<double *>(&X)[w] = __ldcg(reinterpret_cast<const double *>(cur_exc + k) + w);
+                            reinterpret_cast<double *>(&X)[w] = __ldcg(reinterpret_cast<const double *>(cur_exc + slot) + w);
                         int t = 0;
 #pragma unroll
                         for (int j = 0; j < NF; ++j) {
@@ -903,9 +936,10 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
 #pragma unroll
                     for (int j = 0; j < kExcVals; ++j) a[j] = 0.0;
                     for (int k = tid; k < ne; k += kThreads) {
+                        const int slot = xsorted ? (int)(unsigned int)(xkeys[k] & 0xffffffffull) : k;
                         ExcEntry X;
                         for (int w = 0; w < (int)(sizeof(ExcEntry) / sizeof(double)); ++w)
-                            reinterpret_cast<double *>(&X)[w] = __ldcg(reinterpret_cast<const double *>(cur_exc + k) + w);
+                            reinterpret_cast<double *>(&X)[w] = __ldcg(reinterpret_cast<const double *>(cur_exc + slot) + w);
                         const double q = X.se2 / (X.ees + fmin(fmax(X.ees, lo), hi) / R);
                         const double er = fma(X.e0, X.r0, X.e1 * X.r1);
                         double fe[NF > 0 ? NF : 1];
@@ -1004,9 +1038,9 @@ static int launch_persistent(rsdsfm_ctx *ctx, RefineData D, double *d0, double *
     const size_t smem = sizeof(Stage) * (size_t)kStages;
     RS_CUDA(ctx, cudaFuncSetAttribute(k_lm_persistent<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void *args[] = {&D, &d0, &d1, &sh, &partials, &exc, &exc_cap, &z_in, &z_stride, &out, &invert_out};
-    if (ctx->profile) cudaEventRecord(ctx->pe0, ctx->stream);
+    if (ctx->profile) cudaEventRecord(ctx->pe0[ctx->io_slot], ctx->stream);
     RS_CUDA(ctx, cudaLaunchCooperativeKernel((void *)k_lm_persistent<NF>, dim3(grid), dim3(kThreads), args, smem, ctx->stream));
-    if (ctx->profile) cudaEventRecord(ctx->pe1, ctx->stream);
+    if (ctx->profile) cudaEventRecord(ctx->pe1[ctx->io_slot], ctx->stream);
     ctx->launches++;
     return RSDSFM_OK;
 }
@@ -1033,10 +1067,10 @@ static int lm_solve_async(rsdsfm_ctx *ctx, const RefineData &D, double *d0, doub
     RS_TRY(ensure(ctx, ctx->partials, sizeof(double) * (size_t)grid * nv));
     if (ctx->exc_cap < 4096) ctx->exc_cap = 4096;
     RS_TRY(ensure(ctx, ctx->exc, sizeof(ExcEntry) * 2 * (size_t)ctx->exc_cap));   // current + speculative list
-    RS_TRY(ensure_pinned(ctx, sizeof(LmShared) * 2 + 1024));
+    static_assert(sizeof(LmShared) <= 8192 - 256, "pinned slot layout (common.cuh)");
 
-    // initial control block, staged through pinned memory (second half; the first half receives results)
-    LmShared *h = (LmShared *)((char *)ctx->pinned + sizeof(LmShared));
+    // initial control block, staged through the I/O slot's pinned area
+    LmShared *h = (LmShared *)pinned_lm_init(ctx);
     memset(h, 0, sizeof(LmShared));
     double f0[kMaxNF] = {0, 0, 0, 0, 0, 0, 0};
     if (nf >= 6) { for (int j = 0; j < 3; ++j) { f0[j] = mot0.v[j]; f0[3 + j] = mot0.w[j]; } }
@@ -1066,19 +1100,25 @@ static int lm_solve_async(rsdsfm_ctx *ctx, const RefineData &D, double *d0, doub
     return launch_persistent<7>(ctx, D, d0, d1, sh, partials, exc, cap, z_in, z_stride, out, invert_out, grid);
 }
 
-// Reads the control block back (synchronises the stream).  RSDSFM_ERR_INTERNAL when the in-kernel
-// watchdog tripped; *overflow: the exception list was too small (ctx->exc_cap was raised: retry).
-int lm_collect(rsdsfm_ctx *ctx, int nf, int m, Motion *mot, rsdsfm_lm_summary *summary, bool *overflow)
+// Queues the read-back of the control block into the current I/O slot's pinned area.
+int lm_collect_enqueue(rsdsfm_ctx *ctx)
 {
     LmShared *sh = (LmShared *)ctx->lm_shared.p;
-    LmShared *h = (LmShared *)ctx->pinned;
-    RS_CUDA(ctx, cudaMemcpyAsync(h, sh, sizeof(LmShared), cudaMemcpyDeviceToHost, ctx->stream));
-    RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RS_CUDA(ctx, cudaMemcpyAsync(pinned_lm_result(ctx), sh, sizeof(LmShared), cudaMemcpyDeviceToHost, ctx->stream));
+    return RSDSFM_OK;
+}
+
+// Parses the control block of the current I/O slot once its read-back has completed.
+// RSDSFM_ERR_INTERNAL when the in-kernel watchdog tripped; *overflow: the exception list was too
+// small (ctx->exc_cap was raised: run the solve again).
+int lm_collect_finish(rsdsfm_ctx *ctx, int nf, int m, Motion *mot, rsdsfm_lm_summary *summary, bool *overflow)
+{
+    LmShared *h = (LmShared *)pinned_lm_result(ctx);
     if (h->error) return fail(ctx, RSDSFM_ERR_INTERNAL, "LM kernel: grid barrier watchdog tripped");
     *overflow = h->exc_overflow != 0;
-    if (*overflow) { ctx->exc_cap = m + 1024; return RSDSFM_OK; }
+    if (*overflow) { if (ctx->exc_cap < m + 1024) ctx->exc_cap = m + 1024; return RSDSFM_OK; }
     float kms = 0.f;
-    if (ctx->profile) cudaEventElapsedTime(&kms, ctx->pe0, ctx->pe1);
+    if (ctx->profile) cudaEventElapsedTime(&kms, ctx->pe0[ctx->io_slot], ctx->pe1[ctx->io_slot]);
     if (summary) {
         h->ctl.fill_summary(summary);
         summary->device_ms = (double)(h->t_phase[0] + h->t_phase[2]) * 1e-6;
@@ -1098,6 +1138,14 @@ int lm_collect(rsdsfm_ctx *ctx, int nf, int m, Motion *mot, rsdsfm_lm_summary *s
     return RSDSFM_OK;
 }
 
+// Reads the control block back (synchronises the stream).
+int lm_collect(rsdsfm_ctx *ctx, int nf, int m, Motion *mot, rsdsfm_lm_summary *summary, bool *overflow)
+{
+    RS_TRY(lm_collect_enqueue(ctx));
+    RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return lm_collect_finish(ctx, nf, m, mot, summary, overflow);
+}
+
 // Device address of the refined motion (v[3], w[3], k) inside the control block, for the
 // rectification stage that follows on the same stream.
 const double *lm_motion_device(rsdsfm_ctx *ctx)
@@ -1113,6 +1161,16 @@ static int ensure_lm_buffers(rsdsfm_ctx *ctx, size_t mm)
     RS_TRY(ensure(ctx, ctx->dB, sizeof(double) * kTile * tiles));
     RS_TRY(ensure(ctx, ctx->lm_shared, sizeof(LmShared)));
     return RSDSFM_OK;
+}
+
+// Pre-sizes every solver buffer for up to m residual blocks so that a pipelined sequence does not
+// reallocate (and therefore synchronise) between pairs.
+int lm_reserve(rsdsfm_ctx *ctx, int m)
+{
+    RS_TRY(ensure_lm_buffers(ctx, (size_t)(m > 0 ? m : 1)));
+    RS_TRY(ensure(ctx, ctx->partials, sizeof(double) * (size_t)ctx->num_sms * Acc<7>::NV));
+    if (ctx->exc_cap < 4096) ctx->exc_cap = 4096;
+    return ensure(ctx, ctx->exc, sizeof(ExcEntry) * 2 * (size_t)ctx->exc_cap);
 }
 
 // a9 on device pointers: queues gather + solve on the stream, no synchronisation.

@@ -256,3 +256,156 @@ def test_cpp_host_shim_single_run(capi):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "rectified image" in r.stdout
+
+
+# ---------------------------------------------------------------------------- sequence / whole-pipeline drivers
+def _seq_pairs(oracle, synth, n_pairs, const_acc):
+    cases = []
+    for p in range(n_pairs):
+        rows, cols = (120, 160) if p % 2 == 0 else (120, 160)
+        c = helpers.make_case(oracle, synth, rows, cols, helpers.small_K(8), k=0.5 if const_acc else 0.0, const_acc=const_acc,
+                              H=8, seed=20 + p, sample_seed=40 + p, outliers=0.05 + 0.03 * p)
+        cases.append(c)
+    return cases
+
+
+@pytest.mark.parametrize("mem", ["host", "device"])
+@pytest.mark.parametrize("const_acc", [False, True])
+def test_refine_rectify_sequence_equals_single_calls(ctx, oracle, synth, mem, const_acc):
+    """The software-pipelined sequence entry point must return exactly what n single calls return
+    (same kernels, same order per pair; different m per pair, 5 pairs so both I/O slots are reused)."""
+    import torch
+    cases = _seq_pairs(oracle, synth, 5, const_acc)
+    dev = torch.device("cuda", 0)
+    to = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)) if mem == "device" else (lambda a: np.ascontiguousarray(a))
+    pairs, single = [], []
+    for c in cases:
+        R = c["ransac"]
+        d = dict(flow=to(c["flow"][:2 * c["m"]]), inliers3=to(c["inliers3"]), alpha=to(c["alpha_in"]), alpha_k=to(c["alpha_k_in"]),
+                 image=to(c["P"]["image"]), m=c["m"], v=R["v"], w=R["w"], k=R["k"])
+        pairs.append(d)
+        single.append(ctx.refine_rectify(d["flow"], d["inliers3"], d["alpha"], d["alpha_k"], d["m"], d["v"], d["w"], d["k"], const_acc,
+                                         False, d["image"], c["K4"], c["gamma"]))
+    seq = ctx.refine_rectify_sequence(pairs, const_acc, False, cases[0]["K4"], cases[0]["gamma"])
+    assert len(seq) == len(single)
+    host = (lambda a: a.cpu().numpy()) if mem == "device" else (lambda a: a)
+    for s, r in zip(seq, single):
+        assert s["status"] == 0
+        assert np.array_equal(s["v"], r["v"]) and np.array_equal(s["w"], r["w"]) and s["k"] == r["k"]
+        assert s["summary"]["iterations"] == r["summary"]["iterations"]
+        assert s["summary"]["final_cost"] == r["summary"]["final_cost"]
+        for key in ("z", "depth_map", "rectified"):
+            assert np.array_equal(host(s[key]), host(r[key])), key
+
+
+def test_refine_rectify_sequence_bad_pair_is_reported(ctx, oracle, synth):
+    cases = _seq_pairs(oracle, synth, 3, False)
+    pairs = []
+    for c in cases:
+        R = c["ransac"]
+        pairs.append(dict(flow=c["flow"][:2 * c["m"]], inliers3=c["inliers3"], alpha=c["alpha_in"], alpha_k=c["alpha_k_in"],
+                          image=c["P"]["image"], m=c["m"], v=R["v"], w=R["w"], k=R["k"]))
+    pairs[1]["m"] = 0
+    capi = __import__("importlib").import_module("rs-aware-differential-sfm_b200.capi")
+    with pytest.raises(capi.RsdsfmError):
+        ctx.refine_rectify_sequence(pairs, False, False, cases[0]["K4"], cases[0]["gamma"])
+    # the context stays usable and the valid pairs still run
+    ok = ctx.refine_rectify_sequence([pairs[0], pairs[2]], False, False, cases[0]["K4"], cases[0]["gamma"])
+    assert [r["status"] for r in ok] == [0, 0]
+
+
+@pytest.mark.parametrize("mem", ["host", "device"])
+@pytest.mark.parametrize("which,repair", [("cv", False), ("ca", False), ("ca", True)])
+def test_pipeline_pair_equals_stagewise_calls(ctx, oracle, case_cv, case_ca, which, repair, mem):
+    """rsdsfm_pipeline_pair (flatten .. crack fill in one call) against the oracle's RANSAC winner and
+    the per-stage entry points on the same sample list."""
+    import torch
+    c = case_cv if which == "cv" else case_ca
+    dev = torch.device("cuda", 0)
+    to = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)) if mem == "device" else (lambda a: np.ascontiguousarray(a))
+    host = (lambda a: a.cpu().numpy()) if mem == "device" else (lambda a: a)
+    got = ctx.pipeline_pair(to(c["P"]["flow_img"]), to(c["P"]["image"]), c["K4"], c["gamma"], c["tol"], c["const_acc"],
+                            samples=c["samples"], repair_pairing=repair)
+    R = c["ransac"]
+    assert got["status"] == 0 and got["n"] == c["n"] and got["m"] == c["m"] and got["best_idx"] == R["best_idx"]
+    assert np.array_equal(got["ransac_v"], R["v"]) and np.array_equal(got["ransac_w"], R["w"]) and got["ransac_k"] == R["k"]
+    # stage-wise on the device: same kernels, so identical results
+    fi = torch.from_numpy(c["P"]["flow_img"]).to(dev)
+    n, coord, flow, cpx, fpx, pidx = ctx.flatten(fi, c["K4"], c["gamma"])
+    alpha, alpha_k = ctx.alpha(fpx[:2 * n], cpx[:2 * n], n, c["rows"], c["gamma"])
+    Rg = ctx.ransac(coord[:2 * n], flow[:2 * n], alpha, alpha_k, n, c["const_acc"], c["samples"], c["tol"])
+    inl, a_in, ak_in, ix, m = ctx.gather_inliers(coord[:2 * n], alpha, alpha_k, n, Rg["mask"], Rg["inv_depth"])
+    if repair:
+        ref_r = ctx.refine(flow[:2 * n].contiguous(), inl.contiguous(), a_in.contiguous(), ak_in.contiguous(), m, Rg["v"], Rg["w"], Rg["k"],
+                           c["const_acc"], flow_index=ix[:m].contiguous())
+        _motion_close(got["w"], ref_r[1], "w")
+        assert abs(got["k"] - ref_r[2]) <= 1e-9 * max(1.0, abs(ref_r[2]))
+    else:
+        ref = ctx.refine_rectify(flow[:2 * n].contiguous(), inl.contiguous(), a_in.contiguous(), ak_in.contiguous(), m, Rg["v"], Rg["w"],
+                                 Rg["k"], c["const_acc"], False, torch.from_numpy(c["P"]["image"]).to(dev), c["K4"], c["gamma"])
+        assert np.array_equal(got["v"], ref["v"]) and np.array_equal(got["w"], ref["w"]) and got["k"] == ref["k"]
+        assert np.array_equal(host(got["depth_map"]), ref["depth_map"].cpu().numpy())
+        assert np.array_equal(host(got["rectified"]), ref["rectified"].cpu().numpy())
+
+
+def test_pipeline_no_refinement_and_gs_mode(ctx, oracle, case_cv):
+    """use_refinement = 0 rectifies with the RANSAC winner (main.cc:455); gs_mode sets alpha = 1."""
+    c = case_cv
+    R = c["ransac"]
+    got = ctx.pipeline_pair(c["P"]["flow_img"], c["P"]["image"], c["K4"], c["gamma"], c["tol"], False, samples=c["samples"],
+                            use_refinement=False)
+    assert got["m"] == c["m"]
+    inl = c["inliers3"].copy()
+    _, v_fix, dm, _, _ = oracle.depth_glue(inl, c["m"], R["v"].copy(), c["K4"], c["rows"], c["cols"])
+    assert np.array_equal(got["depth_map"], dm)
+    assert np.array_equal(got["v"], v_fix) and np.array_equal(got["w"], R["w"])
+    # global-shutter mode: alpha = 1 everywhere -> same consensus as the oracle run with alpha = 1
+    n = c["n"]
+    ones = np.ones(n)
+    Rgs = oracle.ransac(c["coord"], c["flow"], ones, c["alpha_k"], n, False, c["tol"], samples=c["samples"])
+    got = ctx.pipeline_pair(c["P"]["flow_img"], c["P"]["image"], c["K4"], c["gamma"], c["tol"], False, samples=c["samples"],
+                            gs_mode=True, use_refinement=False)
+    assert got["best_idx"] == Rgs["best_idx"] and got["m"] == int(Rgs["mask"].sum())
+
+
+def test_pipeline_sequence_and_reference_draws(ctx, oracle, synth):
+    """Sequence driver == pair driver per entry; `draws` are mapped to samples like minimal.cc:226-244."""
+    cases = _seq_pairs(oracle, synth, 3, False)
+    rng = np.random.RandomState(7)
+    pairs = []
+    for c in cases:
+        draws = rng.randint(0, 2 ** 31 - 1, size=(c["samples"].shape[0], 9)).astype(np.uint32)
+        pairs.append(dict(flow_img=c["P"]["flow_img"], image=c["P"]["image"], draws=draws))
+    seq = ctx.pipeline_sequence(pairs, cases[0]["K4"], cases[0]["gamma"], cases[0]["tol"], False)
+    for c, p, s in zip(cases, pairs, seq):
+        # the reference's draw: persistent index vector, swap with the last live entry
+        idx = np.arange(c["n"])
+        samples = []
+        for t in range(p["draws"].shape[0]):
+            nt = c["n"]
+            for j in range(9):
+                r = int(p["draws"][t, j]) % nt
+                idx[nt - 1], idx[r] = idx[r], idx[nt - 1]
+                samples.append(idx[nt - 1])
+                nt -= 1
+        samples = np.array(samples, dtype=np.int32).reshape(-1, 9)
+        one = ctx.pipeline_pair(c["P"]["flow_img"], c["P"]["image"], c["K4"], c["gamma"], c["tol"], False, samples=samples)
+        assert s["status"] == 0 and s["n"] == one["n"] and s["m"] == one["m"] and s["best_idx"] == one["best_idx"]
+        assert np.array_equal(s["v"], one["v"]) and np.array_equal(s["w"], one["w"])
+        assert np.array_equal(s["depth_map"], one["depth_map"]) and np.array_equal(s["rectified"], one["rectified"])
+
+
+@pytest.mark.parametrize("const_acc", [False, True])
+def test_refine_is_bit_reproducible(ctx, oracle, synth, const_acc):
+    """Fixed-order reductions: repeated solves of the same problem agree to the last bit, including
+    problems with listed (clamped-diagonal) pixels whose list slots are handed out by atomics."""
+    for p in (3, 0):
+        c = helpers.make_case(oracle, synth, 120, 160, helpers.small_K(8), k=0.5 if const_acc else 0.0, const_acc=const_acc,
+                              H=8, seed=20 + p, sample_seed=40 + p, outliers=0.05 + 0.03 * p)
+        R = c["ransac"]
+        runs = [ctx.refine(c["flow"][:2 * c["m"]], c["inliers3"], c["alpha_in"], c["alpha_k_in"], c["m"], R["v"], R["w"], R["k"], const_acc)
+                for _ in range(6)]
+        for r in runs[1:]:
+            assert np.array_equal(r[0], runs[0][0]) and np.array_equal(r[1], runs[0][1]) and r[2] == runs[0][2]
+            assert np.array_equal(r[3], runs[0][3])
+            assert r[4]["final_cost"] == runs[0][4]["final_cost"] and r[4]["iterations"] == runs[0][4]["iterations"]
