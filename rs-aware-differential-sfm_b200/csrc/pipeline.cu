@@ -44,8 +44,7 @@ static int queue_step(rsdsfm_ctx *ctx, const StepArgs &a, const double *v, const
     RS_TRY(backproject_device(ctx, a.image, a.depth_map, a.layout, a.rows, a.cols, a.K4, dR, dt, a.gs_mode,
                               (uint8_t *)ctx->tmp_img.p, nullptr));
     RS_TRY(fill_cracks_device(ctx, (const uint8_t *)ctx->tmp_img.p, a.rows, a.cols, 1, a.rectified));
-    RS_CUDA(ctx, cudaMemcpyAsync(pinned_stats(ctx), stats, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    return lm_collect_enqueue(ctx);
+    return lm_collect_enqueue(ctx, stats);
 }
 
 // Parses the current I/O slot's read-backs (which must have completed).
@@ -313,9 +312,12 @@ int rsdsfm_refine_rectify_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm
         }
 
     // Pair `j` occupies I/O slot j&1.  In flight at any time: upload of pair i (s_in), compute of
-    // pairs <= i (stream, in order), download of pairs < i (s_out).  A pair is finished (results
-    // parsed on the host) one iteration after it was submitted.
+    // pairs <= i (stream, in order), download of pairs < i (s_out).  The upload of pair i starts as
+    // soon as the compute of pair i-2 has released the slot's staging buffers (stream-side wait, the
+    // host does not block for it); pair i-2 is finished (results parsed on the host) before the
+    // compute of pair i is queued, because that compute overwrites the slot's read-back area.
     int submitted[2] = {-1, -1};                 // pair occupying each slot, not yet finished
+    bool retried = false;
     auto finish = [&](int slot) -> int {
         const int j = submitted[slot];
         if (j < 0) return RSDSFM_OK;
@@ -331,28 +333,39 @@ int rsdsfm_refine_rectify_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm
             drain(ctx);
             rc = step_sync(ctx, mem, slot, p.flow, p.inliers3, p.alpha, p.alpha_k, p.m, p.v, p.w, &p.k, const_acceleration,
                            gs_mode, p.image, rows, cols, K4, gamma, layout, p.z_out, p.depth_map, p.rectified, &p.summary);
+            retried = true;                       // the slot's staging buffers were reused
         }
         p.status = rc;
         return rc;
+    };
+    auto upload = [&](const rsdsfm_pair_io &p, int s) -> int {
+        const size_t mm = (size_t)p.m;
+        const void *src[5] = {p.flow, p.inliers3, p.alpha, p.alpha_k, p.image};
+        const size_t sz[5] = {sizeof(double) * 2 * mm, sizeof(double) * 3 * mm, sizeof(double) * mm, sizeof(double) * mm, tot * 3};
+        for (int j = 0; j < 5; ++j)
+            RS_CUDA(ctx, cudaMemcpyAsync(ctx->stage[8 * s + j].p, src[j], sz[j], cudaMemcpyHostToDevice, ctx->s_in));
+        RS_CUDA(ctx, cudaEventRecord(ctx->ev_in[s], ctx->s_in));
+        return RSDSFM_OK;
     };
 
     for (int i = 0; i < n_pairs; ++i) {
         rsdsfm_pair_io &p = pairs[i];
         if (p.status != RSDSFM_OK) continue;
         const int s = i & 1, b = 8 * s;
-        int rc = finish(s);                       // the pair that used this slot two submissions ago
-        if (rc != RSDSFM_OK && first_err == RSDSFM_OK) first_err = rc;
         const size_t mm = (size_t)p.m;
         StepArgs a{p.flow, p.inliers3, p.alpha, p.alpha_k, nullptr, p.image, p.m, const_acceleration, gs_mode, rows, cols,
                    layout, K4, gamma, p.z_out, p.depth_map, p.rectified};
-        rc = [&]() -> int {
+        int rc = [&]() -> int {
             if (host) {
-                // upload: the slot's staging buffers were last read by the compute of the pair finished above
-                const void *src[5] = {p.flow, p.inliers3, p.alpha, p.alpha_k, p.image};
-                const size_t sz[5] = {sizeof(double) * 2 * mm, sizeof(double) * 3 * mm, sizeof(double) * mm, sizeof(double) * mm, tot * 3};
-                for (int j = 0; j < 5; ++j)
-                    RS_CUDA(ctx, cudaMemcpyAsync(ctx->stage[b + j].p, src[j], sz[j], cudaMemcpyHostToDevice, ctx->s_in));
-                RS_CUDA(ctx, cudaEventRecord(ctx->ev_in[s], ctx->s_in));
+                // the slot's input staging was last read by the compute of its previous occupant
+                if (submitted[s] >= 0) RS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_cdone[s], 0));
+                RS_TRY(upload(p, s));
+            }
+            retried = false;
+            const int frc = finish(s);            // the previous occupant: blocks until its download is complete
+            if (frc != RSDSFM_OK && first_err == RSDSFM_OK) first_err = frc;
+            if (host) {
+                if (retried) RS_TRY(upload(p, s));
                 RS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[s], 0));
                 a.flow = (const double *)ctx->stage[b + 0].p; a.inliers3 = (const double *)ctx->stage[b + 1].p;
                 a.alpha = (const double *)ctx->stage[b + 2].p; a.alpha_k = (const double *)ctx->stage[b + 3].p;

@@ -362,7 +362,7 @@ __device__ __noinline__ void eval_slow(const Loaded &L, double d, int index, con
 // the even lane applies the n-direction update of both lanes' pixels, the odd lane the e-direction.
 template <int NF>
 __device__ __forceinline__ void eval_pair(const Loaded (&L)[2], const double (&dv)[2], const bool (&valid)[2],
-                                          const int (&idx)[2], const Motion &mot,
+                                          int base_i, const Motion &mot,
                                           double c2, bool first, const PhaseParams &P, double (&acc)[TAcc<NF>::NV],
                                           unsigned int *n_exc, unsigned int *overflow, ExcEntry *exc, unsigned int exc_cap)
 {
@@ -433,7 +433,8 @@ __device__ __forceinline__ void eval_pair(const Loaded (&L)[2], const double (&d
         if (slow[0] || slow[1]) {
 #pragma unroll
             for (int p = 0; p < 2; ++p)
-                if (slow[p]) eval_slow<NF>(L[p], dv[p], idx[p], mot, c2, first, P.base, n_exc, overflow, exc, exc_cap);
+                if (slow[p])      // residual-block index rebuilt here: nothing extra stays live on the common path
+                    eval_slow<NF>(L[p], dv[p], base_i + (int)threadIdx.x + p * kThreads, mot, c2, first, P.base, n_exc, overflow, exc, exc_cap);
         }
     }
 }
@@ -785,11 +786,11 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
             }
             if (run_init) {
                 const double dv[2] = {L[0].d, L[1].d};
-                eval_pair<NF>(L, dv, valid, idx, P.mot, c2, P.first != 0, P, acc, n_exc, &sh->exc_overflow, elist_p, exc_cap);
+                eval_pair<NF>(L, dv, valid, base_i, P.mot, c2, P.first != 0, P, acc, n_exc, &sh->exc_overflow, elist_p, exc_cap);
             } else {
                 double dc[2];
                 step_pair<NF>(L, valid, idx, P, c2, rfac, inv_radius, acc, dcand, dc);
-                eval_pair<NF>(L, dc, valid, idx, P.cand, c2c, false, P, acc, n_exc, &sh->exc_overflow, elist_p, exc_cap);
+                eval_pair<NF>(L, dc, valid, base_i, P.cand, c2c, false, P, acc, n_exc, &sh->exc_overflow, elist_p, exc_cap);
             }
         }
         consumed += (unsigned)n_my;
@@ -1045,13 +1046,34 @@ static int launch_persistent(rsdsfm_ctx *ctx, RefineData D, double *d0, double *
     return RSDSFM_OK;
 }
 
-__global__ void k_apply_input_flag(LmShared *sh)
-{   // "gather found a non-finite start depth" => the FAILURE Ceres reports before evaluating anything
-    if (sh->nonfinite_input) {
+// The initial control block travels as a kernel parameter and the final one is written straight
+// into pinned host memory by a kernel: neither transfer queues behind the large uploads /
+// downloads that a pipelined sequence keeps on the copy engines.
+static_assert(sizeof(LmShared) <= 3840 && sizeof(LmShared) % 4 == 0, "control block must fit the kernel parameter space");
+
+__global__ void __launch_bounds__(256) k_lm_begin(LmShared *sh, const __grid_constant__ LmShared init, int keep_input_flag)
+{
+    // nonfinite_input is the LAST field: with keep_input_flag the gather kernel's verdict survives
+    const int words = (int)((keep_input_flag ? offsetof(LmShared, nonfinite_input) : sizeof(LmShared)) / 4);
+    const unsigned int *src = reinterpret_cast<const unsigned int *>(&init);
+    unsigned int *dst = reinterpret_cast<unsigned int *>(sh);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    // "gather found a non-finite start depth" => the FAILURE Ceres reports before evaluating anything
+    if (threadIdx.x == 0 && keep_input_flag && sh->nonfinite_input) {
         sh->bc.next = LM_DONE;
         sh->ctl.termination = RSDSFM_FAILURE;
         sh->ctl.reason = RSDSFM_REASON_NONFINITE_INPUT;
     }
+}
+
+__global__ void __launch_bounds__(256) k_lm_readback(const LmShared *sh, const double *stats8, LmShared *host_block,
+                                                     double *host_stats8)
+{
+    const unsigned int *src = reinterpret_cast<const unsigned int *>(sh);
+    unsigned int *dst = reinterpret_cast<unsigned int *>(host_block);            // mapped pinned memory (UVA)
+    for (int i = threadIdx.x; i < (int)(sizeof(LmShared) / 4); i += blockDim.x) dst[i] = src[i];
+    if (stats8 && threadIdx.x < 8) host_stats8[threadIdx.x] = stats8[threadIdx.x];
 }
 
 // Queues one LM solve on the context's stream (no host synchronisation).  The control block
@@ -1069,8 +1091,9 @@ static int lm_solve_async(rsdsfm_ctx *ctx, const RefineData &D, double *d0, doub
     RS_TRY(ensure(ctx, ctx->exc, sizeof(ExcEntry) * 2 * (size_t)ctx->exc_cap));   // current + speculative list
     static_assert(sizeof(LmShared) <= 8192 - 256, "pinned slot layout (common.cuh)");
 
-    // initial control block, staged through the I/O slot's pinned area
-    LmShared *h = (LmShared *)pinned_lm_init(ctx);
+    // initial control block: built on the host, passed by value to k_lm_begin
+    LmShared init_block;
+    LmShared *h = &init_block;
     memset(h, 0, sizeof(LmShared));
     double f0[kMaxNF] = {0, 0, 0, 0, 0, 0, 0};
     if (nf >= 6) { for (int j = 0; j < 3; ++j) { f0[j] = mot0.v[j]; f0[3 + j] = mot0.w[j]; } }
@@ -1084,14 +1107,8 @@ static int lm_solve_async(rsdsfm_ctx *ctx, const RefineData &D, double *d0, doub
     if (!finite) {              // solver.cc: non-finite parameter blocks => FAILURE, nothing evaluated
         h->bc.next = LM_DONE; h->ctl.termination = RSDSFM_FAILURE; h->ctl.reason = RSDSFM_REASON_NONFINITE_INPUT;
     }
-    if (keep_input_flag) {
-        // nonfinite_input is the LAST field: upload everything before it, keep what the gather kernel raised
-        RS_CUDA(ctx, cudaMemcpyAsync(sh, h, offsetof(LmShared, nonfinite_input), cudaMemcpyHostToDevice, ctx->stream));
-        k_apply_input_flag<<<1, 1, 0, ctx->stream>>>(sh);
-        ctx->launches++;
-    } else {
-        RS_CUDA(ctx, cudaMemcpyAsync(sh, h, sizeof(LmShared), cudaMemcpyHostToDevice, ctx->stream));
-    }
+    k_lm_begin<<<1, 256, 0, ctx->stream>>>(sh, *h, keep_input_flag ? 1 : 0);
+    ctx->launches++;
     double *partials = (double *)ctx->partials.p;
     ExcEntry *exc = (ExcEntry *)ctx->exc.p;
     const unsigned int cap = (unsigned int)ctx->exc_cap;
@@ -1100,11 +1117,14 @@ static int lm_solve_async(rsdsfm_ctx *ctx, const RefineData &D, double *d0, doub
     return launch_persistent<7>(ctx, D, d0, d1, sh, partials, exc, cap, z_in, z_stride, out, invert_out, grid);
 }
 
-// Queues the read-back of the control block into the current I/O slot's pinned area.
-int lm_collect_enqueue(rsdsfm_ctx *ctx)
+// Queues the read-back of the control block (and, if given, of the 8 depth statistics) into the
+// current I/O slot's pinned area.
+int lm_collect_enqueue(rsdsfm_ctx *ctx, const double *stats_dev)
 {
-    LmShared *sh = (LmShared *)ctx->lm_shared.p;
-    RS_CUDA(ctx, cudaMemcpyAsync(pinned_lm_result(ctx), sh, sizeof(LmShared), cudaMemcpyDeviceToHost, ctx->stream));
+    k_lm_readback<<<1, 256, 0, ctx->stream>>>((const LmShared *)ctx->lm_shared.p, stats_dev, (LmShared *)pinned_lm_result(ctx),
+                                              pinned_stats(ctx));
+    ctx->launches++;
+    RS_CUDA(ctx, cudaGetLastError());
     return RSDSFM_OK;
 }
 
@@ -1141,7 +1161,7 @@ int lm_collect_finish(rsdsfm_ctx *ctx, int nf, int m, Motion *mot, rsdsfm_lm_sum
 // Reads the control block back (synchronises the stream).
 int lm_collect(rsdsfm_ctx *ctx, int nf, int m, Motion *mot, rsdsfm_lm_summary *summary, bool *overflow)
 {
-    RS_TRY(lm_collect_enqueue(ctx));
+    RS_TRY(lm_collect_enqueue(ctx, nullptr));
     RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return lm_collect_finish(ctx, nf, m, mot, summary, overflow);
 }

@@ -38,7 +38,7 @@ int refine_async(rsdsfm_ctx *, const double *flow, const double *inliers3, const
                  int m, const double *v, const double *w, double k, int const_acc, const int32_t *flow_index,
                  const rsdsfm_lm_options *, double *z_out);
 int lm_reserve(rsdsfm_ctx *, int m);                     // pre-sizes the solver's buffers for up to m residual blocks
-int lm_collect_enqueue(rsdsfm_ctx *);
+int lm_collect_enqueue(rsdsfm_ctx *, const double *stats_dev8);   // zero-copy read-back into the I/O slot's pinned area
 int lm_collect_finish(rsdsfm_ctx *, int nf, int m, Motion *mot, rsdsfm_lm_summary *, bool *overflow);
 int lm_collect(rsdsfm_ctx *, int nf, int m, Motion *mot, rsdsfm_lm_summary *, bool *overflow);            // [synchronises]
 const double *lm_motion_device(rsdsfm_ctx *);
