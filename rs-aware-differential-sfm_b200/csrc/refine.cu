@@ -433,8 +433,12 @@ __device__ __forceinline__ void eval_pair(const Loaded (&L)[2], const double (&d
         if (slow[0] || slow[1]) {
 #pragma unroll
             for (int p = 0; p < 2; ++p)
-                if (slow[p])      // residual-block index rebuilt here: nothing extra stays live on the common path
-                    eval_slow<NF>(L[p], dv[p], base_i + (int)threadIdx.x + p * kThreads, mot, c2, first, P.base, n_exc, overflow, exc, exc_cap);
+                if (slow[p]) {
+                    // the out-of-line call takes the pixel by address: hand it a copy made HERE, so that the
+                    // common path keeps L[] in registers instead of spilling it to the stack every iteration
+                    const Loaded Lc = L[p];
+                    eval_slow<NF>(Lc, dv[p], base_i + (int)threadIdx.x + p * kThreads, mot, c2, first, P.base, n_exc, overflow, exc, exc_cap);
+                }
         }
     }
 }
