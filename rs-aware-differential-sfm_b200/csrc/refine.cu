@@ -817,15 +817,23 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
             __threadfence();
             const unsigned long long t_ctl = (tid == 0) ? globaltimer() : 0ull;
             constexpr int nv = A::NV, ns = A::NS;
-            // final reduce: warp w sums rows w, w+8, ...; lanes cover the columns (coalesced); loads are
-            // issued in batches of 8 rows before they are combined, in a fixed order
-            {
-                double v[3] = {0.0, 0.0, 0.0};
-                for (int r0 = 0; r0 * kWarps + warp < G; r0 += 8) {
-                    double t[8][3];
+            // final reduce: warp w sums rows w, w+8, ...; lanes cover the columns (coalesced).  All loads of a
+            // warp (up to 19 rows x 3 column groups) and the controller state are issued before anything is
+            // combined -- one L2 round trip instead of one per batch; the sums run in a fixed order.
+            int ctl_w[(sizeof(LmController) / sizeof(int) + kThreads - 1) / kThreads];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int b = (r0 + u) * kWarps + warp;
+            for (int q = 0; q < (int)(sizeof(ctl_w) / sizeof(int)); ++q) {
+                const int w = tid + q * kThreads;
+                ctl_w[q] = (w < (int)(sizeof(LmController) / sizeof(int))) ? __ldcg(reinterpret_cast<const int *>(&sh->ctl) + w) : 0;
+            }
+            {
+                constexpr int kRowsPerWarp = (kNumSMsB200 + kWarps - 1) / kWarps;      // 19
+                double v[3] = {0.0, 0.0, 0.0};
+                if (G <= kNumSMsB200) {
+                    double t[kRowsPerWarp][3];
+#pragma unroll
+                    for (int u = 0; u < kRowsPerWarp; ++u) {
+                        const int b = u * kWarps + warp;
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
                             const int j = lane + 32 * c;
@@ -833,19 +841,30 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
+                    for (int u = 0; u < kRowsPerWarp; ++u)
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
                             const int j = lane + 32 * c;
                             v[c] = (j < ns) ? v[c] + t[u][c] : fmax(v[c], t[u][c]);
+                        }
+                } else {
+                    for (int b = warp; b < G; b += kWarps)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const int j = lane + 32 * c;
+                            const double x = (j < nv) ? __ldcg(partials + (size_t)b * A::NV + j) : 0.0;
+                            v[c] = (j < ns) ? v[c] + x : fmax(v[c], x);
                         }
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { const int j = lane + 32 * c; if (j < nv) part[warp][j] = v[c]; }
             }
             // controller state: global -> shared
-            for (int w = tid; w < (int)(sizeof(LmController) / sizeof(int)); w += kThreads)
-                reinterpret_cast<int *>(&s_ctl)[w] = __ldcg(reinterpret_cast<const int *>(&sh->ctl) + w);
+#pragma unroll
+            for (int q = 0; q < (int)(sizeof(ctl_w) / sizeof(int)); ++q) {
+                const int w = tid + q * kThreads;
+                if (w < (int)(sizeof(LmController) / sizeof(int))) reinterpret_cast<int *>(&s_ctl)[w] = ctl_w[q];
+            }
             __syncthreads();
             if (tid < nv) {
                 double x = part[0][tid];
