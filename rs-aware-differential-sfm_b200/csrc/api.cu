@@ -91,7 +91,7 @@ void rsdsfm_destroy(rsdsfm_ctx *ctx)
         if (ctx->pe1[j]) cudaEventDestroy(ctx->pe1[j]);
     }
     if (ctx->pinned_io) cudaFreeHost(ctx->pinned_io);
-    DevBuf *all[] = {&ctx->partials, &ctx->sums, &ctx->pix, &ctx->dA, &ctx->dB, &ctx->scale_e, &ctx->misc, &ctx->winner,
+    DevBuf *all[] = {&ctx->partials, &ctx->sums, &ctx->pix, &ctx->dA, &ctx->dB, &ctx->rdepth, &ctx->misc, &ctx->winner,
                      &ctx->tmp_img, &ctx->depth_rm, &ctx->poses, &ctx->hyp, &ctx->rpart, &ctx->flags, &ctx->scan,
                      &ctx->lm_shared, &ctx->exc};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);

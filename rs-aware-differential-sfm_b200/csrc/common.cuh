@@ -36,7 +36,7 @@ struct rsdsfm_ctx {
     std::string err;
     // scratch
     std::vector<rsdsfm::DevBuf *> bufs;
-    rsdsfm::DevBuf partials, sums, pix, dA, dB, scale_e, misc, stage[16], winner, tmp_img, depth_rm, poses;
+    rsdsfm::DevBuf partials, sums, pix, dA, dB, rdepth, misc, stage[16], winner, tmp_img, depth_rm, poses;
     rsdsfm::DevBuf hyp, rpart, flags, scan, lm_shared, exc;
     rsdsfm::DevBuf pipe[16];  // intermediates of the fused a2-a15 driver (pipeline.cu)
     int exc_cap = 0;          // capacity (entries) of the clamped-pixel exception list
