@@ -194,6 +194,29 @@ RSDSFM_API int rsdsfm_backproject(rsdsfm_ctx *ctx, int mem, const uint8_t *image
 RSDSFM_API int rsdsfm_fill_cracks(rsdsfm_ctx *ctx, int mem, const uint8_t *in, int rows, int cols, unsigned offset,
                        uint8_t *out);
 
+/* ---- accuracy metric of the rectified geometry ------------------------------ */
+/* RsFrame::relocatePose (rsframe.cc:953-967), host computation: scanline 0 keeps its pose, for
+ * i >= 1  t_i -= t_0,  R_i = R_0^-1 R_i.  R: rows x 9 (row-major 3x3), t: rows x 3. */
+RSDSFM_API int rsdsfm_relocate_pose(const double *R, const double *t, int rows, double *R_out, double *t_out);
+
+/* Camera::meanReprojectionError (camera.cc:593-691) and, when error_image != NULL,
+ * Camera::createErrorImage (camera.cc:503-590), including RsFrame::getGroundtruthDepthMap
+ * (rsframe.cc:416-436) and relocatePose.
+ *   coords3d   rows*cols*3 float: RsFrame::get3dCoordinates() as left by rsdsfm_backproject
+ *   unproj_*   rows*cols doubles each: the frame's unprojection maps (world point per RS pixel)
+ *   R_gt,t_gt  host, rows x 9 / rows x 3: ground-truth camera-from-world pose of every scanline
+ *   depth_est  rows*cols: the frame's depth map (used where the ground-truth depth is exactly 0,
+ *              like planeToSpace's default argument, rsframe.cc:657-659)
+ *   layout     RSDSFM_DEPTH_* of unproj_*, depth_est and gt_depth_map
+ * Outputs (host scalars): *mean_error; nullable *mean_scale, *num_outliers, *points_used;
+ * nullable arrays in `mem`: error_image (rows*cols, row-major 8-bit, max_norm = pixel value 255)
+ * and gt_depth_map (rows*cols). */
+RSDSFM_API int rsdsfm_reprojection_error(rsdsfm_ctx *ctx, int mem, const float *coords3d, const double *unproj_x,
+                          const double *unproj_y, const double *unproj_z, const double *R_gt, const double *t_gt,
+                          const double *depth_est, int layout, int rows, int cols, const double *K4,
+                          double max_norm, double *mean_error, double *mean_scale, int *num_outliers,
+                          int *points_used, uint8_t *error_image, double *gt_depth_map);
+
 /* ---- fused driver of the timed region "refine + rectify" (main.cc:457-523) ---------------- */
 /* nonLinearRefinement -> sign fix -> depth raster -> setPose -> backProject(Gs) ->
  * interpolateCrackyImage(.,1) for one frame pair, without leaving the device.

@@ -227,3 +227,40 @@ def refine_rectify(flow, inliers3, alpha, alpha_k, m, v, w, k, const_acc, gs_mod
                          int(const_acc), int(gs_mode), image.ctypes.data_as(_u8p), rows, cols, _d(K4),
                          C.c_double(gamma), _d(z), _d(dm), out.ctypes.data_as(_u8p), C.byref(S))
     return dict(v=v, w=w, k=kk.value, z=z[:m], depth_map=dm, rectified=out, summary=S.as_dict())
+
+
+# ---- ground-truth depth map, relocatePose, meanReprojectionError / createErrorImage
+def groundtruth_depth_map(ux, uy, uz, R_gt, t_gt):
+    """RsFrame::getGroundtruthDepthMap.  ux,uy,uz: (rows, cols) arrays; returns (rows, cols)."""
+    rows, cols = ux.shape
+    f = lambda a: _f64(np.asarray(a, dtype=np.float64).flatten(order="F"))
+    R = _f64(R_gt).reshape(-1); t = _f64(t_gt).reshape(-1)
+    out = np.empty(rows * cols)
+    a, b, c = f(ux), f(uy), f(uz)
+    lib().orc_groundtruth_depth_map(_d(a), _d(b), _d(c), _d(R), _d(t), rows, cols, _d(out))
+    return out.reshape(cols, rows).T.copy()
+
+
+def relocate_pose(R_gt, t_gt):
+    R = _f64(R_gt).reshape(-1).copy(); t = _f64(t_gt).reshape(-1).copy()
+    rows = t.size // 3
+    lib().orc_relocate_pose(_d(R), _d(t), rows)
+    return R.reshape(rows, 3, 3), t.reshape(rows, 3)
+
+
+def mean_reprojection_error(coords3d, ux, uy, uz, R_gt, t_gt, depth_est_colmajor, K4, max_norm=1.0, want_image=False):
+    """Camera::meanReprojectionError (+ createErrorImage).  Returns dict(mean_error, mean_scale,
+    num_outliers, points_used, error_image)."""
+    rows, cols = ux.shape
+    f = lambda a: _f64(np.asarray(a, dtype=np.float64).flatten(order="F"))
+    co = np.ascontiguousarray(coords3d, dtype=np.float32)
+    R = _f64(R_gt).reshape(-1); t = _f64(t_gt).reshape(-1); K4 = _f64(K4)
+    de = _f64(depth_est_colmajor).reshape(-1)
+    a, b, c = f(ux), f(uy), f(uz)
+    ms = C.c_double(0); no = C.c_int(0); pu = C.c_int(0)
+    img = np.zeros((rows, cols), dtype=np.uint8) if want_image else None
+    fn = lib().orc_mean_reprojection_error
+    fn.restype = C.c_double
+    err = fn(co.ctypes.data_as(_fp), _d(a), _d(b), _d(c), _d(R), _d(t), _d(de), rows, cols, _d(K4), C.c_double(max_norm),
+             C.byref(ms), C.byref(no), C.byref(pu), img.ctypes.data_as(_u8p) if want_image else None)
+    return dict(mean_error=float(err), mean_scale=ms.value, num_outliers=no.value, points_used=pu.value, error_image=img)

@@ -1131,3 +1131,127 @@ ORC_API int orc_refine_rectify(const double *flow, const double *inliers3_in, co
 }
 
 ORC_API int orc_sizeof_summary(void) { return (int)sizeof(OrcLmSummary); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Camera::meanReprojectionError / createErrorImage   camera.cc:503-691         */
+/*                RsFrame::getGroundtruthDepthMap rsframe.cc:416-436, relocatePose :953-967    */
+/* ------------------------------------------------------------------------------------------ */
+/* Eigen 3.3 Inverse.h, compute_inverse_size3_helper: cofactors of column 0, determinant as their
+ * dot product with column 0, every entry = cofactor * (1/det). */
+static double cof3(const double *m, int i, int j)
+{
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    return m[i1 * 3 + j1] * m[i2 * 3 + j2] - m[i1 * 3 + j2] * m[i2 * 3 + j1];
+}
+static void mat3_inverse_eigen(const double *m, double *inv)
+{
+    const double c00 = cof3(m, 0, 0), c10 = cof3(m, 1, 0), c20 = cof3(m, 2, 0);
+    const double det = c00 * m[0] + c10 * m[3] + c20 * m[6];
+    const double invdet = 1.0 / det;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) inv[r * 3 + c] = cof3(m, c, r) * invdet;      /* inverse(r,c) = cofactor<c,r> / det */
+}
+
+/* unprojection maps ux,uy,uz and the output are COLUMN-major rows x cols (Eigen MatrixXd);
+ * R,t: ground-truth scanline poses, rows x 9 (row-major 3x3) and rows x 3. */
+ORC_API void orc_groundtruth_depth_map(const double *ux, const double *uy, const double *uz, const double *R,
+                                       const double *t, int rows, int cols, double *depth)
+{
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) {
+            const size_t i = (size_t)y + (size_t)x * rows;
+            const double P[3] = {ux[i], uy[i], uz[i]};
+            depth[i] = 0.0;
+            if (sqrt(P[0] * P[0] + P[1] * P[1] + P[2] * P[2]) > 0) {                  /* :428 */
+                const double *Rs = R + 9 * y, *ts = t + 3 * y;                          /* worldToCameraFrame :687-708 */
+                depth[i] = Rs[6] * P[0] + Rs[7] * P[1] + Rs[8] * P[2] + ts[2] * 1.0;
+            }
+        }
+}
+
+ORC_API void orc_relocate_pose(double *R, double *t, int rows)
+{
+    double R0[9], R0inv[9], t0[3];
+    memcpy(R0, R, sizeof R0);
+    memcpy(t0, t, sizeof t0);
+    mat3_inverse_eigen(R0, R0inv);                                   /* evaluated per row in the reference: same value */
+    for (int i = 1; i < rows; ++i) {                                  /* row 0 keeps its pose (:961) */
+        double Rn[9];
+        for (int a = 0; a < 3; ++a) t[3 * i + a] = t[3 * i + a] - t0[a];
+        mat3_mul(R0inv, R + 9 * i, Rn);
+        memcpy(R + 9 * i, Rn, sizeof Rn);
+    }
+}
+
+/* coords3d_est: rows*cols*3 float (RsFrame::get3dCoordinates after backProject); depth_est: the
+ * frame's depth_map_ (column-major), used by planeToSpace when the ground-truth depth is exactly 0
+ * (rsframe.cc:657-659).  Returns the mean error; error_image (nullable): rows*cols, row-major. */
+ORC_API double orc_mean_reprojection_error(const float *coords3d_est, const double *ux, const double *uy,
+                                           const double *uz, const double *R_gt, const double *t_gt,
+                                           const double *depth_est, int rows, int cols, const double *K4,
+                                           double max_norm, double *mean_scale, int *num_outliers,
+                                           int *points_used, uint8_t *error_image)
+{
+    const double fx = K4[0], fy = K4[1], cx = K4[2], cy = K4[3];
+    const size_t tot = (size_t)rows * cols;
+    double *gt_depth = (double *)malloc(sizeof(double) * tot);
+    double *R = (double *)malloc(sizeof(double) * 9 * rows), *t = (double *)malloc(sizeof(double) * 3 * rows);
+    float *truep = (float *)malloc(sizeof(float) * 3 * tot);
+    double *scales = (double *)calloc(3 * tot, sizeof(double));
+    orc_groundtruth_depth_map(ux, uy, uz, R_gt, t_gt, rows, cols, gt_depth);       /* camera.cc:612, original poses */
+    memcpy(R, R_gt, sizeof(double) * 9 * rows);
+    memcpy(t, t_gt, sizeof(double) * 3 * rows);
+    orc_relocate_pose(R, t, rows);                                                 /* :620 */
+    int outliers = 0;
+    for (int x = 0; x < cols; ++x)
+        for (int y = 0; y < rows; ++y) {
+            double z = gt_depth[(size_t)y + (size_t)x * rows];
+            const double nx = ((double)x - cx) * 1.0 / fx, ny = ((double)y - cy) * 1.0 / fy;
+            if (z == 0) z = depth_est[(size_t)y + (size_t)x * rows];
+            const double Pc[3] = {z * nx, z * ny, z * 1.0};
+            const double *Rs = R + 9 * y, *ts = t + 3 * y;
+            double Rt[9], ti[3], Pw[3];
+            mat3_t(Rs, Rt);
+            for (int a = 0; a < 3; ++a)
+                ti[a] = (-Rt[a * 3 + 0]) * ts[0] + (-Rt[a * 3 + 1]) * ts[1] + (-Rt[a * 3 + 2]) * ts[2];
+            for (int a = 0; a < 3; ++a)
+                Pw[a] = Rt[a * 3 + 0] * Pc[0] + Rt[a * 3 + 1] * Pc[1] + Rt[a * 3 + 2] * Pc[2] + ti[a] * 1.0;
+            float *pt = truep + ((size_t)y * cols + x) * 3;
+            const float *pe = coords3d_est + ((size_t)y * cols + x) * 3;
+            for (int c = 0; c < 3; ++c) {
+                pt[c] = (float)Pw[c];
+                const float s = pe[c] / pt[c];
+                scales[(size_t)x * 3 * rows + 3 * (size_t)y + c] = s;
+                if (fabsf(s) > 10) { scales[(size_t)x * 3 * rows + 3 * (size_t)y + c] = 0; outliers++; }
+            }
+        }
+    double sum = 0;
+    int inliers = 0;
+    for (size_t i = 0; i < 3 * tot; ++i)
+        if (scales[i] != 0 && scales[i] == scales[i]) { inliers++; sum += scales[i]; }
+    const double scale = sum / (double)inliers;
+    double sum_error = 0;
+    inliers = 0;
+    for (int x = 0; x < cols; ++x)
+        for (int y = 0; y < rows; ++y) {
+            const float *pe = coords3d_est + ((size_t)y * cols + x) * 3;
+            const float *pt = truep + ((size_t)y * cols + x) * 3;
+            const double e0 = pe[0] / scale, e1 = pe[1] / scale, e2 = pe[2] / scale;
+            const double t0 = pt[0], t1 = pt[1], t2 = pt[2];
+            const double d0 = e0 - t0, d1 = e1 - t1, d2 = e2 - t2;
+            const double nrm = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+            if (e0 == e0 && e1 == e1 && e2 == e2 && t0 == t0 && t1 == t1 && t2 == t2)
+                if (nrm < 50) { sum_error += nrm; inliers++; }
+            if (error_image) {                                                     /* createErrorImage :583 */
+                int q = 0;
+                const double val = nrm * 255 / max_norm + 0.5;
+                if (!trunc_to_int(val, &q)) q = (int)0x80000000;
+                error_image[(size_t)y * cols + x] = (uint8_t)(q & 0xff);
+            }
+        }
+    if (mean_scale) *mean_scale = scale;
+    if (num_outliers) *num_outliers = outliers;
+    if (points_used) *points_used = inliers;
+    free(gt_depth); free(R); free(t); free(truep); free(scales);
+    return sum_error * 1.0 / inliers;
+}

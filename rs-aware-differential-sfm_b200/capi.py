@@ -21,6 +21,7 @@ EXPORTS = [
     "rsdsfm_ransac_score", "rsdsfm_ransac", "rsdsfm_gather_inliers", "rsdsfm_estimate_inverse_depths",
     "rsdsfm_refine", "rsdsfm_depth_glue", "rsdsfm_set_relative_pose", "rsdsfm_backproject", "rsdsfm_fill_cracks",
     "rsdsfm_refine_rectify", "rsdsfm_refine_rectify_sequence", "rsdsfm_pipeline_pair", "rsdsfm_pipeline_sequence",
+    "rsdsfm_relocate_pose", "rsdsfm_reprojection_error",
 ]
 
 
@@ -412,6 +413,35 @@ class Context:
         self._ck(rc)
         return res
 
+    # ---- SURVEY 8(f)-1
+    def reprojection_error(self, coords3d, unproj, R_gt, t_gt, depth_est, K4, max_norm=1.0, layout=DEPTH_COLMAJOR,
+                           want_image=False, want_gt_depth=False):
+        """rsdsfm_reprojection_error.  coords3d: rows x cols x 3 float32; unproj: (x, y, z) maps of rows*cols doubles
+        in `layout`; depth_est likewise.  numpy = host, torch CUDA = device.  Returns dict(mean_error, mean_scale,
+        num_outliers, points_used, error_image, gt_depth_map)."""
+        rows, cols = int(coords3d.shape[0]), int(coords3d.shape[1])
+        ux, uy, uz = (_f64(a) for a in unproj)
+        depth_est = _f64(depth_est)
+        R = np.ascontiguousarray(np.asarray(R_gt, dtype=np.float64).reshape(-1)); t = np.ascontiguousarray(np.asarray(t_gt, dtype=np.float64).reshape(-1))
+        assert R.size == 9 * rows and t.size == 3 * rows
+        K4 = _small(K4, 4)
+        if _is_torch(coords3d):
+            import torch
+            assert coords3d.is_cuda and coords3d.is_contiguous() and str(coords3d.dtype) == "torch.float32"
+            img = torch.empty((rows, cols), dtype=torch.uint8, device=coords3d.device) if want_image else None
+            gd = torch.empty(rows * cols, dtype=torch.float64, device=coords3d.device) if want_gt_depth else None
+        else:
+            coords3d = np.ascontiguousarray(coords3d, dtype=np.float32)
+            img = np.empty((rows, cols), dtype=np.uint8) if want_image else None
+            gd = np.empty(rows * cols) if want_gt_depth else None
+        me = C.c_double(0); ms = C.c_double(0); no = C.c_int(0); pu = C.c_int(0)
+        self._ck(self.lib.rsdsfm_reprojection_error(self.h, _mem(coords3d, ux, uy, uz, depth_est, img, gd), _ptr(coords3d), _ptr(ux), _ptr(uy),
+                                                    _ptr(uz), _ptr(R), _ptr(t), _ptr(depth_est), int(layout), rows, cols, _ptr(K4),
+                                                    C.c_double(max_norm), C.byref(me), C.byref(ms), C.byref(no), C.byref(pu),
+                                                    _ptr(img), _ptr(gd)))
+        return dict(mean_error=me.value, mean_scale=ms.value, num_outliers=no.value, points_used=pu.value, error_image=img,
+                    gt_depth_map=gd)
+
     # ---- a2..a15 in one call
     @staticmethod
     def _pipeline_params(rows, cols, K4, gamma, H, tol, const_acc, gs_mode, use_refinement, repair_pairing, layout, thr):
@@ -480,6 +510,18 @@ class Context:
     def pipeline_pair(self, flow_img, image, K4, gamma, tol, const_acc, samples=None, draws=None, **kw):
         return self.pipeline_sequence([dict(flow_img=flow_img, image=image, samples=samples, draws=draws, out=kw.pop("out", None))],
                                       K4, gamma, tol, const_acc, **kw)[0]
+
+
+def relocate_pose(R_gt, t_gt):
+    """RsFrame::relocatePose (host).  Returns (R, t) with shapes (rows, 3, 3), (rows, 3)."""
+    lib = load()
+    R = np.ascontiguousarray(np.asarray(R_gt, dtype=np.float64).reshape(-1)); t = np.ascontiguousarray(np.asarray(t_gt, dtype=np.float64).reshape(-1))
+    rows = t.size // 3
+    Ro = np.empty_like(R); to = np.empty_like(t)
+    rc = lib.rsdsfm_relocate_pose(_ptr(R), _ptr(t), rows, _ptr(Ro), _ptr(to))
+    if rc != 0:
+        raise RsdsfmError("rsdsfm_relocate_pose failed: %d" % rc)
+    return Ro.reshape(rows, 3, 3), to.reshape(rows, 3)
 
 
 def solve9(q9, u9, alpha9, alpha_k9, use_alpha_k):

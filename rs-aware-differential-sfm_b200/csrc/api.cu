@@ -403,4 +403,84 @@ int rsdsfm_fill_cracks(rsdsfm_ctx *ctx, int mem, const uint8_t *in, int rows, in
     return finish_host_call(ctx, mem);
 }
 
+int rsdsfm_relocate_pose(const double *R, const double *t, int rows, double *R_out, double *t_out)
+{
+    if (!R || !t || !R_out || !t_out || rows <= 0) return RSDSFM_ERR_ARG;
+    // RsFrame::relocatePose, rsframe.cc:953-967: scanline 0 keeps its pose; for i >= 1
+    // t_i -= t_0 and R_i = R_0^-1 R_i with Eigen's 3x3 inverse (cofactors / determinant)
+    const double *m = R;
+    auto cof = [&](int i, int j) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        return m[i1 * 3 + j1] * m[i2 * 3 + j2] - m[i1 * 3 + j2] * m[i2 * 3 + j1];
+    };
+    const double det = cof(0, 0) * m[0] + cof(1, 0) * m[3] + cof(2, 0) * m[6];
+    const double invdet = 1.0 / det;
+    double inv[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) inv[r * 3 + c] = cof(c, r) * invdet;
+    const double t0[3] = {t[0], t[1], t[2]};
+    for (int a = 0; a < 9; ++a) R_out[a] = R[a];
+    for (int a = 0; a < 3; ++a) t_out[a] = t[a];
+    for (int i = 1; i < rows; ++i) {
+        const double *Ri = R + 9 * (size_t)i;
+        double Rn[9];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) Rn[r * 3 + c] = inv[r * 3 + 0] * Ri[0 * 3 + c] + inv[r * 3 + 1] * Ri[1 * 3 + c] + inv[r * 3 + 2] * Ri[2 * 3 + c];
+        for (int a = 0; a < 9; ++a) R_out[9 * (size_t)i + a] = Rn[a];
+        for (int a = 0; a < 3; ++a) t_out[3 * (size_t)i + a] = t[3 * (size_t)i + a] - t0[a];
+    }
+    return RSDSFM_OK;
+}
+
+int rsdsfm_reprojection_error(rsdsfm_ctx *ctx, int mem, const float *coords3d, const double *unproj_x, const double *unproj_y,
+                              const double *unproj_z, const double *R_gt, const double *t_gt, const double *depth_est,
+                              int layout, int rows, int cols, const double *K4, double max_norm, double *mean_error,
+                              double *mean_scale, int *num_outliers, int *points_used, uint8_t *error_image,
+                              double *gt_depth_map)
+{
+    RS_ENTER(ctx);
+    if (rows <= 0 || cols <= 0 || !coords3d || !unproj_x || !unproj_y || !unproj_z || !R_gt || !t_gt || !depth_est || !K4 ||
+        !mean_error)
+        return fail(ctx, RSDSFM_ERR_ARG, "rsdsfm_reprojection_error: bad argument");
+    const size_t tot = (size_t)rows * cols;
+    const void *d_c = nullptr, *d_x = nullptr, *d_y = nullptr, *d_z = nullptr, *d_de = nullptr;
+    void *d_img = nullptr, *d_gd = nullptr;
+    RS_TRY(stage_in(ctx, mem, 0, coords3d, sizeof(float) * 3 * tot, &d_c));
+    RS_TRY(stage_in(ctx, mem, 1, unproj_x, sizeof(double) * tot, &d_x));
+    RS_TRY(stage_in(ctx, mem, 2, unproj_y, sizeof(double) * tot, &d_y));
+    RS_TRY(stage_in(ctx, mem, 3, unproj_z, sizeof(double) * tot, &d_z));
+    RS_TRY(stage_in(ctx, mem, 4, depth_est, sizeof(double) * tot, &d_de));
+    RS_TRY(stage_out_reserve(ctx, mem, 5, error_image, tot, &d_img));
+    RS_TRY(stage_out_reserve(ctx, mem, 6, gt_depth_map, sizeof(double) * tot, &d_gd));
+    // scanline poses: original + relocated, interleaved per row, staged through pinned memory
+    RS_TRY(ensure_pinned(ctx, sizeof(double) * 24 * (size_t)rows + 256));
+    RS_TRY(ensure(ctx, ctx->pipe[15], sizeof(double) * 24 * (size_t)rows));
+    RS_TRY(ensure(ctx, ctx->pipe[14], sizeof(float) * 3 * tot));
+    RS_TRY(ensure(ctx, ctx->misc, 256));
+    {
+        std::vector<double> Rr((size_t)rows * 9), tr((size_t)rows * 3);
+        rsdsfm_relocate_pose(R_gt, t_gt, rows, Rr.data(), tr.data());
+        double *hp = (double *)ctx->pinned;
+        for (int i = 0; i < rows; ++i) {
+            double *o = hp + 24 * (size_t)i;
+            for (int a = 0; a < 9; ++a) { o[a] = R_gt[9 * (size_t)i + a]; o[12 + a] = Rr[9 * (size_t)i + a]; }
+            for (int a = 0; a < 3; ++a) { o[9 + a] = t_gt[3 * (size_t)i + a]; o[21 + a] = tr[3 * (size_t)i + a]; }
+        }
+        RS_CUDA(ctx, cudaMemcpyAsync(ctx->pipe[15].p, hp, sizeof(double) * 24 * (size_t)rows, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    double *sums = (double *)ctx->misc.p;
+    RS_TRY(reproj_device(ctx, (const float *)d_c, (const double *)d_x, (const double *)d_y, (const double *)d_z,
+                         (const double *)ctx->pipe[15].p, (const double *)d_de, layout, rows, cols, K4, max_norm,
+                         (float *)ctx->pipe[14].p, (uint8_t *)d_img, (double *)d_gd, sums));
+    RS_TRY(stage_out(ctx, mem, error_image, d_img, tot));
+    RS_TRY(stage_out(ctx, mem, gt_depth_map, d_gd, sizeof(double) * tot));
+    double *hs = (double *)((char *)ctx->pinned + sizeof(double) * 24 * (size_t)rows);
+    RS_CUDA(ctx, cudaMemcpyAsync(hs, sums, sizeof(double) * 5, cudaMemcpyDeviceToHost, ctx->stream));
+    RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *mean_error = hs[3] * 1.0 / hs[4];                                  // camera.cc:690
+    if (mean_scale) *mean_scale = hs[0] / hs[1];
+    if (num_outliers) *num_outliers = (int)hs[2];
+    if (points_used) *points_used = (int)hs[4];
+    return RSDSFM_OK;
+}
+
 }  // extern "C"

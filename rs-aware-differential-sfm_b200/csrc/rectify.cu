@@ -275,4 +275,97 @@ int fill_cracks_device(rsdsfm_ctx *ctx, const uint8_t *in, int rows, int cols, u
     return RSDSFM_OK;
 }
 
+// ---------------------------------------------------------------- reprojection error
+// Camera::meanReprojectionError / createErrorImage (camera.cc:503-691) with
+// RsFrame::getGroundtruthDepthMap (rsframe.cc:416-436).  Two per-pixel map-reduce passes:
+//   k_reproj_points  ground-truth depth under the ORIGINAL scanline pose, ground-truth world point
+//                    under the RELOCATED pose (float, like the reference's Vec3f), per-component scale
+//                    est/true with the |s| > 10 outlier rule; sums: scale, valid entries, outliers
+//   k_reproj_error   mean scale -> per-pixel Euclidean error, < 50 rule, optional 8-bit error image
+// poses: rows x 24 doubles = original R[9], t[3], relocated R[9], t[3] per scanline.
+struct ReprojParams {
+    double fx, fy, cx, cy, max_norm;
+    int rows, cols, layout;
+};
+
+__global__ void __launch_bounds__(kThreads) k_reproj_points(const float *__restrict__ est, const double *__restrict__ ux,
+                                                            const double *__restrict__ uy, const double *__restrict__ uz,
+                                                            const double *__restrict__ poses,
+                                                            const double *__restrict__ depth_est, ReprojParams P,
+                                                            float *__restrict__ truep, double *__restrict__ gt_depth,
+                                                            double *__restrict__ partials)
+{
+    const long long total = (long long)P.rows * P.cols;
+    double s[3] = {0.0, 0.0, 0.0}, mx[1] = {0.0};
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(p / P.cols), x = (int)(p - (long long)y * P.cols);
+        const size_t mi = (P.layout == RSDSFM_DEPTH_COLMAJOR) ? ((size_t)y + (size_t)x * P.rows) : (size_t)p;
+        const double *po = poses + 24 * (size_t)y;
+        const double W[3] = {ux[mi], uy[mi], uz[mi]};
+        double z = 0.0;
+        if (sqrt(W[0] * W[0] + W[1] * W[1] + W[2] * W[2]) > 0)                       // rsframe.cc:428
+            z = po[6] * W[0] + po[7] * W[1] + po[8] * W[2] + po[11] * 1.0;            // worldToCameraFrame(., y, false).z
+        if (gt_depth) gt_depth[mi] = z;
+        if (z == 0) z = depth_est[mi];                                               // planeToSpace default (rsframe.cc:657-659)
+        const double nx = ((double)x - P.cx) * 1.0 / P.fx;
+        const double ny = ((double)y - P.cy) * 1.0 / P.fy;
+        const double Pc[3] = {z * nx, z * ny, z * 1.0};
+        const double *Rs = po + 12, *ts = po + 21;                                   // relocated pose
+        double Rt[9], ti[3];
+        for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) Rt[a * 3 + c] = Rs[c * 3 + a];
+        for (int a = 0; a < 3; ++a) ti[a] = (-Rt[a * 3 + 0]) * ts[0] + (-Rt[a * 3 + 1]) * ts[1] + (-Rt[a * 3 + 2]) * ts[2];
+        for (int a = 0; a < 3; ++a) {
+            const double Pw = Rt[a * 3 + 0] * Pc[0] + Rt[a * 3 + 1] * Pc[1] + Rt[a * 3 + 2] * Pc[2] + ti[a] * 1.0;
+            const float pt = (float)Pw;
+            truep[3 * p + a] = pt;
+            const float sc = est[3 * p + a] / pt;                                    // camera.cc:632-634 (float division)
+            if (fabsf(sc) > 10) s[2] += 1.0;                                         // outlier: entry zeroed, not averaged
+            else if (sc != 0 && sc == sc) { s[0] += (double)sc; s[1] += 1.0; }
+        }
+    }
+    block_reduce_store<3, 0>(s, mx, partials);
+}
+
+__global__ void __launch_bounds__(kThreads) k_reproj_error(const float *__restrict__ est, const float *__restrict__ truep,
+                                                           const double *__restrict__ sums, ReprojParams P,
+                                                           uint8_t *__restrict__ error_image, double *__restrict__ partials)
+{
+    const long long total = (long long)P.rows * P.cols;
+    const double scale = sums[0] / sums[1];                                          // camera.cc:657
+    double s[2] = {0.0, 0.0}, mx[1] = {0.0};
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+        const double e0 = est[3 * p] / scale, e1 = est[3 * p + 1] / scale, e2 = est[3 * p + 2] / scale;
+        const double t0 = truep[3 * p], t1 = truep[3 * p + 1], t2 = truep[3 * p + 2];
+        const double d0 = e0 - t0, d1 = e1 - t1, d2 = e2 - t2;
+        const double nrm = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        if (e0 == e0 && e1 == e1 && e2 == e2 && t0 == t0 && t1 == t1 && t2 == t2 && nrm < 50) { s[0] += nrm; s[1] += 1.0; }
+        if (error_image) {                                                           // createErrorImage, camera.cc:583
+            int q;
+            if (!to_int_trunc(nrm * 255 / P.max_norm + 0.5, q)) q = (int)0x80000000;
+            error_image[p] = (uint8_t)(q & 0xff);
+        }
+    }
+    block_reduce_store<2, 0>(s, mx, partials);
+}
+
+// sums5 (device, 8 doubles): [0] sum of scales, [1] entries averaged, [2] outliers, [3] sum of errors, [4] points used
+int reproj_device(rsdsfm_ctx *ctx, const float *est, const double *ux, const double *uy, const double *uz,
+                  const double *poses24, const double *depth_est, int layout, int rows, int cols, const double *K4,
+                  double max_norm, float *truep, uint8_t *error_image, double *gt_depth, double *sums5)
+{
+    const long long total = (long long)rows * cols;
+    const int grid = grid_for(ctx, total, 4);
+    RS_TRY(ensure(ctx, ctx->rpart, sizeof(double) * 3 * (size_t)grid));
+    double *partials = (double *)ctx->rpart.p;
+    ReprojParams P{K4[0], K4[1], K4[2], K4[3], max_norm, rows, cols, layout};
+    k_reproj_points<<<grid, kThreads, 0, ctx->stream>>>(est, ux, uy, uz, poses24, depth_est, P, truep, gt_depth, partials);
+    ctx->launches++;
+    launch_final_reduce(ctx, partials, grid, 3, 0, sums5);
+    k_reproj_error<<<grid, kThreads, 0, ctx->stream>>>(est, truep, sums5, P, error_image, partials);
+    ctx->launches++;
+    launch_final_reduce(ctx, partials, grid, 2, 0, sums5 + 3);
+    RS_CUDA(ctx, cudaGetLastError());
+    return RSDSFM_OK;
+}
+
 }  // namespace rsdsfm

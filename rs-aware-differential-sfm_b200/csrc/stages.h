@@ -54,4 +54,10 @@ int backproject_device(rsdsfm_ctx *, const uint8_t *image, const double *depth, 
 // a15: interpolateCrackyImage (camera.cc:753-774)
 int fill_cracks_device(rsdsfm_ctx *, const uint8_t *in, int rows, int cols, unsigned offset, uint8_t *out);
 
+// meanReprojectionError / createErrorImage (camera.cc:503-691); poses24 = per scanline
+// original R[9], t[3] and relocated R[9], t[3]; sums5 (device): scale sum, entries, outliers, error sum, points
+int reproj_device(rsdsfm_ctx *, const float *est, const double *ux, const double *uy, const double *uz, const double *poses24,
+                  const double *depth_est, int layout, int rows, int cols, const double *K4, double max_norm, float *truep,
+                  uint8_t *error_image, double *gt_depth, double *sums5);
+
 }  // namespace rsdsfm

@@ -315,7 +315,68 @@ public:
     void backProject() { backProjectImpl(0); }
     void backProjectGs() { backProjectImpl(1); }
 
+    // ---- ground truth of a synthetic frame.  The reference fills these members from
+    // the fixture CSVs (rsframe.cc:222-378, :444-553); the loaders are upstream of this path, so the
+    // values are attached instead.
+    void setUnprojectionMaps(const Eigen::MatrixXd &x, const Eigen::MatrixXd &y, const Eigen::MatrixXd &z)
+    {
+        unprojection_map_x_ = x; unprojection_map_y_ = y; unprojection_map_z_ = z;
+    }
+    void setScanlinePose(const int scanlineNr, const Eigen::Matrix3d &rotation, const Eigen::Vector3d &translation)
+    {
+        scanlines_[(size_t)scanlineNr].setRotation(rotation);
+        scanlines_[(size_t)scanlineNr].setTranslation(translation);
+    }
+    // rsframe.cc:416-436
+    Eigen::MatrixXd getGroundtruthDepthMap()
+    {
+        Eigen::MatrixXd out = Eigen::MatrixXd::Zero(rows_, cols_);
+        double mean_error = 0;
+        std::vector<float> no_estimate((size_t)3 * rows_ * cols_, 0.f);
+        reprojection(no_estimate.data(), 1.0, &mean_error, nullptr, out.data());
+        return out;
+    }
+    // rsframe.cc:953-967
+    void relocatePose()
+    {
+        std::vector<double> R, t;
+        packPoses(R, t);
+        std::vector<double> Ro(R.size()), to(t.size());
+        rsdsfm_host::check(rsdsfm_relocate_pose(R.data(), t.data(), rows_, Ro.data(), to.data()), "relocatePose");
+        for (int i = 0; i < rows_; ++i) {
+            Eigen::Matrix3d Ri; Eigen::Vector3d ti;
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Ri(r, c) = Ro[(size_t)9 * i + 3 * r + c];
+            for (int a = 0; a < 3; ++a) ti(a) = to[(size_t)3 * i + a];
+            scanlines_[(size_t)i].setRotation(Ri);
+            scanlines_[(size_t)i].setTranslation(ti);
+        }
+    }
+    // the per-pixel map-reduce behind Camera::meanReprojectionError / createErrorImage (camera.cc:503-691)
+    void reprojection(const float *coords3d, double max_norm, double *mean_error, unsigned char *error_image, double *gt_depth)
+    {
+        std::vector<double> R, t;
+        packPoses(R, t);
+        const double K4[4] = {f_x_, f_y_, c_x_, c_y_};
+        Eigen::MatrixXd depth = depth_map_;
+        if (depth.rows() != rows_ || depth.cols() != cols_) depth = Eigen::MatrixXd::Zero(rows_, cols_);
+        rsdsfm_host::check(rsdsfm_reprojection_error(rsdsfm_host::context(), RSDSFM_HOST, coords3d, unprojection_map_x_.data(),
+                                                     unprojection_map_y_.data(), unprojection_map_z_.data(), R.data(), t.data(),
+                                                     depth.data(), RSDSFM_DEPTH_COLMAJOR, rows_, cols_, K4, max_norm, mean_error,
+                                                     nullptr, nullptr, nullptr, error_image, gt_depth),
+                           "meanReprojectionError");
+    }
+
 private:
+    void packPoses(std::vector<double> &R, std::vector<double> &t) const
+    {
+        R.resize((size_t)9 * rows_); t.resize((size_t)3 * rows_);
+        for (int i = 0; i < rows_; ++i) {
+            const Eigen::Matrix3d &Ri = scanlines_[(size_t)i].getRotation();
+            const Eigen::Vector3d &ti = scanlines_[(size_t)i].getTranslation();
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[(size_t)9 * i + 3 * r + c] = Ri(r, c);
+            for (int a = 0; a < 3; ++a) t[(size_t)3 * i + a] = ti(a);
+        }
+    }
     void backProjectImpl(int gs_mode)
     {
         std::vector<double> R((size_t)9 * rows_), t((size_t)3 * rows_);
@@ -340,6 +401,7 @@ private:
     double f_x_ = 0, f_y_ = 0, c_x_ = 0, c_y_ = 0, gamma_ = 0;
     cv::Mat image_, gs_image_, coordinates_3d_;
     Eigen::MatrixXd depth_map_;
+    Eigen::MatrixXd unprojection_map_x_, unprojection_map_y_, unprojection_map_z_;
     std::vector<Scanline> scanlines_;
 };
 
@@ -384,6 +446,35 @@ public:
     void setCachedFlow(const cv::Mat_<cv::Point_<double>> &flow) { cached_flow_ = flow; }
     cv::Mat_<cv::Point_<double>> calculateDeepFlow(const int, const int) { return cached_flow_; }
     cv::Mat_<cv::Point_<double>> calculateTrueFlow(const int, const int) { return cached_flow_; }
+
+    // ground-truth attachments (stand-ins for the CSV loaders, camera.cc:99-176)
+    void setUnprojectionMaps(const int frameNr, const Eigen::MatrixXd &x, const Eigen::MatrixXd &y, const Eigen::MatrixXd &z)
+    {
+        frames_[(size_t)frameNr - 1].setUnprojectionMaps(x, y, z);
+    }
+    void setScanlinePose(const int frameNr, const int scanlineNr, const Eigen::Matrix3d &rotation, const Eigen::Vector3d &translation)
+    {
+        frames_[(size_t)frameNr - 1].setScanlinePose(scanlineNr, rotation, translation);
+    }
+    // camera.cc:593-691 -- works on a copy of the frame, like the reference
+    double meanReprojectionError(const int frameNr)
+    {
+        RsFrame frame = frames_[(size_t)frameNr - 1];
+        cv::Mat coords = frame.get3dCoordinates();
+        double mean_error = 0;
+        frame.reprojection(reinterpret_cast<const float *>(coords.data), 1.0, &mean_error, nullptr, nullptr);
+        return mean_error;
+    }
+    // camera.cc:503-590
+    cv::Mat createErrorImage(const int frameNr, const double max_norm)
+    {
+        RsFrame frame = frames_[(size_t)frameNr - 1];
+        cv::Mat coords = frame.get3dCoordinates();
+        cv::Mat error_image(frame.getRows(), frame.getCols(), CV_8UC1, cv::Scalar(0));
+        double mean_error = 0;
+        frame.reprojection(reinterpret_cast<const float *>(coords.data), max_norm, &mean_error, error_image.data, nullptr);
+        return error_image;
+    }
 
     // camera.cc:753-774
     cv::Mat interpolateCrackyImage(cv::Mat image_in, const unsigned offset)

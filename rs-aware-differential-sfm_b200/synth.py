@@ -125,6 +125,37 @@ def make_pair(rows=1080, cols=1920, intrinsics="galaxy_stabil", gamma=0.95, v=(0
                 rows=rows, cols=cols)
 
 
+def ground_truth(P, world_R=None, world_t=None, void_frac=0.0, seed=11):
+    """Ground-truth fixtures of the RS frame of a synthetic pair, in the layout the reference loads from
+    disk (rsframe.cc:222-378): per-pixel world points `unproj` = (X, Y, Z) maps (rows x cols each) and
+    per-scanline camera-from-world poses R_gt (rows x 3 x 3), t_gt (rows x 3).  The scanline poses follow
+    the small-motion model of RsFrame::setRelativePose with the true motion; (world_R, world_t) places the
+    world frame away from scanline 0 so that relocatePose has something to do.  void_frac: fraction of
+    pixels without a world point (all-zero entries, as for background pixels of the renderer)."""
+    rows, cols = P["rows"], P["cols"]
+    fx, fy, cx, cy = [float(a) for a in P["K4"]]
+    v, w, k, gamma = P["v"], P["w"], P["k"], P["gamma"]
+    i = np.arange(rows, dtype=np.float64)
+    beta = (gamma * i / rows + 0.5 * k * (gamma * gamma * i * i) / (rows * rows)) * (2.0 / (2.0 + k))
+    skew = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]], dtype=np.float64)
+    R = np.eye(3)[None] + beta[:, None, None] * skew[None]
+    t = beta[:, None] * np.asarray(v, dtype=np.float64)[None]
+    if world_R is not None:
+        wt = np.zeros(3) if world_t is None else np.asarray(world_t, dtype=np.float64)
+        t = np.einsum("rij,j->ri", R, wt) + t
+        R = R @ np.asarray(world_R, dtype=np.float64)
+    Z = 1.0 / P["inv_depth"]
+    xn = (np.arange(cols) - cx) / fx
+    yn = (np.arange(rows) - cy) / fy
+    Xc = np.stack([Z * xn[None, :], Z * yn[:, None], Z], axis=-1)
+    Xw = np.einsum("rij,rcj->rci", np.linalg.inv(R), Xc - t[:, None, :])
+    if void_frac > 0:
+        hole = np.random.default_rng(seed).random((rows, cols)) < void_frac
+        Xw[hole] = 0.0
+    return dict(unproj=(np.ascontiguousarray(Xw[..., 0]), np.ascontiguousarray(Xw[..., 1]), np.ascontiguousarray(Xw[..., 2])),
+                R_gt=R, t_gt=t, depth=Z)
+
+
 def sample_list(n, H, seed=3):
     """H x 9 distinct point indices (replaces srand(time)/rand of minimal.cc:230-244)."""
     rng = np.random.default_rng(seed)

@@ -409,3 +409,60 @@ def test_refine_is_bit_reproducible(ctx, oracle, synth, const_acc):
             assert np.array_equal(r[0], runs[0][0]) and np.array_equal(r[1], runs[0][1]) and r[2] == runs[0][2]
             assert np.array_equal(r[3], runs[0][3])
             assert r[4]["final_cost"] == runs[0][4]["final_cost"] and r[4]["iterations"] == runs[0][4]["iterations"]
+
+
+# ---------------------------------------------------------------------------- reprojection error metric
+def _reproj_case(oracle, synth, rows=120, cols=160):
+    K4 = helpers.small_K(8)
+    P = synth.make_pair(rows, cols, K4, gamma=0.95, seed=31, k=0.3)
+    a = 0.02
+    Rg = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+    G = synth.ground_truth(P, world_R=Rg, world_t=(0.1, -0.05, 0.2), void_frac=0.01)
+    depth_cm = (G["depth"] * 1.3).flatten(order="F")                      # estimate with the usual scale ambiguity
+    R, t = oracle.set_relative_pose(P["v"] * 1.3, P["w"], P["k"], P["gamma"], rows)
+    _, coords = oracle.back_project(P["image"], depth_cm, K4, R, t, want_coords=True)
+    rng = np.random.default_rng(5)
+    bad = rng.random((rows, cols)) < 0.01                                 # gross outliers and non-finite estimates
+    coords[bad] *= -40.0
+    coords[rng.random((rows, cols)) < 0.002] = np.nan
+    return P, G, K4, depth_cm, coords
+
+
+@pytest.mark.parametrize("mem", ["host", "device"])
+def test_reprojection_error_matches_oracle(ctx, oracle, synth, capi, mem):
+    """Camera::meanReprojectionError / createErrorImage / getGroundtruthDepthMap / relocatePose."""
+    import torch
+    P, G, K4, depth_cm, coords = _reproj_case(oracle, synth)
+    ref = oracle.mean_reprojection_error(coords, *G["unproj"], G["R_gt"], G["t_gt"], depth_cm, K4, max_norm=2.0, want_image=True)
+    unproj = [u.flatten(order="F") for u in G["unproj"]]
+    to = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()) if mem == "device" else (lambda a: a)
+    host = (lambda a: a.cpu().numpy()) if mem == "device" else (lambda a: a)
+    got = ctx.reprojection_error(to(coords), [to(u) for u in unproj], G["R_gt"], G["t_gt"], to(depth_cm), K4, max_norm=2.0,
+                                 want_image=True, want_gt_depth=True)
+    assert got["num_outliers"] == ref["num_outliers"] and got["points_used"] == ref["points_used"]
+    assert abs(got["mean_scale"] - ref["mean_scale"]) <= 1e-12 * abs(ref["mean_scale"])
+    assert abs(got["mean_error"] - ref["mean_error"]) <= 1e-10 * abs(ref["mean_error"])
+    # 8-bit error image: identical up to pixels sitting on a rounding boundary of the (summation-order dependent) mean scale
+    assert (host(got["error_image"]) != ref["error_image"]).mean() < 1e-3
+    gd = oracle.groundtruth_depth_map(*G["unproj"], G["R_gt"], G["t_gt"])
+    assert np.array_equal(host(got["gt_depth_map"]).reshape(gd.shape[1], gd.shape[0]).T, gd)
+    Rr, tr = capi.relocate_pose(G["R_gt"], G["t_gt"])
+    Ro, to_ = oracle.relocate_pose(G["R_gt"], G["t_gt"])
+    assert np.array_equal(Rr, Ro) and np.array_equal(tr, to_)
+
+
+def test_reprojection_error_of_the_pipeline_output(ctx, oracle, synth):
+    """End of the reference's evaluation loop: refine + rectify, then the reprojection error of the
+    back-projected 3D points against the ground truth -- small for a noise-free pair."""
+    K4 = helpers.small_K(8)
+    c = helpers.make_case(oracle, synth, 120, 160, K4, k=0.0, const_acc=False, H=8, seed=33, noise=0.0, outliers=0.0)
+    R = c["ransac"]
+    out = ctx.refine_rectify(c["flow"], c["inliers3"], c["alpha_in"], c["alpha_k_in"], c["m"], R["v"], R["w"], R["k"], False, False,
+                             c["P"]["image"], c["K4"], c["gamma"])
+    Rrel, trel = ctx.set_relative_pose(out["v"], out["w"], out["k"], c["gamma"], c["rows"])
+    _, coords = ctx.backproject(c["P"]["image"], out["depth_map"], c["K4"], Rrel, trel, want_coords=True)
+    G = synth.ground_truth(c["P"])
+    got = ctx.reprojection_error(coords, [u.flatten(order="F") for u in G["unproj"]], G["R_gt"], G["t_gt"], out["depth_map"], c["K4"])
+    mean_depth = float(np.mean(G["depth"]))
+    assert got["points_used"] > 0.95 * c["rows"] * c["cols"]
+    assert got["mean_error"] < 0.02 * mean_depth, got
