@@ -217,6 +217,16 @@ RSDSFM_API int rsdsfm_reprojection_error(rsdsfm_ctx *ctx, int mem, const float *
                           double max_norm, double *mean_error, double *mean_scale, int *num_outliers,
                           int *points_used, uint8_t *error_image, double *gt_depth_map);
 
+/* ---- ground-truth flow between two synthetic RS frames ---------------------- */
+/* Camera::calculateTrueFlow (camera.cc:209-249) with RsFrame::calculateImageCoordinatesRsFrame
+ * (rsframe.cc:740-768): the world point of every pixel of frame 1 (unproj_*, rows*cols doubles in
+ * `layout`) is projected with every scanline pose of frame 2 (R2: rows x 9, t2: rows x 3, host) and
+ * the pose whose row is closest to the projected y is used.  flow: rows*cols*2 row-major (dx,dy),
+ * i.e. the cv::Mat_<Point2d> that rsdsfm_flatten consumes. */
+RSDSFM_API int rsdsfm_true_flow(rsdsfm_ctx *ctx, int mem, const double *unproj_x, const double *unproj_y,
+                          const double *unproj_z, const double *R2, const double *t2, int layout, int rows,
+                          int cols, const double *K4, double *flow);
+
 /* ---- fused driver of the timed region "refine + rectify" (main.cc:457-523) ---------------- */
 /* nonLinearRefinement -> sign fix -> depth raster -> setPose -> backProject(Gs) ->
  * interpolateCrackyImage(.,1) for one frame pair, without leaving the device.

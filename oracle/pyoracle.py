@@ -264,3 +264,16 @@ def mean_reprojection_error(coords3d, ux, uy, uz, R_gt, t_gt, depth_est_colmajor
     err = fn(co.ctypes.data_as(_fp), _d(a), _d(b), _d(c), _d(R), _d(t), _d(de), rows, cols, _d(K4), C.c_double(max_norm),
              C.byref(ms), C.byref(no), C.byref(pu), img.ctypes.data_as(_u8p) if want_image else None)
     return dict(mean_error=float(err), mean_scale=ms.value, num_outliers=no.value, points_used=pu.value, error_image=img)
+
+
+# ---- ground-truth flow between two RS frames
+def true_flow(ux, uy, uz, R2, t2, K4):
+    """Camera::calculateTrueFlow.  ux,uy,uz: (rows, cols) unprojection maps of frame 1; R2,t2: scanline
+    poses of frame 2.  Returns (rows, cols, 2)."""
+    rows, cols = ux.shape
+    f = lambda a: _f64(np.asarray(a, dtype=np.float64).flatten(order="F"))
+    R = _f64(R2).reshape(-1); t = _f64(t2).reshape(-1); K4 = _f64(K4)
+    out = np.empty(rows * cols * 2)
+    a, b, c = f(ux), f(uy), f(uz)
+    lib().orc_true_flow(_d(a), _d(b), _d(c), _d(R), _d(t), rows, cols, _d(K4), _d(out))
+    return out.reshape(rows, cols, 2)

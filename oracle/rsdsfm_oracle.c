@@ -1255,3 +1255,47 @@ ORC_API double orc_mean_reprojection_error(const float *coords3d_est, const doub
     free(gt_depth); free(R); free(t); free(truep); free(scales);
     return sum_error * 1.0 / inliers;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Camera::calculateTrueFlow                          camera.cc:209-249         */
+/*                RsFrame::calculateImageCoordinatesRsFrame          rsframe.cc:740-768        */
+/* ------------------------------------------------------------------------------------------ */
+/* ux,uy,uz: unprojection maps of frame 1 (COLUMN-major rows x cols).  R2,t2: the (relative)
+ * scanline poses of frame 2 (worldToCameraFrame's default argument, rsframe.h:239).  flow:
+ * rows*cols*2 row-major (dx,dy).  O(rows^2 cols): every scanline pose is tried per pixel.
+ * `best_row` is uninitialised in the reference when no displacement compares smaller than
+ * INFINITY (all NaN); it starts at 0 here. */
+ORC_API void orc_true_flow(const double *ux, const double *uy, const double *uz, const double *R2,
+                           const double *t2, int rows, int cols, const double *K4, double *flow)
+{
+    const double fx = K4[0], cx = K4[2], cy = K4[3];
+    for (int v = 0; v < rows; ++v)
+        for (int u = 0; u < cols; ++u) {
+            const size_t mi = (size_t)v + (size_t)u * rows;
+            const double W[3] = {ux[mi], uy[mi], uz[mi]};
+            double px = (double)u, py = (double)v;
+            if (sqrt(W[0] * W[0] + W[1] * W[1] + W[2] * W[2]) != 0) {
+                double min_diff = INFINITY, bx = 0, by = 0;
+                int best = 0;
+                for (int i = 0; i < rows; ++i) {
+                    const double *R = R2 + 9 * i, *t = t2 + 3 * i;
+                    const double Y = R[3] * W[0] + R[4] * W[1] + R[5] * W[2] + t[1] * 1.0;
+                    const double Z = R[6] * W[0] + R[7] * W[1] + R[8] * W[2] + t[2] * 1.0;
+                    const double qy = Y / Z * fx + cy;                       /* spaceToPlane: f_x for y too (Q12) */
+                    const double diff = fabs(qy - (double)i);
+                    if (diff < min_diff) { min_diff = diff; best = i; }
+                }
+                {
+                    const double *R = R2 + 9 * best, *t = t2 + 3 * best;
+                    const double X = R[0] * W[0] + R[1] * W[1] + R[2] * W[2] + t[0] * 1.0;
+                    const double Y = R[3] * W[0] + R[4] * W[1] + R[5] * W[2] + t[1] * 1.0;
+                    const double Z = R[6] * W[0] + R[7] * W[1] + R[8] * W[2] + t[2] * 1.0;
+                    bx = X / Z * fx + cx;
+                    by = Y / Z * fx + cy;
+                }
+                if (sqrt(bx * bx + by * by) != 0) { px = bx; py = by; }       /* camera.cc:236-238 */
+            }
+            flow[2 * ((size_t)v * cols + u)] = px - (double)u;
+            flow[2 * ((size_t)v * cols + u) + 1] = py - (double)v;
+        }
+}

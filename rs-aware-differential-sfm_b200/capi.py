@@ -21,7 +21,7 @@ EXPORTS = [
     "rsdsfm_ransac_score", "rsdsfm_ransac", "rsdsfm_gather_inliers", "rsdsfm_estimate_inverse_depths",
     "rsdsfm_refine", "rsdsfm_depth_glue", "rsdsfm_set_relative_pose", "rsdsfm_backproject", "rsdsfm_fill_cracks",
     "rsdsfm_refine_rectify", "rsdsfm_refine_rectify_sequence", "rsdsfm_pipeline_pair", "rsdsfm_pipeline_sequence",
-    "rsdsfm_relocate_pose", "rsdsfm_reprojection_error",
+    "rsdsfm_relocate_pose", "rsdsfm_reprojection_error", "rsdsfm_true_flow",
 ]
 
 
@@ -441,6 +441,23 @@ class Context:
                                                     _ptr(img), _ptr(gd)))
         return dict(mean_error=me.value, mean_scale=ms.value, num_outliers=no.value, points_used=pu.value, error_image=img,
                     gt_depth_map=gd)
+
+    # ---- SURVEY 8(f)-2
+    def true_flow(self, unproj, R2, t2, K4, rows, cols, layout=DEPTH_COLMAJOR):
+        """rsdsfm_true_flow.  unproj: (x, y, z) maps of frame 1 (rows*cols doubles in `layout`); R2, t2: scanline
+        poses of frame 2.  Returns the (rows, cols, 2) flow image (numpy or torch like the inputs)."""
+        ux, uy, uz = (_f64(a) for a in unproj)
+        R = np.ascontiguousarray(np.asarray(R2, dtype=np.float64).reshape(-1)); t = np.ascontiguousarray(np.asarray(t2, dtype=np.float64).reshape(-1))
+        assert R.size == 9 * rows and t.size == 3 * rows
+        K4 = _small(K4, 4)
+        if _is_torch(ux):
+            import torch
+            flow = torch.empty((rows, cols, 2), dtype=torch.float64, device=ux.device)
+        else:
+            flow = np.empty((rows, cols, 2))
+        self._ck(self.lib.rsdsfm_true_flow(self.h, _mem(ux, uy, uz), _ptr(ux), _ptr(uy), _ptr(uz), _ptr(R), _ptr(t), int(layout),
+                                           int(rows), int(cols), _ptr(K4), _ptr(flow)))
+        return flow
 
     # ---- a2..a15 in one call
     @staticmethod

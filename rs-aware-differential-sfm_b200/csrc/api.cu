@@ -483,4 +483,33 @@ int rsdsfm_reprojection_error(rsdsfm_ctx *ctx, int mem, const float *coords3d, c
     return RSDSFM_OK;
 }
 
+int rsdsfm_true_flow(rsdsfm_ctx *ctx, int mem, const double *unproj_x, const double *unproj_y, const double *unproj_z,
+                     const double *R2, const double *t2, int layout, int rows, int cols, const double *K4, double *flow)
+{
+    RS_ENTER(ctx);
+    if (rows <= 0 || cols <= 0 || !unproj_x || !unproj_y || !unproj_z || !R2 || !t2 || !K4 || !flow)
+        return fail(ctx, RSDSFM_ERR_ARG, "rsdsfm_true_flow: bad argument");
+    const size_t tot = (size_t)rows * cols;
+    const void *d_x = nullptr, *d_y = nullptr, *d_z = nullptr;
+    void *d_f = nullptr;
+    RS_TRY(stage_in(ctx, mem, 0, unproj_x, sizeof(double) * tot, &d_x));
+    RS_TRY(stage_in(ctx, mem, 1, unproj_y, sizeof(double) * tot, &d_y));
+    RS_TRY(stage_in(ctx, mem, 2, unproj_z, sizeof(double) * tot, &d_z));
+    RS_TRY(stage_out_reserve(ctx, mem, 3, flow, sizeof(double) * 2 * tot, &d_f));
+    RS_TRY(ensure_pinned(ctx, sizeof(double) * 12 * (size_t)rows));
+    RS_TRY(ensure(ctx, ctx->pipe[15], sizeof(double) * 24 * (size_t)rows));
+    double *hp = (double *)ctx->pinned;
+    for (int i = 0; i < rows; ++i) {
+        for (int a = 0; a < 9; ++a) hp[12 * (size_t)i + a] = R2[9 * (size_t)i + a];
+        for (int a = 0; a < 3; ++a) hp[12 * (size_t)i + 9 + a] = t2[3 * (size_t)i + a];
+    }
+    RS_CUDA(ctx, cudaMemcpyAsync(ctx->pipe[15].p, hp, sizeof(double) * 12 * (size_t)rows, cudaMemcpyHostToDevice, ctx->stream));
+    RS_TRY(true_flow_device(ctx, (const double *)d_x, (const double *)d_y, (const double *)d_z, (const double *)ctx->pipe[15].p,
+                            layout, rows, cols, K4, (double *)d_f));
+    RS_TRY(stage_out(ctx, mem, flow, d_f, sizeof(double) * 2 * tot));
+    // R2, t2 were staged through the context's pinned buffer: the copy must have been consumed before it is reused
+    RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RSDSFM_OK;
+}
+
 }  // extern "C"

@@ -368,4 +368,67 @@ int reproj_device(rsdsfm_ctx *ctx, const float *est, const double *ux, const dou
     return RSDSFM_OK;
 }
 
+// ---------------------------------------------------------------- ground-truth flow
+// Camera::calculateTrueFlow (camera.cc:209-249) + RsFrame::calculateImageCoordinatesRsFrame
+// (rsframe.cc:740-768): for every pixel of frame 1 its world point is projected with EVERY scanline
+// pose of frame 2 and the pose whose row index is closest to the projected y wins (first minimum).
+// O(rows^2 cols) projections -- one thread per pixel, the poses stream through shared memory in
+// chunks that every thread of the CTA walks in the same order (broadcast reads).  FP64-issue bound:
+// one IEEE division per (pixel, scanline); plain IEEE sequence => bit-exact against the oracle.
+constexpr int kPoseChunk = 128;            // scanline poses per shared-memory chunk (12 doubles each)
+
+__global__ void __launch_bounds__(kThreads) k_true_flow(const double *__restrict__ ux, const double *__restrict__ uy,
+                                                        const double *__restrict__ uz, const double *__restrict__ poses2,
+                                                        ReprojParams P, double2 *__restrict__ flow)
+{
+    __shared__ double sp[kPoseChunk * 12];
+    const long long total = (long long)P.rows * P.cols;
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = p < total;
+    const int v = in ? (int)(p / P.cols) : 0, u = in ? (int)(p - (long long)v * P.cols) : 0;
+    const size_t mi = (P.layout == RSDSFM_DEPTH_COLMAJOR) ? ((size_t)v + (size_t)u * P.rows) : (size_t)(in ? p : 0);
+    const double W0 = in ? ux[mi] : 0.0, W1 = in ? uy[mi] : 0.0, W2 = in ? uz[mi] : 0.0;
+    const bool solid = in && sqrt(W0 * W0 + W1 * W1 + W2 * W2) != 0;                 // camera.cc:230
+    double min_diff = INFINITY;
+    int best = 0;
+    for (int c0 = 0; c0 < P.rows; c0 += kPoseChunk) {
+        const int nc = (P.rows - c0 < kPoseChunk) ? (P.rows - c0) : kPoseChunk;
+        __syncthreads();
+        for (int j = threadIdx.x; j < nc * 12; j += blockDim.x) sp[j] = poses2[(size_t)c0 * 12 + j];
+        __syncthreads();
+        if (solid)
+            for (int i = 0; i < nc; ++i) {
+                const double *R = sp + 12 * i;
+                const double Y = R[3] * W0 + R[4] * W1 + R[5] * W2 + R[10] * 1.0;
+                const double Z = R[6] * W0 + R[7] * W1 + R[8] * W2 + R[11] * 1.0;
+                const double qy = Y / Z * P.fx + P.cy;                               // spaceToPlane: f_x for y too (Q12)
+                const double diff = fabs(qy - (double)(c0 + i));
+                if (diff < min_diff) { min_diff = diff; best = c0 + i; }
+            }
+    }
+    if (!in) return;
+    double px = (double)u, py = (double)v;
+    if (solid) {
+        const double *R = poses2 + 12 * (size_t)best;
+        const double X = R[0] * W0 + R[1] * W1 + R[2] * W2 + R[9] * 1.0;
+        const double Y = R[3] * W0 + R[4] * W1 + R[5] * W2 + R[10] * 1.0;
+        const double Z = R[6] * W0 + R[7] * W1 + R[8] * W2 + R[11] * 1.0;
+        const double bx = X / Z * P.fx + P.cx, by = Y / Z * P.fx + P.cy;
+        if (sqrt(bx * bx + by * by) != 0) { px = bx; py = by; }                      // camera.cc:236-238
+    }
+    flow[p] = make_double2(px - (double)u, py - (double)v);
+}
+
+// poses2: device, rows x 12 doubles (R[9] row-major, t[3]) of frame 2's scanlines
+int true_flow_device(rsdsfm_ctx *ctx, const double *ux, const double *uy, const double *uz, const double *poses2, int layout,
+                     int rows, int cols, const double *K4, double *flow)
+{
+    const long long total = (long long)rows * cols;
+    ReprojParams P{K4[0], K4[1], K4[2], K4[3], 1.0, rows, cols, layout};
+    k_true_flow<<<(unsigned)((total + kThreads - 1) / kThreads), kThreads, 0, ctx->stream>>>(ux, uy, uz, poses2, P, (double2 *)flow);
+    ctx->launches++;
+    RS_CUDA(ctx, cudaGetLastError());
+    return RSDSFM_OK;
+}
+
 }  // namespace rsdsfm

@@ -59,5 +59,8 @@ int fill_cracks_device(rsdsfm_ctx *, const uint8_t *in, int rows, int cols, unsi
 int reproj_device(rsdsfm_ctx *, const float *est, const double *ux, const double *uy, const double *uz, const double *poses24,
                   const double *depth_est, int layout, int rows, int cols, const double *K4, double max_norm, float *truep,
                   uint8_t *error_image, double *gt_depth, double *sums5);
+// calculateTrueFlow (camera.cc:209-249); poses2 = frame 2's scanlines, rows x 12 (R[9], t[3])
+int true_flow_device(rsdsfm_ctx *, const double *ux, const double *uy, const double *uz, const double *poses2, int layout,
+                     int rows, int cols, const double *K4, double *flow);
 
 }  // namespace rsdsfm

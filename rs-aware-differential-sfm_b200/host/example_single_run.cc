@@ -105,6 +105,23 @@ int main()
         }
     }
     camera.setUnprojectionMaps(1, ux, uy, uz);
+    // ground-truth flow towards frame 2 (camera.cc:209-249): frame 2 is read out one frame period later
+    for (int j = 0; j < rows; ++j) {
+        const double beta = 1.0 + gamma * j / rows;
+        Eigen::Matrix3d Rj;
+        Rj(0, 0) = 1; Rj(0, 1) = -beta * w_true(2); Rj(0, 2) = beta * w_true(1);
+        Rj(1, 0) = beta * w_true(2); Rj(1, 1) = 1; Rj(1, 2) = -beta * w_true(0);
+        Rj(2, 0) = -beta * w_true(1); Rj(2, 1) = beta * w_true(0); Rj(2, 2) = 1;
+        camera.setScanlinePose(2, j, Rj, v_true * beta);
+    }
+    cv::Mat_<cv::Point_<double>> true_flow = camera.calculateTrueFlow(1, 2);
+    double flow_dev = 0, flow_mag = 0;
+    for (int j = 0; j < rows; ++j)
+        for (int i = 0; i < cols; ++i) {
+            flow_dev += std::fabs(true_flow(j, i).x - flow_image(j, i).x) + std::fabs(true_flow(j, i).y - flow_image(j, i).y);
+            flow_mag += std::fabs(flow_image(j, i).x) + std::fabs(flow_image(j, i).y);
+        }
+    std::printf("ground-truth flow vs differential model: mean |difference| / mean |flow| = %.3e\n", flow_dev / flow_mag);
     const double mean_error = camera.meanReprojectionError(1);
     cv::Mat error_image = camera.createErrorImage(1, 1.0);
     Eigen::MatrixXd gt_depth = camera.getFrame(1).getGroundtruthDepthMap();

@@ -324,8 +324,30 @@ public:
     }
     void setScanlinePose(const int scanlineNr, const Eigen::Matrix3d &rotation, const Eigen::Vector3d &translation)
     {
+        // the fixture loaders initialise the absolute and the relative pose alike (rsframe.cc:505-540)
         scanlines_[(size_t)scanlineNr].setRotation(rotation);
         scanlines_[(size_t)scanlineNr].setTranslation(translation);
+        scanlines_[(size_t)scanlineNr].setRelativeRotation(rotation);
+        scanlines_[(size_t)scanlineNr].setRelativeTranslation(translation);
+    }
+    bool hasUnprojectionMaps() const { return unprojection_map_x_.rows() == rows_ && unprojection_map_x_.cols() == cols_ && rows_ > 0; }
+    // camera.cc:209-249 seen from frame 1: flow towards `frame2` (its relative scanline poses, rsframe.h:239)
+    cv::Mat_<cv::Point_<double>> trueFlowTo(const RsFrame &frame2)
+    {
+        std::vector<double> R((size_t)9 * rows_), t((size_t)3 * rows_);
+        for (int i = 0; i < rows_; ++i) {
+            const Eigen::Matrix3d &Ri = frame2.scanlines_[(size_t)i].getRelativeRotation();
+            const Eigen::Vector3d &ti = frame2.scanlines_[(size_t)i].getRelativeTranslation();
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[(size_t)9 * i + 3 * r + c] = Ri(r, c);
+            for (int a = 0; a < 3; ++a) t[(size_t)3 * i + a] = ti(a);
+        }
+        const double K4[4] = {f_x_, f_y_, c_x_, c_y_};
+        cv::Mat_<cv::Point_<double>> flow(rows_, cols_);
+        rsdsfm_host::check(rsdsfm_true_flow(rsdsfm_host::context(), RSDSFM_HOST, unprojection_map_x_.data(), unprojection_map_y_.data(),
+                                            unprojection_map_z_.data(), R.data(), t.data(), RSDSFM_DEPTH_COLMAJOR, rows_, cols_, K4,
+                                            reinterpret_cast<double *>(flow.data)),
+                           "calculateTrueFlow");
+        return flow;
     }
     // rsframe.cc:416-436
     Eigen::MatrixXd getGroundtruthDepthMap()
@@ -445,7 +467,13 @@ public:
     // of this path (both sides consume a cached flow field), so the flow is attached instead.
     void setCachedFlow(const cv::Mat_<cv::Point_<double>> &flow) { cached_flow_ = flow; }
     cv::Mat_<cv::Point_<double>> calculateDeepFlow(const int, const int) { return cached_flow_; }
-    cv::Mat_<cv::Point_<double>> calculateTrueFlow(const int, const int) { return cached_flow_; }
+    // camera.cc:209-249: from the attached ground truth when there is one, else the cached field
+    cv::Mat_<cv::Point_<double>> calculateTrueFlow(const int frameNr1, const int frameNr2)
+    {
+        RsFrame &f1 = frames_[(size_t)frameNr1 - 1];
+        if (!f1.hasUnprojectionMaps()) return cached_flow_;
+        return f1.trueFlowTo(frames_[(size_t)frameNr2 - 1]);
+    }
 
     // ground-truth attachments (stand-ins for the CSV loaders, camera.cc:99-176)
     void setUnprojectionMaps(const int frameNr, const Eigen::MatrixXd &x, const Eigen::MatrixXd &y, const Eigen::MatrixXd &z)

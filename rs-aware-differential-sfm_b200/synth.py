@@ -125,18 +125,21 @@ def make_pair(rows=1080, cols=1920, intrinsics="galaxy_stabil", gamma=0.95, v=(0
                 rows=rows, cols=cols)
 
 
-def ground_truth(P, world_R=None, world_t=None, void_frac=0.0, seed=11):
+def ground_truth(P, world_R=None, world_t=None, void_frac=0.0, seed=11, frame=1):
     """Ground-truth fixtures of the RS frame of a synthetic pair, in the layout the reference loads from
     disk (rsframe.cc:222-378): per-pixel world points `unproj` = (X, Y, Z) maps (rows x cols each) and
     per-scanline camera-from-world poses R_gt (rows x 3 x 3), t_gt (rows x 3).  The scanline poses follow
     the small-motion model of RsFrame::setRelativePose with the true motion; (world_R, world_t) places the
     world frame away from scanline 0 so that relocatePose has something to do.  void_frac: fraction of
-    pixels without a world point (all-zero entries, as for background pixels of the renderer)."""
+    pixels without a world point (all-zero entries, as for background pixels of the renderer).
+    frame=2: the poses of the second frame's scanlines (read-out starts one frame period later); its
+    `unproj`/`depth` entries still describe frame 1 and are not meaningful."""
     rows, cols = P["rows"], P["cols"]
     fx, fy, cx, cy = [float(a) for a in P["K4"]]
     v, w, k, gamma = P["v"], P["w"], P["k"], P["gamma"]
     i = np.arange(rows, dtype=np.float64)
-    beta = (gamma * i / rows + 0.5 * k * (gamma * gamma * i * i) / (rows * rows)) * (2.0 / (2.0 + k))
+    tau = (frame - 1) + gamma * i / rows                      # time in frame periods since the first scanline
+    beta = (tau + 0.5 * k * tau * tau) * (2.0 / (2.0 + k))
     skew = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]], dtype=np.float64)
     R = np.eye(3)[None] + beta[:, None, None] * skew[None]
     t = beta[:, None] * np.asarray(v, dtype=np.float64)[None]

@@ -466,3 +466,30 @@ def test_reprojection_error_of_the_pipeline_output(ctx, oracle, synth):
     mean_depth = float(np.mean(G["depth"]))
     assert got["points_used"] > 0.95 * c["rows"] * c["cols"]
     assert got["mean_error"] < 0.02 * mean_depth, got
+
+
+# ---------------------------------------------------------------------------- ground-truth flow
+@pytest.mark.parametrize("mem", ["host", "device"])
+def test_true_flow_bit_exact(ctx, oracle, synth, mem):
+    """Camera::calculateTrueFlow: every scanline pose of frame 2 tried per pixel, first minimum wins."""
+    import torch
+    rows, cols = 96, 128
+    K4 = helpers.small_K(12)
+    P = synth.make_pair(rows, cols, K4, gamma=0.95, seed=41, k=0.4)
+    a = -0.015
+    Rg = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    G1 = synth.ground_truth(P, world_R=Rg, world_t=(0.05, 0.02, -0.1), void_frac=0.02)
+    G2 = synth.ground_truth(P, world_R=Rg, world_t=(0.05, 0.02, -0.1), frame=2)
+    ref = oracle.true_flow(*G1["unproj"], G2["R_gt"], G2["t_gt"], K4)
+    unproj = [u.flatten(order="F") for u in G1["unproj"]]
+    if mem == "device":
+        unproj = [torch.from_numpy(u).cuda() for u in unproj]
+    got = ctx.true_flow(unproj, G2["R_gt"], G2["t_gt"], K4, rows, cols)
+    got = got.cpu().numpy() if mem == "device" else got
+    assert np.array_equal(got, ref)
+    void = (G1["unproj"][0] == 0) & (G1["unproj"][1] == 0) & (G1["unproj"][2] == 0)
+    assert void.any() and np.all(got[void] == 0)
+    # sanity: close to the analytic differential flow the pair was generated with (first-order model)
+    solid = ~void
+    err = np.abs(got[solid] - P["flow_img"][solid])
+    assert np.median(err) < 0.15 * np.median(np.abs(P["flow_img"][solid])) + 0.05
