@@ -170,8 +170,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL's version banner goes to stdout by default; stdout carries the one JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import __graft_entry__ as ge
     if rank == 0:
@@ -330,7 +328,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(pairs[0], threads=1, budget_s=args.cpu_budget)
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -391,7 +389,27 @@ def run_reference(args):
             "config": {"workload": WORKLOAD, "rows": ROWS, "cols": COLS, "inliers_per_pair": p["m"]},
             "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": vals[-1]["sample"]},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: everything else that writes to fd 1 (NCCL's version
+    banner, library chatter) is sent to stderr; emit() writes to the saved descriptor."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -411,6 +429,7 @@ def main():
         WORKLOAD = WORKLOAD.replace("constant-acceleration trajectory k=0.5", "constant-velocity trajectory k=0").replace(
             "refine (const-acc, 7 motion parameters", "refine (const-vel, 6 motion parameters")
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
