@@ -35,15 +35,17 @@ static int queue_step(rsdsfm_ctx *ctx, const StepArgs &a, const double *v, const
     double *dR = (double *)ctx->poses.p, *dt = dR + 9 * (size_t)a.rows;
     // nonLinearRefinement (main.cc:457): the refined motion stays in the solver's device control
     // block and feeds the pose kernel directly
-    RS_TRY(refine_async(ctx, a.flow, a.inliers3, a.alpha, a.alpha_k, a.m, v, w, k, a.const_acc, a.flow_index, nullptr, a.z));
+    // (the solve's epilogue also leaves the per-CTA sums of z the sign fix needs)
+    RS_TRY(ensure(ctx, ctx->sums, sizeof(double) * 3 * (size_t)ctx->num_sms));
+    double *zrows = (double *)ctx->sums.p;
+    RS_TRY(refine_async(ctx, a.flow, a.inliers3, a.alpha, a.alpha_k, a.m, v, w, k, a.const_acc, a.flow_index, nullptr, a.z, zrows));
     // sign fix + depth raster (main.cc:466-509)
-    RS_TRY(glue_device(ctx, a.z, 1, a.inliers3, 3, a.m, a.K4, a.rows, a.cols, INFINITY, a.layout, a.depth_map, nullptr, stats));
+    RS_TRY(glue_device(ctx, a.z, 1, a.inliers3, 3, a.m, a.K4, a.rows, a.cols, INFINITY, a.layout, a.depth_map, nullptr, stats,
+                       zrows, ctx->num_sms));
     // setPose (main.cc:516) -> per-scanline poses, with the sign-fixed v
     RS_TRY(poses_device(ctx, lm_motion_device(ctx), stats, a.gamma, a.rows, dR, dt));
     // backProject / backProjectGs (main.cc:518-522) + interpolateCrackyImage (main.cc:523)
-    RS_TRY(backproject_device(ctx, a.image, a.depth_map, a.layout, a.rows, a.cols, a.K4, dR, dt, a.gs_mode,
-                              (uint8_t *)ctx->tmp_img.p, nullptr));
-    RS_TRY(fill_cracks_device(ctx, (const uint8_t *)ctx->tmp_img.p, a.rows, a.cols, 1, a.rectified));
+    RS_TRY(backproject_fill_device(ctx, a.image, a.depth_map, a.layout, a.rows, a.cols, a.K4, dR, dt, a.gs_mode, a.rectified));
     return lm_collect_enqueue(ctx, stats);
 }
 
@@ -237,9 +239,7 @@ static int pipeline_device(rsdsfm_ctx *ctx, const rsdsfm_pipeline_params &P, con
         RS_CUDA(ctx, cudaMemcpyAsync(dmot, hm, sizeof(double) * 7, cudaMemcpyHostToDevice, ctx->stream));
         RS_TRY(glue_device(ctx, inl + 2, 3, inl, 3, m, P.K4, P.rows, P.cols, INFINITY, P.layout, d_dm, nullptr, stats));
         RS_TRY(poses_device(ctx, dmot, stats, P.gamma, P.rows, dR, dt));
-        RS_TRY(backproject_device(ctx, d_image, d_dm, P.layout, P.rows, P.cols, P.K4, dR, dt, P.gs_mode,
-                                  (uint8_t *)ctx->tmp_img.p, nullptr));
-        RS_TRY(fill_cracks_device(ctx, (const uint8_t *)ctx->tmp_img.p, P.rows, P.cols, 1, d_out));
+        RS_TRY(backproject_fill_device(ctx, d_image, d_dm, P.layout, P.rows, P.cols, P.K4, dR, dt, P.gs_mode, d_out));
         RS_CUDA(ctx, cudaMemcpyAsync(pinned_stats(ctx), stats, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
         RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (pinned_stats(ctx)[3] < 0) for (int j = 0; j < 3; ++j) v[j] *= -1.0;

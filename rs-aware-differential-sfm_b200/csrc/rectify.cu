@@ -57,17 +57,36 @@ __global__ void __launch_bounds__(kThreads) k_glue_reduce(const double *__restri
     block_reduce_store<1, 2>(s, mx, partials);
 }
 
-// stats (device, 8 doubles): [0] sum z, [1] max z, [2] max -z  ->  writes [3] sign (+1/-1),
-// [4] z_min, [5] z_max after the sign fix (z_min starts at z_min_init, z_max at 0 like the reference)
-__global__ void k_glue_stats(double *stats, int m, double z_min_init)
+// rows: nrows x {sum z, max z, max -z} (one row per CTA of the producing kernel).  Reduces them in a
+// fixed order (warp c = column c; lane l takes rows l, l+32, ...; shuffle tree) and derives
+// stats (device, 8 doubles): [0] sum z, [1] max z, [2] max -z, [3] sign (+1/-1), [4] z_min, [5] z_max
+// after the sign fix (z_min starts at z_min_init, z_max at 0 like the reference, main.cc:481-489).
+__global__ void __launch_bounds__(96) k_glue_stats(const double *__restrict__ rows, int nrows, double *stats, int m,
+                                                   double z_min_init)
 {
-    const double z_mean = stats[0] * 1.0 / m;
-    const double sign = (z_mean < 0) ? -1.0 : 1.0;
-    double zmax = sign > 0 ? stats[1] : stats[2];
-    double zmin = sign > 0 ? -stats[2] : -stats[1];
-    stats[3] = sign;
-    stats[4] = fmin(z_min_init, zmin);
-    stats[5] = fmax(0.0, zmax);
+    __shared__ double red[3];
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double v = (c == 0) ? 0.0 : -INFINITY;
+    for (int b = lane; b < nrows; b += 32) {
+        const double x = rows[(size_t)b * 3 + c];
+        v = (c == 0) ? v + x : fmax(v, x);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double y = __shfl_xor_sync(0xffffffffu, v, o);
+        v = (c == 0) ? v + y : fmax(v, y);
+    }
+    if (lane == 0) red[c] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double z_mean = red[0] * 1.0 / m;
+        const double sign = (z_mean < 0) ? -1.0 : 1.0;
+        const double zmax = sign > 0 ? red[1] : red[2];
+        const double zmin = sign > 0 ? -red[2] : -red[1];
+        stats[0] = red[0]; stats[1] = red[1]; stats[2] = red[2];
+        stats[3] = sign;
+        stats[4] = fmin(z_min_init, zmin);
+        stats[5] = fmax(0.0, zmax);
+    }
 }
 
 __device__ __forceinline__ bool to_int_trunc(double a, int &out)
@@ -222,19 +241,88 @@ __global__ void __launch_bounds__(kThreads) k_fill_cracks(const uint8_t *__restr
     }
 }
 
+// Fused a14 gather + a15 crack fill (offset 1) for the drivers that do not hand the cracky GS image
+// out: a CTA gathers a (kFH+2) x (kFW+2) tile of winning source colours into shared memory (one
+// halo pixel all round) and fills from there; every thread produces 4 consecutive pixels = 12
+// bytes, written as three 32-bit words when the row pitch allows it.
+constexpr int kFW = 128, kFH = 8;
+static_assert(kFW * kFH == 4 * kThreads, "4 pixels per thread");
+
+__global__ void __launch_bounds__(kThreads) k_gather_fill(const uint8_t *__restrict__ image,
+                                                          const unsigned int *__restrict__ winner, int rows, int cols,
+                                                          uint8_t *__restrict__ out)
+{
+    __shared__ uchar4 tile[kFH + 2][kFW + 2];
+    const int x0 = blockIdx.x * kFW, y0 = blockIdx.y * kFH;
+    for (int idx = threadIdx.x; idx < (kFH + 2) * (kFW + 2); idx += kThreads) {
+        const int ty = idx / (kFW + 2), tx = idx - ty * (kFW + 2);
+        const int y = y0 - 1 + ty, x = x0 - 1 + tx;
+        uchar4 px = make_uchar4(0, 0, 0, 0);
+        if (y >= 0 && y < rows && x >= 0 && x < cols) {
+            const unsigned int wv = winner[(size_t)y * cols + x];
+            if (wv) { const size_t q = (size_t)(wv - 1) * 3; px = make_uchar4(image[q], image[q + 1], image[q + 2], 0); }
+        }
+        tile[ty][tx] = px;
+    }
+    __syncthreads();
+    const int ly = threadIdx.x / (kFW / 4), lx = (threadIdx.x % (kFW / 4)) * 4;
+    const int y = y0 + ly;
+    if (y >= rows) return;
+    uint8_t o[12];
+    int nvalid = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x = x0 + lx + j;
+        const uchar4 c = tile[ly + 1][lx + j + 1];
+        uint8_t o0 = c.x, o1 = c.y, o2 = c.z;
+        const bool black = ((int)c.x * c.x + (int)c.y * c.y + (int)c.z * c.z) <= 225;      // cv::norm(Vec3b) <= 15
+        if (x < cols) nvalid = j + 1;
+        if (x < cols && y >= 1 && y < rows - 1 && x >= 1 && x < cols - 1 && black) {
+            const uchar4 nb[4] = {tile[ly][lx + j + 1], tile[ly + 2][lx + j + 1], tile[ly + 1][lx + j], tile[ly + 1][lx + j + 2]};
+            double s0 = 0, s1 = 0, s2 = 0;
+            unsigned count = 0;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+                if (((int)nb[a].x * nb[a].x + (int)nb[a].y * nb[a].y + (int)nb[a].z * nb[a].z) > 225) {
+                    s0 += nb[a].x; s1 += nb[a].y; s2 += nb[a].z; count++;
+                }
+            if (count > 0) {
+                const double f = 1 / (double)count;
+                o0 = saturate_u8(f * s0); o1 = saturate_u8(f * s1); o2 = saturate_u8(f * s2);
+            }
+        }
+        o[3 * j] = o0; o[3 * j + 1] = o1; o[3 * j + 2] = o2;
+    }
+    const size_t base = 3 * ((size_t)y * cols + x0 + lx);
+    if (nvalid == 4 && (base & 3) == 0) {
+        unsigned int *w = reinterpret_cast<unsigned int *>(out + base);
+        w[0] = o[0] | (o[1] << 8) | (o[2] << 16) | ((unsigned int)o[3] << 24);
+        w[1] = o[4] | (o[5] << 8) | (o[6] << 16) | ((unsigned int)o[7] << 24);
+        w[2] = o[8] | (o[9] << 8) | (o[10] << 16) | ((unsigned int)o[11] << 24);
+    } else {
+        for (int j = 0; j < 3 * nvalid; ++j) out[base + j] = o[j];
+    }
+}
+
 // ---------------------------------------------------------------- host-side launchers (device pointers)
+// zrows (nullable): nzrows x {sum z, max z, max -z} already produced by the kernel that wrote z (the LM
+// solve's epilogue); otherwise one pass over z computes them.
 int glue_device(rsdsfm_ctx *ctx, double *z, int zs, const double *xyz, int xs, int m, const double *K4, int rows,
-                int cols, double z_min_init, int layout, double *depth_map, uint8_t *depth_img, double *stats /*device, 8*/)
+                int cols, double z_min_init, int layout, double *depth_map, uint8_t *depth_img, double *stats /*device, 8*/,
+                const double *zrows, int nzrows)
 {
     const int grid = grid_for(ctx, m, 4);
     RS_TRY(ensure(ctx, ctx->rpart, sizeof(double) * 3 * (size_t)grid));
     RS_CUDA(ctx, cudaMemsetAsync(depth_map, 0, sizeof(double) * (size_t)rows * cols, ctx->stream));
     if (depth_img) RS_CUDA(ctx, cudaMemsetAsync(depth_img, 0, (size_t)rows * cols, ctx->stream));
     if (m > 0) {
-        k_glue_reduce<<<grid, kThreads, 0, ctx->stream>>>(z, zs, m, (double *)ctx->rpart.p);
-        ctx->launches++;
-        launch_final_reduce(ctx, (double *)ctx->rpart.p, grid, 1, 2, stats);
-        k_glue_stats<<<1, 1, 0, ctx->stream>>>(stats, m, z_min_init);
+        if (!zrows) {
+            k_glue_reduce<<<grid, kThreads, 0, ctx->stream>>>(z, zs, m, (double *)ctx->rpart.p);
+            ctx->launches++;
+            zrows = (const double *)ctx->rpart.p;
+            nzrows = grid;
+        }
+        k_glue_stats<<<1, 96, 0, ctx->stream>>>(zrows, nzrows, stats, m, z_min_init);
         ctx->launches++;
         k_glue_raster<<<grid, kThreads, 0, ctx->stream>>>(z, zs, xyz, xs, m, stats, K4[0], K4[1], K4[2], K4[3], rows,
                                                           cols, layout, depth_map, depth_img);
@@ -262,6 +350,22 @@ int backproject_device(rsdsfm_ctx *ctx, const uint8_t *image, const double *dept
     k_splat_vote<<<grid, kThreads, 0, ctx->stream>>>(image, depth, R, t, P, (unsigned int *)ctx->winner.p, coords3d);
     ctx->launches++;
     k_splat_gather<<<grid, kThreads, 0, ctx->stream>>>(image, (const unsigned int *)ctx->winner.p, total, gs_out);
+    ctx->launches++;
+    return RSDSFM_OK;
+}
+
+// a13/a14 + a15 with offset 1 in one go: vote, then gather + fill straight into `rectified`
+int backproject_fill_device(rsdsfm_ctx *ctx, const uint8_t *image, const double *depth, int layout, int rows, int cols,
+                            const double *K4, const double *R, const double *t, int gs_mode, uint8_t *rectified)
+{
+    const long long total = (long long)rows * cols;
+    RS_TRY(ensure(ctx, ctx->winner, sizeof(unsigned int) * (size_t)total));
+    RS_CUDA(ctx, cudaMemsetAsync(ctx->winner.p, 0, sizeof(unsigned int) * (size_t)total, ctx->stream));
+    SplatParams P{K4[0], K4[1], K4[2], K4[3], rows, cols, layout, gs_mode};
+    k_splat_vote<<<grid_for(ctx, total, 8), kThreads, 0, ctx->stream>>>(image, depth, R, t, P, (unsigned int *)ctx->winner.p, nullptr);
+    ctx->launches++;
+    const dim3 grid((unsigned)((cols + kFW - 1) / kFW), (unsigned)((rows + kFH - 1) / kFH));
+    k_gather_fill<<<grid, kThreads, 0, ctx->stream>>>(image, (const unsigned int *)ctx->winner.p, rows, cols, rectified);
     ctx->launches++;
     return RSDSFM_OK;
 }

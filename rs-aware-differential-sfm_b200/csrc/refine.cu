@@ -697,7 +697,7 @@ __device__ __forceinline__ bool sort_exceptions(const ExcEntry *list, int ne, un
 template <int NF>
 __global__ void __launch_bounds__(kThreads, 1)
 k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *partials, ExcEntry *exc, unsigned int exc_cap,
-                const double *z_in, int z_stride, double *out, int invert_out)
+                const double *z_in, int z_stride, double *out, int invert_out, double *zstats)
 {
     using A = Acc<NF>;
     constexpr int LD = kRowVals<NF>;
@@ -1043,12 +1043,18 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
     // start values (solver.cc Minimize): 1/z_in for a9 (double reciprocal, :213/:247), 1.0 for a8.
     const bool failed = (__ldcg(&sh->ctl.termination) == RSDSFM_FAILURE) || P.error;
     const double *dfin = P.which_x ? d1 : d0;
+    // zstats (nullable): per-CTA rows {sum z, max z, max -z} of what was written, for the sign fix
+    // and depth range of main.cc:466-489 -- saves the rectification stage a pass over z
+    double zs[1] = {0.0}, zm[2] = {-INFINITY, -INFINITY};
     for (int i = blockIdx.x * kThreads + tid; i < D.m; i += G * kThreads) {
         double dv;
         if (failed) dv = z_in ? 1.0 / z_in[(size_t)i * z_stride] : 1.0;
         else dv = dfin[i];
-        out[i] = invert_out ? 1.0 / dv : dv;
+        const double o = invert_out ? 1.0 / dv : dv;
+        out[i] = o;
+        zs[0] += o; zm[0] = fmax(zm[0], o); zm[1] = fmax(zm[1], -o);
     }
+    if (zstats) block_reduce_store<1, 2>(zs, zm, zstats);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1057,11 +1063,11 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
 template <int NF>
 static int launch_persistent(rsdsfm_ctx *ctx, RefineData D, double *d0, double *d1, LmShared *sh, double *partials,
                              ExcEntry *exc, unsigned int exc_cap, const double *z_in, int z_stride, double *out,
-                             int invert_out, int grid)
+                             int invert_out, double *zstats, int grid)
 {
     const size_t smem = sizeof(Stage) * (size_t)kStages;
     RS_CUDA(ctx, cudaFuncSetAttribute(k_lm_persistent<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    void *args[] = {&D, &d0, &d1, &sh, &partials, &exc, &exc_cap, &z_in, &z_stride, &out, &invert_out};
+    void *args[] = {&D, &d0, &d1, &sh, &partials, &exc, &exc_cap, &z_in, &z_stride, &out, &invert_out, &zstats};
     if (ctx->profile) cudaEventRecord(ctx->pe0[ctx->io_slot], ctx->stream);
     RS_CUDA(ctx, cudaLaunchCooperativeKernel((void *)k_lm_persistent<NF>, dim3(grid), dim3(kThreads), args, smem, ctx->stream));
     if (ctx->profile) cudaEventRecord(ctx->pe1[ctx->io_slot], ctx->stream);
@@ -1103,7 +1109,7 @@ __global__ void __launch_bounds__(256) k_lm_readback(const LmShared *sh, const d
 // (ctx->lm_shared) receives the result; lm_collect() reads it back.
 static int lm_solve_async(rsdsfm_ctx *ctx, const RefineData &D, double *d0, double *d1, int nf, const Motion &mot0,
                           const rsdsfm_lm_options &opt, const double *z_in, int z_stride, double *out, int invert_out,
-                          bool keep_input_flag)
+                          bool keep_input_flag, double *zstats = nullptr)
 {
     RS_TRY(ensure(ctx, ctx->lm_shared, sizeof(LmShared)));
     LmShared *sh = (LmShared *)ctx->lm_shared.p;
@@ -1135,9 +1141,9 @@ static int lm_solve_async(rsdsfm_ctx *ctx, const RefineData &D, double *d0, doub
     double *partials = (double *)ctx->partials.p;
     ExcEntry *exc = (ExcEntry *)ctx->exc.p;
     const unsigned int cap = (unsigned int)ctx->exc_cap;
-    if (nf == 0) return launch_persistent<0>(ctx, D, d0, d1, sh, partials, exc, cap, z_in, z_stride, out, invert_out, grid);
-    if (nf == 6) return launch_persistent<6>(ctx, D, d0, d1, sh, partials, exc, cap, z_in, z_stride, out, invert_out, grid);
-    return launch_persistent<7>(ctx, D, d0, d1, sh, partials, exc, cap, z_in, z_stride, out, invert_out, grid);
+    if (nf == 0) return launch_persistent<0>(ctx, D, d0, d1, sh, partials, exc, cap, z_in, z_stride, out, invert_out, zstats, grid);
+    if (nf == 6) return launch_persistent<6>(ctx, D, d0, d1, sh, partials, exc, cap, z_in, z_stride, out, invert_out, zstats, grid);
+    return launch_persistent<7>(ctx, D, d0, d1, sh, partials, exc, cap, z_in, z_stride, out, invert_out, zstats, grid);
 }
 
 // Queues the read-back of the control block (and, if given, of the 8 depth statistics) into the
@@ -1219,7 +1225,7 @@ int lm_reserve(rsdsfm_ctx *ctx, int m)
 // a9 on device pointers: queues gather + solve on the stream, no synchronisation.
 int refine_async(rsdsfm_ctx *ctx, const double *flow, const double *inliers3, const double *alpha,
                  const double *alpha_k, int m, const double *v, const double *w, double k, int const_acc,
-                 const int32_t *flow_index, const rsdsfm_lm_options *opts, double *z_out)
+                 const int32_t *flow_index, const rsdsfm_lm_options *opts, double *z_out, double *zstats)
 {
     rsdsfm_lm_options o;
     if (opts) o = *opts; else rsdsfm_lm_default_options(&o);
@@ -1235,7 +1241,7 @@ int refine_async(rsdsfm_ctx *ctx, const double *flow, const double *inliers3, co
     Motion mot;
     for (int j = 0; j < 3; ++j) { mot.v[j] = v[j]; mot.w[j] = w[j]; }
     mot.k = k;
-    return lm_solve_async(ctx, D, d0, d1, const_acc ? 7 : 6, mot, o, inliers3 + 2, 3, z_out, 1, true);
+    return lm_solve_async(ctx, D, d0, d1, const_acc ? 7 : 6, mot, o, inliers3 + 2, 3, z_out, 1, true, zstats);
 }
 
 // a9, synchronous: returns the refined motion and the summary on the host.
@@ -1248,7 +1254,7 @@ int refine_device(rsdsfm_ctx *ctx, const double *flow, const double *inliers3, c
     memset(summary, 0, sizeof *summary);
     if (m == 0) { summary->termination = RSDSFM_CONVERGENCE; summary->reason = RSDSFM_REASON_FUNCTION_TOL; return RSDSFM_OK; }
     for (int attempt = 0; attempt < 2; ++attempt) {
-        RS_TRY(refine_async(ctx, flow, inliers3, alpha, alpha_k, m, v, w, *k, const_acc, flow_index, opts, z_out));
+        RS_TRY(refine_async(ctx, flow, inliers3, alpha, alpha_k, m, v, w, *k, const_acc, flow_index, opts, z_out, nullptr));
         Motion mot;
         for (int j = 0; j < 3; ++j) { mot.v[j] = v[j]; mot.w[j] = w[j]; }
         mot.k = *k;

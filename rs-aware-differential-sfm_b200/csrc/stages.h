@@ -36,7 +36,7 @@ int refine_device(rsdsfm_ctx *, const double *flow, const double *inliers3, cons
                   const rsdsfm_lm_options *, double *z_out, rsdsfm_lm_summary *);                        // [synchronises]
 int refine_async(rsdsfm_ctx *, const double *flow, const double *inliers3, const double *alpha, const double *alpha_k,
                  int m, const double *v, const double *w, double k, int const_acc, const int32_t *flow_index,
-                 const rsdsfm_lm_options *, double *z_out);
+                 const rsdsfm_lm_options *, double *z_out, double *zstats_rows = nullptr);   // zstats_rows: num_sms x 3, see glue_device
 int lm_reserve(rsdsfm_ctx *, int m);                     // pre-sizes the solver's buffers for up to m residual blocks
 int lm_collect_enqueue(rsdsfm_ctx *, const double *stats_dev8);   // zero-copy read-back into the I/O slot's pinned area
 int lm_collect_finish(rsdsfm_ctx *, int nf, int m, Motion *mot, rsdsfm_lm_summary *, bool *overflow);
@@ -44,13 +44,17 @@ int lm_collect(rsdsfm_ctx *, int nf, int m, Motion *mot, rsdsfm_lm_summary *, bo
 const double *lm_motion_device(rsdsfm_ctx *);
 // a10/a11: sign fix + depth raster (main.cc:466-509)
 int glue_device(rsdsfm_ctx *, double *z, int zs, const double *xyz, int xs, int m, const double *K4, int rows, int cols,
-                double z_min_init, int layout, double *depth_map, uint8_t *depth_img, double *stats_dev8);
+                double z_min_init, int layout, double *depth_map, uint8_t *depth_img, double *stats_dev8,
+                const double *zrows = nullptr, int nzrows = 0);   // zrows: {sum z, max z, max -z} per producer CTA, if already known
 // a12: setRelativePose (rsframe.cc:771-800), motion and depth statistics read on the device
 int poses_device(rsdsfm_ctx *, const double *motion7_dev, const double *stats_dev, double gamma, int rows, double *R,
                  double *t);
 // a13/a14: backProject(Gs) (rsframe.cc:803-878)
 int backproject_device(rsdsfm_ctx *, const uint8_t *image, const double *depth, int layout, int rows, int cols,
                        const double *K4, const double *R, const double *t, int gs_mode, uint8_t *gs_out, float *coords3d);
+// a13/a14 + a15 (offset 1) fused: the cracky GS image only ever exists tile by tile in shared memory
+int backproject_fill_device(rsdsfm_ctx *, const uint8_t *image, const double *depth, int layout, int rows, int cols,
+                            const double *K4, const double *R, const double *t, int gs_mode, uint8_t *rectified);
 // a15: interpolateCrackyImage (camera.cc:753-774)
 int fill_cracks_device(rsdsfm_ctx *, const uint8_t *in, int rows, int cols, unsigned offset, uint8_t *out);
 

@@ -493,3 +493,23 @@ def test_true_flow_bit_exact(ctx, oracle, synth, mem):
     solid = ~void
     err = np.abs(got[solid] - P["flow_img"][solid])
     assert np.median(err) < 0.15 * np.median(np.abs(P["flow_img"][solid])) + 0.05
+
+
+@pytest.mark.parametrize("rows,cols", [(77, 123), (120, 160)])
+def test_fused_driver_equals_stagewise_rectification(ctx, oracle, synth, rows, cols):
+    """rsdsfm_refine_rectify takes shortcuts the per-stage entry points do not (depth statistics from
+    the solve's epilogue, gather + crack fill through a shared-memory tile): the rectified frame must
+    be bit-identical to setPose -> backProject -> interpolateCrackyImage run stage by stage, also
+    for image sizes that are not multiples of the tile."""
+    c = helpers.make_case(oracle, synth, rows, cols, helpers.small_K(10), k=0.0, const_acc=False, H=8, seed=51, outliers=0.1)
+    R = c["ransac"]
+    got = ctx.refine_rectify(c["flow"], c["inliers3"], c["alpha_in"], c["alpha_k_in"], c["m"], R["v"], R["w"], R["k"], False, False,
+                             c["P"]["image"], c["K4"], c["gamma"])
+    Rrel, trel = ctx.set_relative_pose(got["v"], got["w"], got["k"], c["gamma"], rows)
+    gs, _ = ctx.backproject(c["P"]["image"], got["depth_map"], c["K4"], Rrel, trel)
+    assert np.array_equal(ctx.fill_cracks(gs, 1), got["rectified"])
+    # and the depth raster equals the stage-wise glue on the refined depths
+    inl = c["inliers3"].copy(); inl[2::3] = got["z"] if inl.ndim == 1 else inl[2::3]
+    ref = oracle.refine_rectify(c["flow"], c["inliers3"], c["alpha_in"], c["alpha_k_in"], c["m"], R["v"], R["w"], R["k"], False, False,
+                                c["P"]["image"], c["K4"], c["gamma"])
+    assert np.array_equal(got["depth_map"] != 0, ref["depth_map"] != 0)
