@@ -30,7 +30,6 @@ static int queue_step(rsdsfm_ctx *ctx, const StepArgs &a, const double *v, const
     const size_t tot = (size_t)a.rows * a.cols;
     RS_TRY(ensure(ctx, ctx->misc, 256));
     RS_TRY(ensure(ctx, ctx->poses, sizeof(double) * 12 * (size_t)a.rows));
-    RS_TRY(ensure(ctx, ctx->tmp_img, tot * 3));
     double *stats = (double *)ctx->misc.p;
     double *dR = (double *)ctx->poses.p, *dt = dR + 9 * (size_t)a.rows;
     // nonLinearRefinement (main.cc:457): the refined motion stays in the solver's device control
@@ -230,8 +229,7 @@ static int pipeline_device(rsdsfm_ctx *ctx, const rsdsfm_pipeline_params &P, con
         // results = ransac_results (main.cc:455): row 2 of the inliers is used as it is
         RS_TRY(ensure(ctx, ctx->misc, 256));
         RS_TRY(ensure(ctx, ctx->poses, sizeof(double) * 12 * (size_t)P.rows));
-        RS_TRY(ensure(ctx, ctx->tmp_img, tot * 3));
-        double *stats = (double *)ctx->misc.p, *dmot = stats + 16;
+            double *stats = (double *)ctx->misc.p, *dmot = stats + 16;
         double *dR = (double *)ctx->poses.p, *dt = dR + 9 * (size_t)P.rows;
         double *hm = (double *)pinned_lm_init(ctx);
         for (int j = 0; j < 3; ++j) { hm[j] = v[j]; hm[3 + j] = w[j]; }

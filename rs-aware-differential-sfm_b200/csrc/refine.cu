@@ -3,29 +3,33 @@
 //   a9  nonlinear_refinement::nonLinearRefinement    (nonlinearRefinement.cc:183-252)  NF = 6 | 7
 //
 // ONE persistent cooperative kernel runs the whole solve: one CTA per SM stays resident and
-// loops over LM phases.  A phase is a pass over the residual blocks, streamed through a ring of
+// loops over LM phases.  A phase is a sweep over the residual blocks, streamed through a ring of
 // shared-memory stages by TMA bulk copies (cp.async.bulk + mbarrier complete_tx; one elected
-// thread issues, kStages tiles of 256 blocks in flight per SM), followed by a grid reduction
-// (registers -> shared-memory transpose -> warp shuffles -> one row per CTA -> the last CTA to
-// arrive sums the rows in a fixed order) and the O(1) controller (lm_controller.h: Ceres 1.14
-// trust-region semantics, 7x7 Cholesky) run by that last CTA, which then releases the grid.
-// No host round trip per iteration; the host launches once and reads one summary back.
+// thread issues, kStages tiles of 512 blocks in flight per SM), followed by a grid reduction
+// (shuffles -> one row per CTA -> the last CTA to arrive sums the rows in a fixed order) and the
+// O(1) controller (lm_controller.h: Ceres 1.14 trust-region semantics; warp-parallel bookkeeping
+// and register/shuffle Cholesky in ctl_on_eval / ctl_solve) run by that last CTA, which then
+// releases the grid.  No host round trip per iteration; the host launches once and the kernel's
+// last act is a summary the host reads back.
 //
-//   pass A (evaluation at x): residual + analytic Jacobian, closed-form 1x1 Schur elimination of
-//       the pixel's inverse depth, FP64 accumulation of the radius-independent factors G1, G2,
-//       h1, h2 (two sparse rank-1 updates per pixel), cost, |x|^2, max depth gradient.
-//   pass B (candidate): depth back-substitution, candidate point + cost, model cost change, |step|^2.
-//   A rejected step re-solves from the stored factors: it costs a pass B only.
+//   INIT phase (once): residual + analytic Jacobian at the start point, closed-form 1x1 Schur
+//       elimination of the pixel's inverse depth, FP64 accumulation of the radius-independent
+//       factors G1, G2, h1, h2 (two sparse rank-1 updates per pixel), cost, |x|^2, max gradient.
+//   FUSED phase (one per LM iteration): depth back-substitution of the candidate step at x
+//       (step_pair: candidate depth, model cost change, |step|^2) and, in the same sweep, the
+//       evaluation of the next iteration's sums AT THE CANDIDATE (eval_pair), speculatively.
+//   A rejected step re-solves from the stored factors at the smaller radius: no sweep at all.
 //
-// Data layout in HBM (structure of arrays, one entry per residual block, 16-byte aligned):
-//   xy[m] double2 (x, y) | uu[m] double2 (ux, uy; Q1 pairing applied once by the gather kernel)
-//   aa[m] double2 (alpha, alpha_k) | d[2][m] inverse depth ping-pong (x / candidate)
+// Data layout in HBM: tile-blocked structure of arrays, tile = 512 residual blocks:
+//   blk[tile] = { xy[512] (x, y) | uu[512] (ux, uy; Q1 pairing applied once by the gather kernel)
+//                 | aa[512] (alpha, alpha_k) } as double2, 24 KB contiguous = ONE bulk copy,
+//   d[2][tiles*512] inverse depth ping-pong (x / candidate), 4 KB per tile.
 // The Jacobi scale of a depth column (fixed at iteration 0 by Ceres) only matters for the
-// min/max_lm_diagonal clamp; it is bounded from below by a global quantity, so the passes test
-// e^Te against that bound and only the handful of pixels below it (focus of expansion) recompute
-// their scale from the start point.  Nothing per-pixel besides the arrays above is stored.
-// Traffic per residual block: pass A reads 56 B, pass B reads 56 B and writes 8 B
-// (algorithmic minimum, SURVEY.md 8d: 24 B / 32 B -- x, y, alpha, alpha_k are inputs of the C ABI).
+// min/max_lm_diagonal clamp; it is bounded from below by a global quantity, so the sweeps test
+// e^Te against that bound and the handful of pixels below it (focus of expansion) go to an
+// exception list that the controller CTA handles exactly (sorted by block index: reproducible).
+// Traffic per residual block: INIT reads 56 B, FUSED reads 56 B and writes 8 B (algorithmic
+// minimum, SURVEY.md 8d: 24 B / 56 B -- x, y, alpha, alpha_k are inputs of the C ABI).
 #include "common.cuh"
 #include "lm_controller.h"
 #include "rs_math.cuh"
