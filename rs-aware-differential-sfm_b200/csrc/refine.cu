@@ -130,6 +130,16 @@ __device__ __forceinline__ double fast_rcp(double x)
     r = fma(r, t, r);
     return r;
 }
+__device__ __forceinline__ double fast_rsqrt(double x)
+{   // MUFU.RSQ64H seed + two Newton steps (x > 0, normal)
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double hx = 0.5 * x;
+    r = r * fma(-hx * r, r, 1.5);
+    r = r * fma(-hx * r, r, 1.5);
+    return r;
+}
+
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p)
 {
     unsigned int v;
@@ -402,36 +412,32 @@ __device__ __forceinline__ void eval_pair(const Loaded (&L)[2], const double (&d
             fast = (E[p].ee >= P.ee_fast_min && E[p].ee <= P.max_diag);
         }
         slow[p] = (NF > 0) && valid[p] && !fast;
-        const double r = fast_rcp(E[p].ee);
+        const double r = fast_rsqrt(E[p].ee);                           // sqrt(mu) = 1/|e|
         mu[p] = (valid[p] && fast) ? r : 0.0;
     }
     if (NF > 0) {
-        // projector = (n n^T + e e^T/(radius+1)) / e^Te: two radius-independent rank-1 factors
+        // projector = (n n^T + e e^T/(radius+1)) / e^Te: two radius-independent rank-1 factors.  Each lane
+        // projects its pixel onto ITS direction (kept) and onto the partner's direction (handed over), both
+        // pre-scaled by 1/|e| so that the accumulation is a plain symmetric rank-1 update.
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
             const double dbeta = (NF == 7) ? c2 * fma(-E[p].ak, 0.5 * c2, L[p].a.y) : 0.0;
-            double fn[NF > 0 ? NF : 1], fe[NF > 0 ? NF : 1];
-            ft_times<NF>(E[p].beta, dbeta, d[p], E[p].x, E[p].y, E[p].xy, E[p].xx1, E[p].yy1, E[p].p0, E[p].p1, -E[p].e1, E[p].e0, fn);
-            ft_times<NF>(E[p].beta, dbeta, d[p], E[p].x, E[p].y, E[p].xy, E[p].xx1, E[p].yy1, E[p].p0, E[p].p1, E[p].e0, E[p].e1, fe);
-            const double rn = fma(-E[p].e1, E[p].r0, E[p].e0 * E[p].r1);    // n^T r, n = (-e1, e0)
-            const double re = fma(E[p].e0, E[p].r0, E[p].e1 * E[p].r1);
-            // keep my direction, hand the other one to the partner lane
-            double kv[NF > 0 ? NF : 1], pv[NF > 0 ? NF : 1];
+            const double n0 = -E[p].e1, n1 = E[p].e0;                    // n = (-e1, e0)
+            const double my0 = mu[p] * (e_role ? E[p].e0 : n0), my1 = mu[p] * (e_role ? E[p].e1 : n1);
+            const double ot0 = mu[p] * (e_role ? n0 : E[p].e0), ot1 = mu[p] * (e_role ? n1 : E[p].e1);
+            double kv[NF > 0 ? NF : 1], sv[NF > 0 ? NF : 1], pv[NF > 0 ? NF : 1];
+            ft_times<NF>(E[p].beta, dbeta, d[p], E[p].x, E[p].y, E[p].xy, E[p].xx1, E[p].yy1, E[p].p0, E[p].p1, my0, my1, kv);
+            ft_times<NF>(E[p].beta, dbeta, d[p], E[p].x, E[p].y, E[p].xy, E[p].xx1, E[p].yy1, E[p].p0, E[p].p1, ot0, ot1, sv);
+            const double ks = fma(my0, E[p].r0, my1 * E[p].r1);
+            const double ps = __shfl_xor_sync(0xffffffffu, fma(ot0, E[p].r0, ot1 * E[p].r1), 1);
 #pragma unroll
-            for (int j = 0; j < NF; ++j) {
-                kv[j] = e_role ? fe[j] : fn[j];
-                pv[j] = __shfl_xor_sync(0xffffffffu, e_role ? fn[j] : fe[j], 1);
-            }
-            const double ks = e_role ? re : rn;
-            const double ps = __shfl_xor_sync(0xffffffffu, e_role ? rn : re, 1);
-            const double pmu = __shfl_xor_sync(0xffffffffu, mu[p], 1);
+            for (int j = 0; j < NF; ++j) pv[j] = __shfl_xor_sync(0xffffffffu, sv[j], 1);
             int t = 0;
 #pragma unroll
             for (int j = 0; j < NF; ++j) {
-                const double g = mu[p] * kv[j], gp = pmu * pv[j];
-                acc[T::oH + j] = fma(g, ks, fma(gp, ps, acc[T::oH + j]));
+                acc[T::oH + j] = fma(kv[j], ks, fma(pv[j], ps, acc[T::oH + j]));
 #pragma unroll
-                for (int c = j; c < NF; ++c, ++t) acc[T::oK + t] = fma(g, kv[c], fma(gp, pv[c], acc[T::oK + t]));
+                for (int c = j; c < NF; ++c, ++t) acc[T::oK + t] = fma(kv[j], kv[c], fma(pv[j], pv[c], acc[T::oK + t]));
             }
         }
         if (slow[0] || slow[1]) {
@@ -558,16 +564,6 @@ __device__ __noinline__ int ctl_on_eval(LmController &c)
         nx = (int)c.begin_iteration();
     }
     return __shfl_sync(0xffffffffu, nx, 0);
-}
-
-__device__ __forceinline__ double fast_rsqrt(double x)
-{   // MUFU.RSQ64H seed + two Newton steps (x > 0, normal)
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    const double hx = 0.5 * x;
-    r = r * fma(-hx * r, r, 1.5);
-    r = r * fma(-hx * r, r, 1.5);
-    return r;
 }
 
 // LevenbergMarquardtStrategy::ComputeStep on the Schur-reduced system at the current radius.
