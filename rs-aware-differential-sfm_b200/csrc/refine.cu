@@ -803,7 +803,7 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
         cta_reduce_roles<NF, LD>(acc, part, row);
         if (t_begin) {
             const unsigned long long t2 = globaltimer();
-            sh->t_phase[run_init ? 4 : 7] += t_loop - t_begin; sh->t_phase[run_init ? 5 : 8] += t2 - t_loop;
+            atomicAdd(&sh->t_phase[run_init ? 4 : 7], t_loop - t_begin); atomicAdd(&sh->t_phase[run_init ? 5 : 8], t2 - t_loop);
         }
 
         // ---- grid barrier: the last CTA to arrive reduces the rows and runs the controller
@@ -820,6 +820,8 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
             // final reduce: warp w sums rows w, w+8, ...; lanes cover the columns (coalesced).  All loads of a
             // warp (up to 19 rows x 3 column groups) and the controller state are issued before anything is
             // combined -- one L2 round trip instead of one per batch; the sums run in a fixed order.
+            // (the exception-list counters too: thread 0 needs one of them in the middle of the controller logic)
+            const unsigned int ne_pre0 = (tid == 0) ? __ldcg(&sh->n_exc[0]) : 0u, ne_pre1 = (tid == 0) ? __ldcg(&sh->n_exc[1]) : 0u;
             int ctl_w[(sizeof(LmController) / sizeof(int) + kThreads - 1) / kThreads];
 #pragma unroll
             for (int q = 0; q < (int)(sizeof(ctl_w) / sizeof(int)); ++q) {
@@ -909,7 +911,7 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
                 // exception lists: on acceptance the speculative list becomes the current one
                 const int cur = run_init ? P.cur_list : (s_flag[3] ? (P.cur_list ^ 1) : P.cur_list);
                 s_flag[4] = cur;
-                const unsigned int ne = __ldcg(&sh->n_exc[cur]);
+                const unsigned int ne = cur ? ne_pre1 : ne_pre0;
                 s_flag[2] = (int)(ne < exc_cap ? ne : exc_cap);
                 sh->n_exc[cur ^ 1] = 0u;                       // the other list is rebuilt by the next pass
             }
@@ -992,7 +994,7 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
             // ---- publish the next phase
             if (tid == 0) {
                 const unsigned long long t_solved = globaltimer();
-                sh->t_phase[run_init ? 10 : 11] += t_solved - t_fin;     // controller logic only (after the row reduction)
+                atomicAdd(&sh->t_phase[run_init ? 10 : 11], t_solved - t_fin);   // controller logic only (after the row reduction)
                 const LmNext nx = (LmNext)s_flag[1];                     // LM_RUN_B (another fused pass) or LM_DONE
                 if (!run_init && s_flag[3]) sh->bc.which_x = P.which_x ^ 1;   // the candidate became x
                 Motion mo = P.base, ca = P.base;
@@ -1011,14 +1013,14 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
                 sh->bc.next = (int)nx;
                 if (t_begin) {
                     const unsigned long long dt = globaltimer() - t_begin;
-                    sh->t_phase[run_init ? 0 : 2] += dt; sh->t_phase[run_init ? 1 : 3] += 1ull;
+                    atomicAdd(&sh->t_phase[run_init ? 0 : 2], dt); atomicAdd(&sh->t_phase[run_init ? 1 : 3], 1ull);
                 }
             }
             for (int w = tid; w < (int)(sizeof(LmController) / sizeof(int)); w += kThreads)
                 reinterpret_cast<int *>(&sh->ctl)[w] = reinterpret_cast<const int *>(&s_ctl)[w];
             __syncthreads();
             if (tid == 0) {
-                sh->t_phase[run_init ? 6 : 9] += globaltimer() - t_ctl;
+                atomicAdd(&sh->t_phase[run_init ? 6 : 9], globaltimer() - t_ctl);
                 __threadfence();
                 st_release(&sh->generation, gen + 1u);
             }
@@ -1032,7 +1034,7 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
             }
             if (t_begin && !s_flag[0]) {
                 const unsigned long long dt = globaltimer() - t_begin;
-                sh->t_phase[run_init ? 0 : 2] += dt; sh->t_phase[run_init ? 1 : 3] += 1ull;
+                atomicAdd(&sh->t_phase[run_init ? 0 : 2], dt); atomicAdd(&sh->t_phase[run_init ? 1 : 3], 1ull);   // fire and forget
             }
         }
         __syncthreads();
