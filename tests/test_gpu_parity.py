@@ -513,3 +513,69 @@ def test_fused_driver_equals_stagewise_rectification(ctx, oracle, synth, rows, c
     ref = oracle.refine_rectify(c["flow"], c["inliers3"], c["alpha_in"], c["alpha_k_in"], c["m"], R["v"], R["w"], R["k"], False, False,
                                 c["P"]["image"], c["K4"], c["gamma"])
     assert np.array_equal(got["depth_map"] != 0, ref["depth_map"] != 0)
+
+
+# ---------------------------------------------------------------------------- BASELINE.json configs 1 and 3 as parity cases
+def test_config1_castle_substitute_full_pipeline(ctx, oracle, synth):
+    """BASELINE config 1 (SURVEY 8d substitute for the absent castle tarball): 600 x 600, fx = fy = 800,
+    cx = cy = 300, gamma = 0.8, 35 % background with flow exactly 0 (dropped by the 1e-10 test), 5 RANSAC
+    trials, tol 0.05, constant-velocity refinement, rectification -- the whole a2..a15 chain in one call
+    against the CPU restatement."""
+    rows = cols = 600
+    K4 = np.array([800.0, 800.0, 300.0, 300.0])
+    v = 0.03 * 100.0 * np.array([1.0, 1.0, 0.0]) / np.sqrt(2.0)
+    P = synth.make_pair(rows, cols, tuple(K4), gamma=0.8, v=tuple(v), w=(0.0, 0.0, 8.7266e-3), k=0.0, seed=61,
+                        noise_sigma_px=0.05, outlier_frac=0.02, zero_flow_frac=0.35, z_range=(60.0, 140.0))
+    n, coord, flow, cpx, fpx = oracle.flatten(P["flow_img"], K4, 0.8)
+    assert 0.5 * rows * cols < n < 0.9 * rows * cols          # the background blobs are really dropped
+    alpha = oracle.get_alpha(fpx, n, rows, 0.8)
+    alpha_k = oracle.get_alpha_k(cpx, fpx, n, rows, 0.8)
+    samples = synth.sample_list(n, 5, seed=62)
+    R = oracle.ransac(coord[:2 * n], flow[:2 * n], alpha, alpha_k, n, False, 0.05, samples=samples)
+    inl, a_in, ak_in = oracle.gather_inliers(coord, alpha, alpha_k, n, R["mask"], R["inv_depth"])
+    m = len(a_in)
+    ref = oracle.refine_rectify(flow[:2 * n], inl, a_in, ak_in, m, R["v"], R["w"], R["k"], False, False, P["image"], K4, 0.8)
+    got = ctx.pipeline_pair(P["flow_img"], P["image"], K4, 0.8, 0.05, False, samples=samples)
+    assert got["n"] == n and got["m"] == m and got["best_idx"] == R["best_idx"]          # RANSAC: bit-exact
+    assert np.array_equal(got["ransac_v"], R["v"]) and np.array_equal(got["ransac_w"], R["w"])
+    _motion_close(got["v"], ref["v"], "v")
+    _motion_close(got["w"], ref["w"], "w")
+    assert got["summary"]["iterations"] == ref["summary"]["iterations"]
+    nz = ref["depth_map"] != 0
+    assert np.array_equal(got["depth_map"] != 0, nz)
+    _depth_close(got["depth_map"][nz], ref["depth_map"][nz])
+    diff = np.abs(got["rectified"].astype(np.int32) - ref["rectified"].astype(np.int32)).max(axis=2)
+    assert (diff <= 1).mean() >= 0.999
+
+
+def test_config3_realworld_substitute(ctx, oracle, synth):
+    """BASELINE config 3 substitute: `galaxy` intrinsics, flow quantised to float32 like
+    DeepFlow's output, a smooth low-frequency flow error and outlier blobs.  Inlier sets must be
+    bit-exact for the same sample list; the refinement runs with the reference's flow pairing (m < n)."""
+    rows, cols = 270, 480
+    K4 = np.array(synth.INTRINSICS["galaxy"]) / 4.0
+    P = synth.make_pair(rows, cols, tuple(K4), gamma=0.95, seed=71, k=0.0, noise_sigma_px=0.0, outlier_frac=0.0, flow_f32=False)
+    yy, xx = np.meshgrid(np.arange(rows), np.arange(cols), indexing="ij")
+    smooth = 0.5 * np.stack([np.sin(2 * np.pi * xx / 64.0 + 0.3) * np.cos(2 * np.pi * yy / 64.0),
+                             np.cos(2 * np.pi * xx / 64.0) * np.sin(2 * np.pi * yy / 64.0 - 0.2)], axis=-1)
+    flow_img = P["flow_img"] + smooth
+    blobs = (np.sin(xx * 0.11 + 1.0) * np.cos(yy * 0.13 - 0.5)) > 0.97                 # ~3 % outlier blobs
+    rng = np.random.default_rng(72)
+    flow_img[blobs] = rng.uniform(-15, 15, size=(int(blobs.sum()), 2))
+    flow_img = flow_img.astype(np.float32).astype(np.float64)
+    n, coord, flow, cpx, fpx = oracle.flatten(flow_img, K4, 0.95)
+    alpha = oracle.get_alpha(fpx, n, rows, 0.95)
+    alpha_k = oracle.get_alpha_k(cpx, fpx, n, rows, 0.95)
+    samples = synth.sample_list(n, 12, seed=73)
+    R = oracle.ransac(coord[:2 * n], flow[:2 * n], alpha, alpha_k, n, False, 0.002, samples=samples)
+    G = ctx.ransac(coord[:2 * n], flow[:2 * n], alpha, alpha_k, n, False, samples, 0.002)
+    assert np.array_equal(G["counts"], R["counts"]) and G["best_idx"] == R["best_idx"]
+    assert np.array_equal(G["mask"], R["mask"]) and np.array_equal(G["inv_depth"], R["inv_depth"])
+    m = int(R["mask"].sum())
+    assert 0 < m < n                                                                   # Q1 pairing is active
+    inl, a_in, ak_in = oracle.gather_inliers(coord, alpha, alpha_k, n, R["mask"], R["inv_depth"])
+    ref = oracle.nonlinear_refinement(flow[:2 * n], inl, a_in, ak_in, m, R["v"], R["w"], R["k"], False)
+    got = ctx.refine(flow[:2 * m], inl, a_in, ak_in, m, R["v"], R["w"], R["k"], False)
+    _motion_close(got[0], ref[0], "v")
+    _motion_close(got[1], ref[1], "w")
+    _depth_close(got[3], ref[3])
