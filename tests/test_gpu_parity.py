@@ -579,3 +579,83 @@ def test_config3_realworld_substitute(ctx, oracle, synth):
     _motion_close(got[0], ref[0], "v")
     _motion_close(got[1], ref[1], "w")
     _depth_close(got[3], ref[3])
+
+
+# ---------------------------------------------------------------------------- BASELINE config 2 at full size (1920 x 1080)
+@pytest.fixture(scope="module")
+def full_hd(ctx, synth):
+    """The bench workload's pair, prepared on the GPU (flatten, alpha, RANSAC with 4 trials, gather)."""
+    rows, cols = 1080, 1920
+    P = synth.make_pair(rows, cols, "galaxy_stabil", gamma=0.95, seed=1000, k=0.0, noise_sigma_px=0.3, outlier_frac=0.05)
+    n, coord, flow, cpx, fpx, pidx = ctx.flatten(P["flow_img"], P["K4"], P["gamma"])
+    coord, flow, cpx, fpx = coord[:2 * n], flow[:2 * n], cpx[:2 * n], fpx[:2 * n]
+    alpha, alpha_k = ctx.alpha(fpx, cpx, n, rows, P["gamma"])
+    samples = synth.sample_list(n, 4, seed=1100)
+    R = ctx.ransac(coord, flow, alpha, alpha_k, n, False, samples, 0.05)
+    inl, a_in, ak_in, ix, m = ctx.gather_inliers(coord, alpha, alpha_k, n, R["mask"], R["inv_depth"])
+    return dict(P=P, n=n, coord=coord, flow=flow, alpha=alpha, alpha_k=alpha_k, R=R, inl=inl[:3 * m], a_in=a_in[:m], ak_in=ak_in[:m], m=m,
+                rows=rows, cols=cols)
+
+
+def test_full_hd_refine_rectify_against_oracle_and_reproducible(ctx, oracle, full_hd):
+    """One 1080p pair (2 073 600 residual blocks) against the CPU restatement (a few seconds of oracle
+    time), plus bitwise reproducibility of a second run."""
+    c = full_hd
+    R, P = c["R"], c["P"]
+    args = (c["flow"], c["inl"], c["a_in"], c["ak_in"], c["m"], R["v"], R["w"], R["k"], False, False, P["image"], P["K4"], P["gamma"])
+    got = ctx.refine_rectify(*args)
+    again = ctx.refine_rectify(*args)
+    for key in ("v", "w", "z", "depth_map", "rectified"):
+        assert np.array_equal(got[key], again[key]), key
+    ref = oracle.refine_rectify(*args)
+    _motion_close(got["v"], ref["v"], "v")
+    _motion_close(got["w"], ref["w"], "w")
+    assert got["summary"]["iterations"] == ref["summary"]["iterations"]
+    _depth_close(got["z"], ref["z"])
+    diff = np.abs(got["rectified"].astype(np.int32) - ref["rectified"].astype(np.int32)).max(axis=2)
+    assert (diff <= 1).mean() >= 0.999
+
+
+def test_full_hd_depth_lm_equals_closed_form_and_scoring_is_consistent(ctx, full_hd):
+    """Size-independent properties at 1080p: (i) the depth-only LM (a8) converges to the per-point
+    closed-form least-squares depth; (ii) the consensus mask of the RANSAC winner is exactly the set
+    err < tol recomputed in numpy from the winner's depths with the reference's operation order."""
+    c = full_hd
+    R = c["R"]
+    n = c["n"]
+    q = c["coord"].reshape(-1, 2); u = c["flow"].reshape(-1, 2)
+    x, y = q[:, 0], q[:, 1]
+    v, w, k = R["v"], R["w"], R["k"]
+    beta = (c["alpha"][:n] + k * c["alpha_k"][:n]) * (2.0 / (2.0 + k))
+    av0 = 1.0 * v[0] + 0.0 * v[1] + (-x) * v[2]
+    av1 = 0.0 * v[0] + 1.0 * v[1] + (-y) * v[2]
+    bw0 = (-x * y) * w[0] + (1 + x * x) * w[1] + (-y) * w[2]
+    bw1 = (-(1 + y * y)) * w[0] + (x * y) * w[1] + x * w[2]
+    # (ii) scoring loop, minimal.cc:255-275
+    d = R["inv_depth"][:n]
+    ue0 = beta * (av0 * d + bw0); ue1 = beta * (av1 * d + bw1)
+    dx = ue0 - u[:, 0]; dy = ue1 - u[:, 1]
+    err = np.sqrt(dx * dx + dy * dy)
+    assert np.array_equal(err < 0.05, R["mask"][:n].astype(bool))
+    assert int((err < 0.05).sum()) == int(R["counts"][R["best_idx"]])
+    # (i) closed form: d* = e.(u - beta B w) / (e.e), e = beta A v
+    e0, e1 = beta * av0, beta * av1
+    dstar = (e0 * (u[:, 0] - beta * bw0) + e1 * (u[:, 1] - beta * bw1)) / (e0 * e0 + e1 * e1)
+    got = ctx.estimate_inverse_depths(c["coord"], c["flow"], n, v, w, k, c["alpha"][:n], c["alpha_k"][:n])
+    dd = got[0] if isinstance(got, tuple) else got["inv_depth"]
+    rel = np.abs(dd[:n] - dstar) / np.maximum(np.abs(dstar), 1e-12)
+    assert np.median(rel) < 1e-6 and np.percentile(rel, 99) < 1e-3
+
+
+def test_full_hd_rectification_is_identity_for_a_static_camera(ctx, full_hd):
+    """v = w = 0: every scanline pose is the identity, so backProject maps each pixel onto itself and
+    the crack fill has nothing to do except at the source's own dark / void pixels."""
+    c = full_hd
+    P = c["P"]
+    rows, cols = c["rows"], c["cols"]
+    Rm, tm = ctx.set_relative_pose(np.zeros(3), np.zeros(3), 0.0, P["gamma"], rows)
+    depth = np.full(rows * cols, 5.0)
+    K4 = np.array([1800.0, 1800.0, 960.0, 540.0])          # fx == fy: spaceToPlane scales y with f_x (Q12)
+    gs, _ = ctx.backproject(P["image"], depth, K4, Rm, tm)
+    skipped = np.all(P["image"] == 1, axis=2)
+    assert np.array_equal(gs[~skipped], P["image"][~skipped]) and np.all(gs[skipped] == 0)
