@@ -66,8 +66,6 @@ int rsdsfm_create(int device, void *cuda_stream, rsdsfm_ctx **out)
         if (e != cudaSuccess) { delete ctx; return fail(nullptr, RSDSFM_ERR_CUDA, "cudaStreamCreate", e); }
         ctx->owns_stream = true;
     }
-    cudaEventCreate(&ctx->ev0);
-    cudaEventCreate(&ctx->ev1);
     for (int j = 0; j < 2; ++j) { cudaEventCreate(&ctx->pe0[j]); cudaEventCreate(&ctx->pe1[j]); }
     e = cudaMallocHost(&ctx->pinned_io, 2 * kPinnedSlotBytes);
     if (e != cudaSuccess) { rsdsfm_destroy(ctx); return fail(nullptr, RSDSFM_ERR_NOMEM, "cudaMallocHost", e); }
@@ -92,14 +90,12 @@ void rsdsfm_destroy(rsdsfm_ctx *ctx)
     }
     if (ctx->pinned_io) cudaFreeHost(ctx->pinned_io);
     DevBuf *all[] = {&ctx->partials, &ctx->sums, &ctx->pix, &ctx->dA, &ctx->dB, &ctx->rdepth, &ctx->misc, &ctx->winner,
-                     &ctx->tmp_img, &ctx->depth_rm, &ctx->poses, &ctx->hyp, &ctx->rpart, &ctx->flags, &ctx->scan,
+                     &ctx->poses, &ctx->hyp, &ctx->rpart, &ctx->scan,
                      &ctx->lm_shared, &ctx->exc};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (auto &b : ctx->stage) if (b.p) cudaFree(b.p);
     for (auto &b : ctx->pipe) if (b.p) cudaFree(b.p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -31,13 +31,12 @@ struct rsdsfm_ctx {
     int num_sms = rsdsfm::kNumSMsB200;
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long long launches = 0;
     std::string err;
     // scratch
     std::vector<rsdsfm::DevBuf *> bufs;
-    rsdsfm::DevBuf partials, sums, pix, dA, dB, rdepth, misc, stage[16], winner, tmp_img, depth_rm, poses;
-    rsdsfm::DevBuf hyp, rpart, flags, scan, lm_shared, exc;
+    rsdsfm::DevBuf partials, sums, pix, dA, dB, rdepth, misc, stage[16], winner, poses;
+    rsdsfm::DevBuf hyp, rpart, scan, lm_shared, exc;
     rsdsfm::DevBuf pipe[16];  // intermediates of the fused a2-a15 driver (pipeline.cu)
     int exc_cap = 0;          // capacity (entries) of the clamped-pixel exception list
     void *pinned = nullptr;   // small pinned host buffer for reduced sums / scalars
