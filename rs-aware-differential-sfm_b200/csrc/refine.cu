@@ -1107,6 +1107,16 @@ __global__ void __launch_bounds__(256) k_lm_readback(const LmShared *sh, const d
     if (stats8 && threadIdx.x < 8) host_stats8[threadIdx.x] = stats8[threadIdx.x];
 }
 
+// Initial capacity (entries) of each clamped-pixel list; an overflow is detected by the kernel and the
+// solve is repeated with room for every residual block.  RSDSFM_EXC_CAP overrides the default so that
+// the tests can drive the overflow path with a handful of clamped pixels.
+static int min_exc_cap()
+{
+    const char *e = getenv("RSDSFM_EXC_CAP");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 4096;
+}
+
 // Queues one LM solve on the context's stream (no host synchronisation).  The control block
 // (ctx->lm_shared) receives the result; lm_collect() reads it back.
 static int lm_solve_async(rsdsfm_ctx *ctx, const RefineData &D, double *d0, double *d1, int nf, const Motion &mot0,
@@ -1118,7 +1128,7 @@ static int lm_solve_async(rsdsfm_ctx *ctx, const RefineData &D, double *d0, doub
     const int grid = ctx->num_sms;                      // one persistent CTA per SM
     const int nv = (nf == 0) ? Acc<0>::NV : (nf == 6 ? Acc<6>::NV : Acc<7>::NV);
     RS_TRY(ensure(ctx, ctx->partials, sizeof(double) * (size_t)grid * nv));
-    if (ctx->exc_cap < 4096) ctx->exc_cap = 4096;
+    if (ctx->exc_cap < min_exc_cap()) ctx->exc_cap = min_exc_cap();
     RS_TRY(ensure(ctx, ctx->exc, sizeof(ExcEntry) * 2 * (size_t)ctx->exc_cap));   // current + speculative list
     static_assert(sizeof(LmShared) <= 8192 - 256, "pinned slot layout (common.cuh)");
 
@@ -1220,7 +1230,7 @@ int lm_reserve(rsdsfm_ctx *ctx, int m)
 {
     RS_TRY(ensure_lm_buffers(ctx, (size_t)(m > 0 ? m : 1)));
     RS_TRY(ensure(ctx, ctx->partials, sizeof(double) * (size_t)ctx->num_sms * Acc<7>::NV));
-    if (ctx->exc_cap < 4096) ctx->exc_cap = 4096;
+    if (ctx->exc_cap < min_exc_cap()) ctx->exc_cap = min_exc_cap();
     return ensure(ctx, ctx->exc, sizeof(ExcEntry) * 2 * (size_t)ctx->exc_cap);
 }
 

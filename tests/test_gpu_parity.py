@@ -659,3 +659,41 @@ def test_full_hd_rectification_is_identity_for_a_static_camera(ctx, full_hd):
     gs, _ = ctx.backproject(P["image"], depth, K4, Rm, tm)
     skipped = np.all(P["image"] == 1, axis=2)
     assert np.array_equal(gs[~skipped], P["image"][~skipped]) and np.all(gs[skipped] == 0)
+
+
+def test_clamped_pixel_list_overflow_is_retried(capi, ctx, oracle, synth, monkeypatch):
+    """More clamped pixels than the list holds: the kernel flags the overflow, the library enlarges the
+    list and repeats the solve -- in the synchronous call and in the middle of a pipelined sequence.
+    RSDSFM_EXC_CAP shrinks the initial capacity so that a handful of clamped pixels is enough."""
+    foe = helpers.make_case(oracle, synth, 240, 320, (1500.0, 1500.0, 160.0, 120.0), k=0.4, const_acc=True, H=10, seed=9,
+                            v=(0.02, 0.01, 0.30), w=(0.001, 0.002, -0.003), noise=0.05, outliers=0.0, tol=0.05)
+    plain = helpers.make_case(oracle, synth, 240, 320, helpers.small_K(6), k=0.4, const_acc=True, H=8, seed=12)
+
+    def pair(c):
+        R = c["ransac"]
+        return dict(flow=c["flow"][:2 * c["m"]], inliers3=c["inliers3"], alpha=c["alpha_in"], alpha_k=c["alpha_k_in"], image=c["P"]["image"],
+                    m=c["m"], v=R["v"], w=R["w"], k=R["k"])
+
+    def run(context):
+        R = foe["ransac"]
+        single = context.refine(foe["flow"], foe["inliers3"], foe["alpha_in"], foe["alpha_k_in"], foe["m"], R["v"], R["w"], R["k"], True)
+        # same K for the whole sequence (the FOE pair's): only the solve matters here
+        seq = context.refine_rectify_sequence([pair(plain), pair(foe), pair(plain), pair(foe)], True, False, foe["K4"], foe["gamma"])
+        return single, seq
+
+    roomy = capi.Context(0)
+    want_single, want_seq = run(roomy)
+    launches_roomy = roomy.launch_count()
+    roomy.close()
+    monkeypatch.setenv("RSDSFM_EXC_CAP", "2")
+    small = capi.Context(0)
+    got_single, got_seq = run(small)
+    launches_small = small.launch_count()
+    small.close()
+    assert launches_small > launches_roomy          # the overflowing solves really ran twice
+    assert np.array_equal(got_single[0], want_single[0]) and np.array_equal(got_single[1], want_single[1]) and got_single[2] == want_single[2]
+    assert np.array_equal(got_single[3], want_single[3]) and got_single[4]["iterations"] == want_single[4]["iterations"]
+    for g, w in zip(got_seq, want_seq):
+        assert g["status"] == 0
+        assert np.array_equal(g["v"], w["v"]) and np.array_equal(g["w"], w["w"]) and g["k"] == w["k"]
+        assert np.array_equal(g["z"], w["z"]) and np.array_equal(g["rectified"], w["rectified"])
