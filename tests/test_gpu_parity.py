@@ -697,3 +697,32 @@ def test_clamped_pixel_list_overflow_is_retried(capi, ctx, oracle, synth, monkey
         assert g["status"] == 0
         assert np.array_equal(g["v"], w["v"]) and np.array_equal(g["w"], w["w"]) and g["k"] == w["k"]
         assert np.array_equal(g["z"], w["z"]) and np.array_equal(g["rectified"], w["rectified"])
+
+
+# ---------------------------------------------------------------------------- committed golden vectors
+@pytest.mark.parametrize("tag,k,cacc,seed", [("cv", 0.0, False, 21), ("ca", 0.5, True, 22)])
+def test_cuda_path_against_committed_golden_vectors(ctx, synth, tag, k, cacc, seed):
+    """tests/golden/pipeline_small.npz (tests/golden/make_golden.py): the CUDA path alone, from the seeded
+    flow image to the rectified frame, against the committed vectors -- no oracle call in this test."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "pipeline_small.npz"))
+    rows, cols = 48, 64
+    K4 = np.array([80.0, 79.0, 32.0, 24.0])
+    P = synth.make_pair(rows, cols, tuple(K4), gamma=0.95, seed=seed, k=k, noise_sigma_px=0.1, outlier_frac=0.05)
+    n, coord, flow, cpx, fpx, pidx = ctx.flatten(P["flow_img"], K4, 0.95)
+    coord, flow, cpx, fpx = coord[:2 * n], flow[:2 * n], cpx[:2 * n], fpx[:2 * n]
+    alpha, alpha_k = ctx.alpha(fpx, cpx, n, rows, 0.95)
+    R = ctx.ransac_score(coord, flow, alpha, alpha_k, n, G[tag + "_hyps"], 0.01)
+    assert np.array_equal(R["counts"], G[tag + "_counts"]) and R["best_idx"] == int(G[tag + "_best"][0])
+    assert np.array_equal(R["mask"][:n], G[tag + "_mask"][:n]) and np.array_equal(R["inv_depth"][:n], G[tag + "_inv_depth"][:n])
+    inl, a_in, ak_in, ix, m = ctx.gather_inliers(coord, alpha, alpha_k, n, R["mask"], R["inv_depth"])
+    h = G[tag + "_hyps"][R["best_idx"]]                       # (w, v, k) of the winner
+    got = ctx.refine_rectify(flow, inl[:3 * m], a_in[:m], ak_in[:m], m, h[3:6], h[0:3], float(h[6]), cacc, False, P["image"], K4, 0.95)
+    want = G[tag + "_motion"]
+    _motion_close(got["v"], want[0:3], "v")
+    _motion_close(got["w"], want[3:6], "w")
+    assert abs(got["k"] - want[6]) <= MOTION_RTOL * max(1.0, abs(want[6]))
+    assert got["summary"]["iterations"] == int(G[tag + "_iterations"][0])
+    _depth_close(got["z"], G[tag + "_z"])
+    diff = np.abs(got["rectified"].astype(np.int32) - G[tag + "_rectified"].astype(np.int32)).max(axis=2)
+    assert (diff <= 1).mean() >= 0.999
