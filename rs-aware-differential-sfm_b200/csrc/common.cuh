@@ -152,8 +152,9 @@ inline int grid_for(const rsdsfm_ctx *ctx, long long n, int per_sm = 2)
 // Fixed shuffle tree + fixed warp order: bit-reproducible for a given launch geometry.
 template <int NS, int NM>
 __device__ __forceinline__ void block_reduce_store(double (&s)[NS > 0 ? NS : 1], double (&mx)[NM > 0 ? NM : 1],
-                                                   double *out)
+                                                   double *out, int row = -1)
 {
+    if (row < 0) row = (int)blockIdx.x;
     __shared__ double sh[kWarps][NS + NM];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -175,7 +176,7 @@ __device__ __forceinline__ void block_reduce_store(double (&s)[NS > 0 ? NS : 1],
         double v = sh[0][j];
         if (j < NS) { for (int w2 = 1; w2 < kWarps; ++w2) v += sh[w2][j]; }
         else        { for (int w2 = 1; w2 < kWarps; ++w2) v = fmax(v, sh[w2][j]); }
-        out[(size_t)blockIdx.x * (NS + NM) + j] = v;
+        out[(size_t)row * (NS + NM) + j] = v;
     }
 }
 

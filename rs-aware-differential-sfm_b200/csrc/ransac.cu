@@ -23,7 +23,7 @@
 
 namespace rsdsfm {
 
-// Hypotheses per CTA row (blockIdx.y) and CTAs per SM.  Measured at 1080p, H = 16 (tools/stage_times.py):
+// Hypotheses per CTA row (blockIdx.x) and CTAs per SM.  Measured at 1080p, H = 16 (tools/stage_times.py):
 // (4,1) 3.23 ms, (4,2) 2.90, (2,2) 2.53, (2,3) 2.45, (1,3) 2.31, (1,4) 2.20 ms -- the IEEE division /
 // square-root sequences are long dependent chains, so occupancy (64 registers, 32 warps/SM) beats
 // sharing one point load between several hypotheses; the point arrays (100 MB) stay L2-resident.
@@ -118,7 +118,9 @@ __global__ void __launch_bounds__(kThreads, OCC) k_ransac_pass(const double2 *__
                                                           double *__restrict__ partials)
 {
     __shared__ HypDev sh[HG];
-    const int h0 = blockIdx.y * HG;
+    // grid = (hypothesis rows, point chunks): consecutive CTAs score DIFFERENT hypotheses on the SAME points,
+    // so the point arrays are fetched from DRAM once per pass and served from L2 to the other hypotheses
+    const int h0 = blockIdx.x * HG, chunk = blockIdx.y, nchunks = gridDim.y;
     load_hyps<HG>(sh, hyps, h0, H);
     double s[HG * RS_NS], mx[HG * RM_NM];
 #pragma unroll
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, OCC) k_ransac_pass(const double2 *__
 #pragma unroll
     for (int j = 0; j < HG * RM_NM; ++j) mx[j] = 0.0;
 
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = chunk * blockDim.x + threadIdx.x; i < n; i += nchunks * blockDim.x) {
         const double2 qq = q[i], uu = u[i];
         const double al = alpha[i], alk = alpha_k[i];
 #pragma unroll
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, OCC) k_ransac_pass(const double2 *__
             mx[g * RM_NM + RM_BAD_CAND] = fmax(mx[g * RM_NM + RM_BAD_CAND], any_nonfinite4(c0, c1, 0.0, 0.0));
         }
     }
-    block_reduce_store<HG * RS_NS, HG * RM_NM>(s, mx, partials + (size_t)blockIdx.y * gridDim.x * (HG * (RS_NS + RM_NM)));
+    block_reduce_store<HG * RS_NS, HG * RM_NM>(s, mx, partials + (size_t)blockIdx.x * nchunks * (HG * (RS_NS + RM_NM)), chunk);
 }
 
 // Scoring loop minimal.cc:255-275 at the final depths: per hypothesis inlier count and error sum.
@@ -191,12 +193,12 @@ __global__ void __launch_bounds__(kThreads, OCC) k_ransac_score(const double2 *_
                                                            const double *__restrict__ depth, double *__restrict__ partials)
 {
     __shared__ HypDev sh[HG];
-    const int h0 = blockIdx.y * HG;
+    const int h0 = blockIdx.x * HG, chunk = blockIdx.y, nchunks = gridDim.y;
     load_hyps<HG>(sh, hyps, h0, H);
     double s[HG * 2], mx[1] = {0.0};
 #pragma unroll
     for (int j = 0; j < HG * 2; ++j) s[j] = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = chunk * blockDim.x + threadIdx.x; i < n; i += nchunks * blockDim.x) {
         const double2 qq = q[i], uu = u[i];
         const double al = alpha[i], alk = alpha_k[i];
 #pragma unroll
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, OCC) k_ransac_score(const double2 *_
             if (err < tol) { s[g * 2] += 1.0; s[g * 2 + 1] += err; }
         }
     }
-    block_reduce_store<HG * 2, 0>(s, mx, partials + (size_t)blockIdx.y * gridDim.x * (HG * 2));
+    block_reduce_store<HG * 2, 0>(s, mx, partials + (size_t)blockIdx.x * nchunks * (HG * 2), chunk);
 }
 
 __global__ void __launch_bounds__(kThreads) k_ransac_winner(const double2 *__restrict__ q, const double2 *__restrict__ u,
@@ -302,7 +304,7 @@ static int score_batch(rsdsfm_ctx *ctx, const double *q, const double *u, const 
         hh[h].failed = finite ? 0 : 1;
         n_active += hh[h].active;
     }
-    const dim3 grid(gx, gy);
+    const dim3 grid(gy, gx);          // x = hypothesis row (fastest), y = point chunk
     while (n_active > 0) {
         RS_CUDA(ctx, cudaMemcpyAsync(hd, hh, sizeof(HypDev) * (size_t)gy * hg, cudaMemcpyHostToDevice, ctx->stream));
         k_ransac_pass<kHG, kPassOcc><<<grid, kThreads, 0, ctx->stream>>>((const double2 *)q, (const double2 *)u, alpha, alpha_k, n, hd, Hb,
