@@ -726,3 +726,30 @@ def test_cuda_path_against_committed_golden_vectors(ctx, synth, tag, k, cacc, se
     _depth_close(got["z"], G[tag + "_z"])
     diff = np.abs(got["rectified"].astype(np.int32) - G[tag + "_rectified"].astype(np.int32)).max(axis=2)
     assert (diff <= 1).mean() >= 0.999
+
+
+def test_negative_mean_depth_is_sign_fixed_in_the_fused_driver(ctx, oracle, case_cv):
+    """The 9-point solver's null-vector sign is arbitrary, so (v, z) may come out negated; main.cc:466-478
+    flips both when the mean depth is negative.  The fused driver takes the depth statistics from the
+    solve's epilogue: force the negative branch and compare with the oracle and the stage-wise glue."""
+    c = case_cv
+    R = c["ransac"]
+    inl = c["inliers3"].copy()
+    inl[2::3] *= -1.0
+    args = (c["flow"], inl, c["alpha_in"], c["alpha_k_in"], c["m"], -R["v"], R["w"], R["k"], False, False, c["P"]["image"], c["K4"], c["gamma"])
+    ref = oracle.refine_rectify(*args)
+    got = ctx.refine_rectify(*args)
+    assert np.mean(got["z"]) > 0 and np.mean(ref["z"]) > 0
+    _motion_close(got["v"], ref["v"], "v")
+    _motion_close(got["w"], ref["w"], "w")
+    _depth_close(got["z"], ref["z"])
+    nz = ref["depth_map"] != 0
+    assert np.array_equal(got["depth_map"] != 0, nz)
+    _depth_close(got["depth_map"][nz], ref["depth_map"][nz])
+    # and it is the same raster the stage-wise glue produces from the refined depths
+    inl2 = inl.copy(); inl2[2::3] = got["z"]
+    g = ctx.depth_glue(inl2, c["m"], got["v"], c["K4"], c["rows"], c["cols"])
+    dm = g[2] if isinstance(g, tuple) else g["depth_map"]
+    assert np.array_equal(np.asarray(dm).reshape(-1), got["depth_map"].reshape(-1))
+    diff = np.abs(got["rectified"].astype(np.int32) - ref["rectified"].astype(np.int32)).max(axis=2)
+    assert (diff <= 1).mean() >= 0.999
