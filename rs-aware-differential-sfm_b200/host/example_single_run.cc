@@ -9,6 +9,8 @@
 // Prints the recovered motion; exits non-zero if w is not recovered (exact constant-velocity data).
 #include <cmath>
 #include <cstdio>
+#include <fstream>
+#include <iomanip>
 
 #include "camera.h"
 #include "errorMeasure.h"
@@ -128,9 +130,44 @@ int main()
     std::printf("mean reprojection error %.4e (ground-truth depth at the centre %.3f, error image %dx%d)\n", mean_error,
                 gt_depth(rows / 2, cols / 2), error_image.cols, error_image.rows);
 
+    // ---- the same ground truth through the reference's fixture files (A.csv, N_rs_t.csv, N_rs_r.csv,
+    // N_rs_unproject_{x,y,z}.csv; camera.cc:49-176, rsframe.cc:58-218, :444-553): written here, loaded back
+    double mean_error_csv = -1.0;
+    {
+        const std::string dir = "/tmp/rsdsfm_example_";
+        auto open = [&](const char *name) { std::ofstream f(dir + name); f << std::setprecision(17); return f; };
+        {
+            std::ofstream A = open("A.csv");
+            for (int r = 0; r < 3; ++r) A << K(r, 0) << "," << K(r, 1) << "," << K(r, 2) << "\n";
+            std::ofstream T = open("1_rs_t.csv"), Rf = open("1_rs_r.csv");
+            for (int j = 0; j < rows; ++j) {
+                const double beta = gamma * j / rows;
+                T << v_true(0) * beta << "," << v_true(1) * beta << "," << v_true(2) * beta << "\n";
+                const double Rj[9] = {1, -beta * w_true(2), beta * w_true(1), beta * w_true(2), 1, -beta * w_true(0),
+                                      -beta * w_true(1), beta * w_true(0), 1};
+                for (int a = 0; a < 9; ++a) Rf << Rj[a] << (a == 8 ? "\n" : ",");
+            }
+            std::ofstream X = open("1_rs_unproject_x.csv"), Y = open("1_rs_unproject_y.csv"), Z = open("1_rs_unproject_z.csv");
+            for (int j = 0; j < rows; ++j)
+                for (int i = 0; i < cols; ++i) {
+                    const char *sep = (i == cols - 1) ? "\n" : ",";
+                    X << ux(j, i) << sep; Y << uy(j, i) << sep; Z << uz(j, i) << sep;
+                }
+        }
+        Camera camera2;
+        const bool ok = camera2.loadIntrinsicsFromFile(dir + "A.csv", true);
+        camera2.addFrameSynthetic(rs1, rs1, depth_map, dir + "1_rs_t.csv", dir + "1_rs_r.csv", dir + "1_rs_unproject_x.csv",
+                                  dir + "1_rs_unproject_y.csv", dir + "1_rs_unproject_z.csv");
+        camera2.setGamma(gamma);
+        camera2.setPose(1, results.k, results.v, results.w);
+        camera2.backProject(1);
+        mean_error_csv = ok ? camera2.meanReprojectionError(1) : -1.0;
+        std::printf("mean reprojection error through the CSV fixtures %.4e\n", mean_error_csv);
+    }
+
     double werr = 0;
     for (int a = 0; a < 3; ++a) werr = std::fmax(werr, std::fabs(results.w(a) - w_true(a)));
     const double cosang = results.v.dot(v_true) / (results.v.norm() * v_true.norm());
     std::printf("max |w - w_true| = %.3e, angle(v, v_true) = %.3e rad\n", werr, std::acos(std::fmin(1.0, cosang)));
-    return (werr < 1e-6 && cosang > 1.0 - 1e-9 && filled > rows * cols * 9 / 10 && mean_error < 0.5) ? 0 : 1;
+    return (werr < 1e-6 && cosang > 1.0 - 1e-9 && filled > rows * cols * 9 / 10 && mean_error < 0.5 && mean_error_csv == mean_error) ? 0 : 1;
 }

@@ -12,7 +12,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <ctime>
+#include <fstream>
 #include <iostream>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -40,6 +42,37 @@ inline rsdsfm_ctx *context()
 inline void check(int rc, const char *what)
 {
     if (rc != RSDSFM_OK) throw std::runtime_error(std::string(what) + ": " + rsdsfm_last_error(context()));
+}
+
+// The reference's fixture files are plain CSV: one matrix row per line, comma separated,
+// fields converted with ::atof (camera.cc:137-160, rsframe.cc:444-553, :58-218).  Reads a whole file;
+// false when it cannot be opened or does not have `lines` lines of `fields` fields (0: not checked).
+inline bool readCsv(const std::string &path, long lines, int fields, std::vector<double> &values, const char *what, bool verbose = true)
+{
+    std::ifstream in(path);
+    if (!in) {
+        if (verbose) std::cout << path << " Is not a valid file path for the " << what << " file!" << std::endl;
+        return false;
+    }
+    values.clear();
+    std::string line, field;
+    long n_lines = 0;
+    bool fields_ok = true;
+    while (std::getline(in, line)) {
+        if (line.empty() && in.eof()) break;
+        std::stringstream ss(line);
+        int n = 0;
+        while (std::getline(ss, field, ',')) { values.push_back(::atof(field.c_str())); ++n; }
+        if (fields > 0 && n != fields) fields_ok = false;
+        ++n_lines;
+    }
+    if ((lines > 0 && n_lines != lines) || !fields_ok) {
+        if (verbose)
+            std::cout << "The number of lines: " << n_lines << " in the file: " << path << " does not conform with the expected " << lines
+                      << " lines of " << fields << " values!" << std::endl;
+        return false;
+    }
+    return true;
 }
 
 }  // namespace rsdsfm_host
@@ -330,6 +363,39 @@ public:
         scanlines_[(size_t)scanlineNr].setRelativeRotation(rotation);
         scanlines_[(size_t)scanlineNr].setRelativeTranslation(translation);
     }
+    // rsframe.cc:444-553: N_rs_t.csv (rows x 3) and N_rs_r.csv (rows x 9, row-major 3x3); both the absolute
+    // and the relative pose of every scanline are initialised.  Nothing is set unless both files fit.
+    bool setPoses(std::string csv_poses, std::string csv_orientation)
+    {
+        std::vector<double> t, R;
+        if (!rsdsfm_host::readCsv(csv_poses, rows_, 3, t, "poses") || !rsdsfm_host::readCsv(csv_orientation, rows_, 9, R, "orientation")) {
+            std::cout << "NO poses and NO orientations were set" << std::endl;
+            return false;
+        }
+        for (int i = 0; i < rows_; ++i) {
+            Eigen::Matrix3d Ri;
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Ri(r, c) = R[(size_t)9 * i + 3 * r + c];
+            setScanlinePose(i, Ri, Eigen::Vector3d(t[(size_t)3 * i], t[(size_t)3 * i + 1], t[(size_t)3 * i + 2]));
+        }
+        return true;
+    }
+    // rsframe.cc:58-218: N_rs_unproject_{x,y,z}.csv, rows lines of cols values each
+    bool setUnprojectionMapRs(const std::string csv_unprojection_x, const std::string csv_unprojection_y,
+                              const std::string csv_unprojection_z)
+    {
+        std::vector<double> v[3];
+        const std::string *paths[3] = {&csv_unprojection_x, &csv_unprojection_y, &csv_unprojection_z};
+        for (int a = 0; a < 3; ++a)
+            if (!rsdsfm_host::readCsv(*paths[a], rows_, cols_, v[a], "unprojection map")) {
+                std::cout << "NO unprojection map was set" << std::endl;
+                return false;
+            }
+        Eigen::MatrixXd m[3] = {Eigen::MatrixXd::Zero(rows_, cols_), Eigen::MatrixXd::Zero(rows_, cols_), Eigen::MatrixXd::Zero(rows_, cols_)};
+        for (int a = 0; a < 3; ++a)
+            for (int y = 0; y < rows_; ++y) for (int x = 0; x < cols_; ++x) m[a](y, x) = v[a][(size_t)y * cols_ + x];
+        setUnprojectionMaps(m[0], m[1], m[2]);
+        return true;
+    }
     bool hasUnprojectionMaps() const { return unprojection_map_x_.rows() == rows_ && unprojection_map_x_.cols() == cols_ && rows_ > 0; }
     // camera.cc:209-249 seen from frame 1: flow towards `frame2` (its relative scanline poses, rsframe.h:239)
     cv::Mat_<cv::Point_<double>> trueFlowTo(const RsFrame &frame2)
@@ -475,7 +541,32 @@ public:
         return f1.trueFlowTo(frames_[(size_t)frameNr2 - 1]);
     }
 
-    // ground-truth attachments (stand-ins for the CSV loaders, camera.cc:99-176)
+    // camera.cc:99-176: A.csv, the 3 x 3 intrinsic matrix
+    bool loadIntrinsicsFromFile(const std::string csv_intrinsic_matrix, bool show_messages)
+    {
+        std::vector<double> a;
+        if (!rsdsfm_host::readCsv(csv_intrinsic_matrix, 3, 3, a, "intrinsic", show_messages)) {
+            if (show_messages) std::cout << "No itrinsics were set" << std::endl;
+            return false;
+        }
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) K_(r, c) = a[(size_t)3 * r + c];
+        return true;
+    }
+    // camera.cc:49-70: a synthetic frame with its ground truth (the images are decoded by the caller)
+    void addFrameSynthetic(cv::Mat rs_image, cv::Mat gs_image, const Eigen::MatrixXd &depth_map, const std::string poses_csv,
+                           const std::string orientation_csv, const std::string csv_unproject_x, const std::string csv_unproject_y,
+                           const std::string csv_unproject_z)
+    {
+        RsFrame frame;
+        frame.setIntrinsics(K_);
+        frame.setImage(rs_image);
+        frame.setGsImage(gs_image);
+        frame.setDepthMap(depth_map);
+        frame.setPoses(poses_csv, orientation_csv);
+        frame.setUnprojectionMapRs(csv_unproject_x, csv_unproject_y, csv_unproject_z);
+        frames_.push_back(frame);
+    }
+    // ground-truth attachments without files
     void setUnprojectionMaps(const int frameNr, const Eigen::MatrixXd &x, const Eigen::MatrixXd &y, const Eigen::MatrixXd &z)
     {
         frames_[(size_t)frameNr - 1].setUnprojectionMaps(x, y, z);
