@@ -162,6 +162,7 @@ int main()
         camera2.setPose(1, results.k, results.v, results.w);
         camera2.backProject(1);
         mean_error_csv = ok ? camera2.meanReprojectionError(1) : -1.0;
+        camera2.createPointCloud(1, dir + "cloud.ply");                      // main.cc:552 (ASCII PLY, world frame)
         std::printf("mean reprojection error through the CSV fixtures %.4e\n", mean_error_csv);
     }
 

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <ctime>
 #include <fstream>
+#include <iomanip>
 #include <iostream>
 #include <sstream>
 #include <stdexcept>
@@ -541,6 +542,38 @@ public:
         return f1.trueFlowTo(frames_[(size_t)frameNr2 - 1]);
     }
 
+    // camera.cc:423-491: ASCII PLY of the back-projected 3D points (world frame) coloured by the RS image,
+    // row-major vertex order, 9 significant digits, BGR written as RGB
+    void createPointCloud(const int frameNr, const std::string fileName)
+    {
+        RsFrame frame = frames_[(size_t)frameNr - 1];
+        cv::Mat coordinates = frame.get3dCoordinates();
+        cv::Mat colors = frame.getRsImage();
+        const int rows = frame.getRows(), cols = frame.getCols();
+        if (coordinates.rows != rows || coordinates.cols != cols) throw std::runtime_error("createPointCloud: backProject has not run");
+        const float *pData = reinterpret_cast<const float *>(coordinates.data);
+        const unsigned char *pColor = colors.data;
+        const unsigned long number_iterations = 3ul * (unsigned long)rows * (unsigned long)cols;
+        std::ofstream outputfile(fileName);
+        outputfile << "ply" << std::endl
+                   << "format ascii 1.0" << std::endl
+                   << "comment PLY File created by RS aware SfM wrapper" << std::endl
+                   << "element vertex " << (unsigned long)rows * (unsigned long)cols << std::endl
+                   << "property float x" << std::endl
+                   << "property float y" << std::endl
+                   << "property float z" << std::endl
+                   << "property uchar red" << std::endl
+                   << "property uchar green" << std::endl
+                   << "property uchar blue" << std::endl
+                   << "end_header" << std::endl;
+        for (unsigned long i = 0; i < number_iterations; i += 3) {
+            for (unsigned int j = 0; j < 3; j++) outputfile << std::setprecision(9) << pData[i + j] << " ";
+            for (int j = 2; j >= 0; j--) outputfile << (unsigned short)pColor[i + j] << (j == 0 ? "" : " ");
+            outputfile << "\n";
+        }
+        outputfile.close();
+        std::cout << "Point cloud file " << fileName << " created." << std::endl;
+    }
     // camera.cc:99-176: A.csv, the 3 x 3 intrinsic matrix
     bool loadIntrinsicsFromFile(const std::string csv_intrinsic_matrix, bool show_messages)
     {
