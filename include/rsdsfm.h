@@ -258,9 +258,14 @@ typedef struct rsdsfm_pair_io {
  * them as a three-stage pipeline on one GPU: while pair i computes, pair i+1's inputs upload on a
  * copy stream and pair i-1's outputs download on another (mem = RSDSFM_HOST; use pinned host
  * memory for the copies to overlap).  With RSDSFM_DEVICE buffers only the result collection is
- * deferred, so that the GPU never waits for the host between pairs.  Results are identical to
- * n_pairs calls of rsdsfm_refine_rectify.  Returns the first failing pair's code (all pairs are
- * attempted; see rsdsfm_pair_io.status). */
+ * deferred, so that the GPU never waits for the host between pairs, and with two or more pairs the
+ * compute itself runs in two lanes (even / odd pairs), each LM solve on half of the SMs, so that one
+ * solve's grid barriers and serial controller steps are covered by the other solve's pixel sweeps
+ * (the host-buffer path is PCIe-bound and keeps one lane).
+ * Results are reproducible to the bit from call to call and agree with n_pairs calls of
+ * rsdsfm_refine_rectify to rounding (same arithmetic; the partial sums are reduced over half as many
+ * rows; a one-pair sequence is the single call).  Returns the first failing pair's code (all pairs
+ * are attempted; see rsdsfm_pair_io.status). */
 RSDSFM_API int rsdsfm_refine_rectify_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm_pair_io *pairs,
                           int const_acceleration, int gs_mode, int rows, int cols, const double *K4,
                           double gamma, int layout);

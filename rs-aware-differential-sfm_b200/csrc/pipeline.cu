@@ -40,7 +40,7 @@ static int queue_step(rsdsfm_ctx *ctx, const StepArgs &a, const double *v, const
     RS_TRY(refine_async(ctx, a.flow, a.inliers3, a.alpha, a.alpha_k, a.m, v, w, k, a.const_acc, a.flow_index, nullptr, a.z, zrows));
     // sign fix + depth raster (main.cc:466-509)
     RS_TRY(glue_device(ctx, a.z, 1, a.inliers3, 3, a.m, a.K4, a.rows, a.cols, INFINITY, a.layout, a.depth_map, nullptr, stats,
-                       zrows, ctx->num_sms));
+                       zrows, lm_grid_size(ctx)));
     // setPose (main.cc:516) -> per-scanline poses, with the sign-fixed v
     RS_TRY(poses_device(ctx, lm_motion_device(ctx), stats, a.gamma, a.rows, dR, dt));
     // backProject / backProjectGs (main.cc:518-522) + interpolateCrackyImage (main.cc:523)
@@ -289,31 +289,57 @@ int rsdsfm_refine_rectify_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm
     const int nf = const_acceleration ? 7 : 6;
     const bool host = (mem == RSDSFM_HOST);
     int first_err = RSDSFM_OK;
-    int max_m = 0;
+    int max_m = 0, n_ok = 0;
     for (int i = 0; i < n_pairs; ++i) {
         pairs[i].status = pair_args_ok(pairs[i]) ? RSDSFM_OK : RSDSFM_ERR_ARG;
         memset(&pairs[i].summary, 0, sizeof pairs[i].summary);
-        if (pairs[i].status == RSDSFM_OK && pairs[i].m > max_m) max_m = pairs[i].m;
-        else if (pairs[i].status != RSDSFM_OK && first_err == RSDSFM_OK)
+        if (pairs[i].status == RSDSFM_OK) { ++n_ok; if (pairs[i].m > max_m) max_m = pairs[i].m; }
+        else if (first_err == RSDSFM_OK)
             first_err = fail(ctx, RSDSFM_ERR_ARG, "rsdsfm_refine_rectify_sequence: bad pair argument");
     }
     if (max_m == 0) return first_err;
+
+    // Two compute lanes (see common.cuh): pair j runs on lane j&1 = I/O slot j&1.  Lane 1 is a second
+    // context of its own; with both lanes busy each LM solve takes half of the SMs.
+    // Host buffers: the sequence is PCIe-bound and a lane holds its staging slot for the whole (twice as
+    // long) half-GPU compute, which would starve the upload stream -- one lane, full-GPU solves.
+    const bool two_lanes = !host && n_ok >= 2 && ctx->num_sms >= 2 && !getenv("RSDSFM_SINGLE_LANE");
+    if (two_lanes && !ctx->lane1) {
+        if (rsdsfm_create(ctx->device, nullptr, &ctx->lane1) != RSDSFM_OK)
+            return fail(ctx, RSDSFM_ERR_CUDA, rsdsfm_last_error(nullptr));
+    }
+    rsdsfm_ctx *lane[2] = {ctx, two_lanes ? ctx->lane1 : ctx};
+    auto drain_all = [&]() { drain(ctx); if (ctx->lane1) cudaStreamSynchronize(ctx->lane1->stream); };
+    const long long launches1_before = ctx->lane1 ? ctx->lane1->launches : 0;
+    if (two_lanes) {
+        ctx->lm_grid = ctx->num_sms / 2; ctx->lane1->lm_grid = ctx->num_sms - ctx->num_sms / 2;
+        ctx->lane1->profile = ctx->profile;
+        ctx->lane1->exc_cap = ctx->exc_cap > ctx->lane1->exc_cap ? ctx->exc_cap : ctx->lane1->exc_cap;
+    }
+    // staging buffer j of I/O slot s (one lane: both slots live in this context; two lanes: slot = lane)
+    auto stg = [&](int s, int j) -> DevBuf & { return two_lanes ? lane[s]->stage[j] : ctx->stage[8 * s + j]; };
+
     // size every buffer once, before anything is in flight
-    drain(ctx);
-    RS_TRY(lm_reserve(ctx, max_m));
-    if (host)
-        for (int s = 0; s < 2; ++s) {
+    drain_all();
+    int rc0 = lm_reserve(lane[0], max_m);
+    if (rc0 == RSDSFM_OK && two_lanes) rc0 = lm_reserve(lane[1], max_m);
+    if (rc0 == RSDSFM_OK && host)
+        for (int s = 0; s < 2 && rc0 == RSDSFM_OK; ++s) {
             const size_t sz[8] = {sizeof(double) * 2 * (size_t)max_m, sizeof(double) * 3 * (size_t)max_m,
                                   sizeof(double) * (size_t)max_m, sizeof(double) * (size_t)max_m, tot * 3,
                                   sizeof(double) * (size_t)max_m, sizeof(double) * tot, tot * 3};
-            for (int j = 0; j < 8; ++j) RS_TRY(ensure(ctx, ctx->stage[8 * s + j], sz[j]));
+            for (int j = 0; j < 8 && rc0 == RSDSFM_OK; ++j) rc0 = ensure(lane[s], stg(s, j), sz[j]);
         }
+    if (rc0 != RSDSFM_OK) {
+        if (two_lanes) { ctx->lm_grid = 0; ctx->lane1->lm_grid = 0; if (lane[1]->err.size()) ctx->err = lane[1]->err; }
+        return rc0;
+    }
 
-    // Pair `j` occupies I/O slot j&1.  In flight at any time: upload of pair i (s_in), compute of
-    // pairs <= i (stream, in order), download of pairs < i (s_out).  The upload of pair i starts as
-    // soon as the compute of pair i-2 has released the slot's staging buffers (stream-side wait, the
-    // host does not block for it); pair i-2 is finished (results parsed on the host) before the
-    // compute of pair i is queued, because that compute overwrites the slot's read-back area.
+    // In flight at any time: upload of pair i (s_in), compute of pairs <= i (one stream per lane, in order
+    // within a lane), download of pairs < i (s_out).  The upload of pair i starts as soon as the compute of
+    // pair i-2 has released the slot's staging buffers (stream-side wait, the host does not block for it);
+    // pair i-2 is finished (results parsed on the host) before the compute of pair i is queued, because that
+    // compute overwrites the slot's read-back area.
     int submitted[2] = {-1, -1};                 // pair occupying each slot, not yet finished
     bool retried = false;
     auto finish = [&](int slot) -> int {
@@ -321,18 +347,21 @@ int rsdsfm_refine_rectify_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm
         if (j < 0) return RSDSFM_OK;
         submitted[slot] = -1;
         rsdsfm_pair_io &p = pairs[j];
+        rsdsfm_ctx *L = lane[slot];
         RS_CUDA(ctx, cudaEventSynchronize(ctx->ev_out[slot]));
-        ctx->io_slot = slot;
+        L->io_slot = two_lanes ? 0 : slot;
         bool overflow = false;
-        int rc = finish_step(ctx, nf, p.m, p.v, p.w, &p.k, &p.summary, &overflow);
+        int rc = finish_step(L, nf, p.m, p.v, p.w, &p.k, &p.summary, &overflow);
         if (rc == RSDSFM_OK && overflow) {
             // Exception list too small for this pair (it has been enlarged): let everything in
             // flight complete, keep the other slot's read-backs, and redo this pair synchronously.
-            drain(ctx);
-            rc = step_sync(ctx, mem, slot, p.flow, p.inliers3, p.alpha, p.alpha_k, p.m, p.v, p.w, &p.k, const_acceleration,
-                           gs_mode, p.image, rows, cols, K4, gamma, layout, p.z_out, p.depth_map, p.rectified, &p.summary);
+            drain_all();
+            rc = step_sync(L, mem, two_lanes ? 0 : slot, p.flow, p.inliers3, p.alpha, p.alpha_k, p.m, p.v, p.w, &p.k,
+                           const_acceleration, gs_mode, p.image, rows, cols, K4, gamma, layout, p.z_out, p.depth_map, p.rectified,
+                           &p.summary);
             retried = true;                       // the slot's staging buffers were reused
         }
+        if (rc != RSDSFM_OK && L != ctx) ctx->err = L->err;
         p.status = rc;
         return rc;
     };
@@ -341,7 +370,7 @@ int rsdsfm_refine_rectify_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm
         const void *src[5] = {p.flow, p.inliers3, p.alpha, p.alpha_k, p.image};
         const size_t sz[5] = {sizeof(double) * 2 * mm, sizeof(double) * 3 * mm, sizeof(double) * mm, sizeof(double) * mm, tot * 3};
         for (int j = 0; j < 5; ++j)
-            RS_CUDA(ctx, cudaMemcpyAsync(ctx->stage[8 * s + j].p, src[j], sz[j], cudaMemcpyHostToDevice, ctx->s_in));
+            RS_CUDA(ctx, cudaMemcpyAsync(stg(s, j).p, src[j], sz[j], cudaMemcpyHostToDevice, ctx->s_in));
         RS_CUDA(ctx, cudaEventRecord(ctx->ev_in[s], ctx->s_in));
         return RSDSFM_OK;
     };
@@ -349,7 +378,8 @@ int rsdsfm_refine_rectify_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm
     for (int i = 0; i < n_pairs; ++i) {
         rsdsfm_pair_io &p = pairs[i];
         if (p.status != RSDSFM_OK) continue;
-        const int s = i & 1, b = 8 * s;
+        const int s = i & 1;
+        rsdsfm_ctx *L = lane[s];
         const size_t mm = (size_t)p.m;
         StepArgs a{p.flow, p.inliers3, p.alpha, p.alpha_k, nullptr, p.image, p.m, const_acceleration, gs_mode, rows, cols,
                    layout, K4, gamma, p.z_out, p.depth_map, p.rectified};
@@ -364,16 +394,17 @@ int rsdsfm_refine_rectify_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm
             if (frc != RSDSFM_OK && first_err == RSDSFM_OK) first_err = frc;
             if (host) {
                 if (retried) RS_TRY(upload(p, s));
-                RS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[s], 0));
-                a.flow = (const double *)ctx->stage[b + 0].p; a.inliers3 = (const double *)ctx->stage[b + 1].p;
-                a.alpha = (const double *)ctx->stage[b + 2].p; a.alpha_k = (const double *)ctx->stage[b + 3].p;
-                a.image = (const uint8_t *)ctx->stage[b + 4].p;
-                a.z = (double *)ctx->stage[b + 5].p; a.depth_map = (double *)ctx->stage[b + 6].p;
-                a.rectified = (uint8_t *)ctx->stage[b + 7].p;
+                RS_CUDA(ctx, cudaStreamWaitEvent(L->stream, ctx->ev_in[s], 0));
+                a.flow = (const double *)stg(s, 0).p; a.inliers3 = (const double *)stg(s, 1).p;
+                a.alpha = (const double *)stg(s, 2).p; a.alpha_k = (const double *)stg(s, 3).p;
+                a.image = (const uint8_t *)stg(s, 4).p;
+                a.z = (double *)stg(s, 5).p; a.depth_map = (double *)stg(s, 6).p;
+                a.rectified = (uint8_t *)stg(s, 7).p;
             }
-            ctx->io_slot = s;
-            RS_TRY(queue_step(ctx, a, p.v, p.w, p.k));
-            RS_CUDA(ctx, cudaEventRecord(ctx->ev_cdone[s], ctx->stream));
+            L->io_slot = two_lanes ? 0 : s;
+            const int qrc = queue_step(L, a, p.v, p.w, p.k);
+            if (qrc != RSDSFM_OK) { if (L != ctx) ctx->err = L->err; return qrc; }
+            RS_CUDA(ctx, cudaEventRecord(ctx->ev_cdone[s], L->stream));
             RS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_cdone[s], 0));
             if (host) {
                 RS_CUDA(ctx, cudaMemcpyAsync(p.z_out, a.z, sizeof(double) * mm, cudaMemcpyDeviceToHost, ctx->s_out));
@@ -384,7 +415,7 @@ int rsdsfm_refine_rectify_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm
             return RSDSFM_OK;
         }();
         if (rc != RSDSFM_OK) {
-            drain(ctx);
+            drain_all();
             p.status = rc;
             if (first_err == RSDSFM_OK) first_err = rc;
             continue;
@@ -398,8 +429,17 @@ int rsdsfm_refine_rectify_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm
         int rc = finish(order[q]);
         if (rc != RSDSFM_OK && first_err == RSDSFM_OK) first_err = rc;
     }
-    drain(ctx);
+    drain_all();
     ctx->io_slot = 0;
+    if (two_lanes) {
+        rsdsfm_ctx *L1 = ctx->lane1;
+        ctx->lm_grid = 0; L1->lm_grid = 0; L1->io_slot = 0;
+        ctx->launches += L1->launches - launches1_before;
+        if (ctx->profile) {                       // lane 1's timers join the caller-visible ones
+            for (int j = 0; j < 8; ++j) { ctx->prof[j] += L1->prof[j]; ctx->prof_detail[j] += L1->prof_detail[j]; L1->prof[j] = 0.0; L1->prof_detail[j] = 0.0; }
+        }
+        if (L1->exc_cap > ctx->exc_cap) ctx->exc_cap = L1->exc_cap;
+    }
     return first_err;
 }
 

@@ -1107,6 +1107,8 @@ __global__ void __launch_bounds__(256) k_lm_readback(const LmShared *sh, const d
     if (stats8 && threadIdx.x < 8) host_stats8[threadIdx.x] = stats8[threadIdx.x];
 }
 
+int lm_grid_size(const rsdsfm_ctx *ctx) { return (ctx->lm_grid > 0 && ctx->lm_grid < ctx->num_sms) ? ctx->lm_grid : ctx->num_sms; }
+
 // Initial capacity (entries) of each clamped-pixel list; an overflow is detected by the kernel and the
 // solve is repeated with room for every residual block.  RSDSFM_EXC_CAP overrides the default so that
 // the tests can drive the overflow path with a handful of clamped pixels.
@@ -1125,7 +1127,7 @@ static int lm_solve_async(rsdsfm_ctx *ctx, const RefineData &D, double *d0, doub
 {
     RS_TRY(ensure(ctx, ctx->lm_shared, sizeof(LmShared)));
     LmShared *sh = (LmShared *)ctx->lm_shared.p;
-    const int grid = ctx->num_sms;                      // one persistent CTA per SM
+    const int grid = lm_grid_size(ctx);                 // one persistent CTA per SM (half of them in a two-lane sequence)
     const int nv = (nf == 0) ? Acc<0>::NV : (nf == 6 ? Acc<6>::NV : Acc<7>::NV);
     RS_TRY(ensure(ctx, ctx->partials, sizeof(double) * (size_t)grid * nv));
     if (ctx->exc_cap < min_exc_cap()) ctx->exc_cap = min_exc_cap();

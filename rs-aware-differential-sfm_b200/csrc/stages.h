@@ -37,6 +37,7 @@ int refine_device(rsdsfm_ctx *, const double *flow, const double *inliers3, cons
 int refine_async(rsdsfm_ctx *, const double *flow, const double *inliers3, const double *alpha, const double *alpha_k,
                  int m, const double *v, const double *w, double k, int const_acc, const int32_t *flow_index,
                  const rsdsfm_lm_options *, double *z_out, double *zstats_rows = nullptr);   // zstats_rows: num_sms x 3, see glue_device
+int lm_grid_size(const rsdsfm_ctx *);                   // CTAs of the LM kernel = rows of its z statistics
 int lm_reserve(rsdsfm_ctx *, int m);                     // pre-sizes the solver's buffers for up to m residual blocks
 int lm_collect_enqueue(rsdsfm_ctx *, const double *stats_dev8);   // zero-copy read-back into the I/O slot's pinned area
 int lm_collect_finish(rsdsfm_ctx *, int nf, int m, Motion *mot, rsdsfm_lm_summary *, bool *overflow);

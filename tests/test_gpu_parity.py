@@ -272,8 +272,8 @@ def _seq_pairs(oracle, synth, n_pairs, const_acc):
 @pytest.mark.parametrize("mem", ["host", "device"])
 @pytest.mark.parametrize("const_acc", [False, True])
 def test_refine_rectify_sequence_equals_single_calls(ctx, oracle, synth, mem, const_acc):
-    """The software-pipelined sequence entry point must return exactly what n single calls return
-    (same kernels, same order per pair; different m per pair, 5 pairs so both I/O slots are reused)."""
+    """The software-pipelined sequence entry point against n single calls (different m per pair, 5 pairs so
+    both I/O slots / compute lanes are reused)."""
     import torch
     cases = _seq_pairs(oracle, synth, 5, const_acc)
     dev = torch.device("cuda", 0)
@@ -289,13 +289,27 @@ def test_refine_rectify_sequence_equals_single_calls(ctx, oracle, synth, mem, co
     seq = ctx.refine_rectify_sequence(pairs, const_acc, False, cases[0]["K4"], cases[0]["gamma"])
     assert len(seq) == len(single)
     host = (lambda a: a.cpu().numpy()) if mem == "device" else (lambda a: a)
+    # the two-lane sequence reduces over half as many CTA rows as a single call: same arithmetic, another
+    # (fixed) summation order, so the results agree to rounding, not to the bit ...
     for s, r in zip(seq, single):
         assert s["status"] == 0
-        assert np.array_equal(s["v"], r["v"]) and np.array_equal(s["w"], r["w"]) and s["k"] == r["k"]
+        assert np.abs(s["v"] - r["v"]).max() <= 1e-10 * np.abs(r["v"]).max() and np.abs(s["w"] - r["w"]).max() <= 1e-10 * np.abs(r["w"]).max()
+        assert abs(s["k"] - r["k"]) <= 1e-10 * max(1.0, abs(r["k"]))
         assert s["summary"]["iterations"] == r["summary"]["iterations"]
-        assert s["summary"]["final_cost"] == r["summary"]["final_cost"]
+        assert abs(s["summary"]["final_cost"] - r["summary"]["final_cost"]) <= 1e-10 * r["summary"]["final_cost"]
+        rel = helpers.rel_err(host(s["z"]), host(r["z"]))
+        assert np.median(rel) < 1e-9 and np.percentile(rel, 99) < 1e-6
+        assert np.array_equal(host(s["depth_map"]) != 0, host(r["depth_map"]) != 0)
+        assert (host(s["rectified"]) != host(r["rectified"])).mean() < 1e-3
+    # ... while the sequence itself is reproducible to the bit, and a one-pair sequence IS the single call
+    again = ctx.refine_rectify_sequence(pairs, const_acc, False, cases[0]["K4"], cases[0]["gamma"])
+    for s, t in zip(seq, again):
+        assert np.array_equal(s["v"], t["v"]) and np.array_equal(s["w"], t["w"]) and s["k"] == t["k"]
         for key in ("z", "depth_map", "rectified"):
-            assert np.array_equal(host(s[key]), host(r[key])), key
+            assert np.array_equal(host(s[key]), host(t[key])), key
+    one = ctx.refine_rectify_sequence(pairs[:1], const_acc, False, cases[0]["K4"], cases[0]["gamma"])[0]
+    assert np.array_equal(one["v"], single[0]["v"]) and np.array_equal(host(one["z"]), host(single[0]["z"]))
+    assert np.array_equal(host(one["rectified"]), host(single[0]["rectified"]))
 
 
 def test_refine_rectify_sequence_bad_pair_is_reported(ctx, oracle, synth):
