@@ -326,6 +326,15 @@ def test_refine_rectify_sequence_bad_pair_is_reported(ctx, oracle, synth):
     # the context stays usable and the valid pairs still run
     ok = ctx.refine_rectify_sequence([pairs[0], pairs[2]], False, False, cases[0]["K4"], cases[0]["gamma"])
     assert [r["status"] for r in ok] == [0, 0]
+    # the same with device buffers (two compute lanes)
+    import torch
+    dpairs = [{k: (torch.from_numpy(np.ascontiguousarray(v)).cuda() if isinstance(v, np.ndarray) and v.size > 7 else v) for k, v in p.items()}
+              for p in pairs]
+    with pytest.raises(capi.RsdsfmError):
+        ctx.refine_rectify_sequence(dpairs, False, False, cases[0]["K4"], cases[0]["gamma"])
+    okd = ctx.refine_rectify_sequence([dpairs[0], dpairs[2], dpairs[0]], False, False, cases[0]["K4"], cases[0]["gamma"])
+    assert [r["status"] for r in okd] == [0, 0, 0]
+    assert np.array_equal(okd[0]["rectified"].cpu().numpy(), okd[2]["rectified"].cpu().numpy())
 
 
 @pytest.mark.parametrize("mem", ["host", "device"])
@@ -675,7 +684,8 @@ def test_full_hd_rectification_is_identity_for_a_static_camera(ctx, full_hd):
     assert np.array_equal(gs[~skipped], P["image"][~skipped]) and np.all(gs[skipped] == 0)
 
 
-def test_clamped_pixel_list_overflow_is_retried(capi, ctx, oracle, synth, monkeypatch):
+@pytest.mark.parametrize("mem", ["host", "device"])
+def test_clamped_pixel_list_overflow_is_retried(capi, ctx, oracle, synth, monkeypatch, mem):
     """More clamped pixels than the list holds: the kernel flags the overflow, the library enlarges the
     list and repeats the solve -- in the synchronous call and in the middle of a pipelined sequence.
     RSDSFM_EXC_CAP shrinks the initial capacity so that a handful of clamped pixels is enough."""
@@ -683,10 +693,14 @@ def test_clamped_pixel_list_overflow_is_retried(capi, ctx, oracle, synth, monkey
                             v=(0.02, 0.01, 0.30), w=(0.001, 0.002, -0.003), noise=0.05, outliers=0.0, tol=0.05)
     plain = helpers.make_case(oracle, synth, 240, 320, helpers.small_K(6), k=0.4, const_acc=True, H=8, seed=12)
 
+    import torch
+    to = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()) if mem == "device" else (lambda a: np.ascontiguousarray(a))
+    host = (lambda a: a.cpu().numpy()) if mem == "device" else (lambda a: a)
+
     def pair(c):
         R = c["ransac"]
-        return dict(flow=c["flow"][:2 * c["m"]], inliers3=c["inliers3"], alpha=c["alpha_in"], alpha_k=c["alpha_k_in"], image=c["P"]["image"],
-                    m=c["m"], v=R["v"], w=R["w"], k=R["k"])
+        return dict(flow=to(c["flow"][:2 * c["m"]]), inliers3=to(c["inliers3"]), alpha=to(c["alpha_in"]), alpha_k=to(c["alpha_k_in"]),
+                    image=to(c["P"]["image"]), m=c["m"], v=R["v"], w=R["w"], k=R["k"])
 
     def run(context):
         R = foe["ransac"]
@@ -710,7 +724,7 @@ def test_clamped_pixel_list_overflow_is_retried(capi, ctx, oracle, synth, monkey
     for g, w in zip(got_seq, want_seq):
         assert g["status"] == 0
         assert np.array_equal(g["v"], w["v"]) and np.array_equal(g["w"], w["w"]) and g["k"] == w["k"]
-        assert np.array_equal(g["z"], w["z"]) and np.array_equal(g["rectified"], w["rectified"])
+        assert np.array_equal(host(g["z"]), host(w["z"])) and np.array_equal(host(g["rectified"]), host(w["rectified"]))
 
 
 # ---------------------------------------------------------------------------- committed golden vectors
