@@ -312,6 +312,10 @@ int rsdsfm_refine_rectify_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm
     auto drain_all = [&]() { drain(ctx); if (ctx->lane1) cudaStreamSynchronize(ctx->lane1->stream); };
     const long long launches1_before = ctx->lane1 ? ctx->lane1->launches : 0;
     if (two_lanes) {
+        // lane 1 has a stream of its own: whatever the caller queued on the context's stream before this call
+        // (e.g. the kernels that produced the device inputs) must be ordered before lane 1's work too
+        RS_CUDA(ctx, cudaEventRecord(ctx->ev_in[0], ctx->stream));
+        RS_CUDA(ctx, cudaStreamWaitEvent(ctx->lane1->stream, ctx->ev_in[0], 0));
         ctx->lm_grid = ctx->num_sms / 2; ctx->lane1->lm_grid = ctx->num_sms - ctx->num_sms / 2;
         ctx->lane1->profile = ctx->profile;
         ctx->lane1->exc_cap = ctx->exc_cap > ctx->lane1->exc_cap ? ctx->exc_cap : ctx->lane1->exc_cap;
