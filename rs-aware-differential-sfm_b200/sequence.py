@@ -30,6 +30,25 @@ def run_shard(process_pair, num_pairs, rank, world_size):
     return lo, rec
 
 
+def run_shard_sequence(ctx, make_pair, num_pairs, rank, world_size, const_acc, gs_mode, K4, gamma, batch=8, layout=0):
+    """This rank's block through the pipelined sequence entry point (rsdsfm_refine_rectify_sequence), `batch`
+    pairs per call so that only `batch` pairs have to be resident at a time.  make_pair(pair_index) -> dict
+    with flow, inliers3, alpha, alpha_k, image, m, v, w, k (numpy = host buffers, torch CUDA = device
+    buffers; optionally `out`).  Returns (lo, records[n_local, RECORD], results) with the per-pair result
+    dicts of capi.Context.refine_rectify_sequence."""
+    lo, hi = shard_range(num_pairs, rank, world_size)
+    rec = np.zeros((hi - lo, RECORD))
+    results = []
+    for b0 in range(lo, hi, batch):
+        block = [make_pair(p) for p in range(b0, min(b0 + batch, hi))]
+        out = ctx.refine_rectify_sequence(block, const_acc, gs_mode, K4, gamma, layout=layout)
+        for j, r in enumerate(out):
+            i = b0 - lo + j
+            rec[i, 0:3] = r["v"]; rec[i, 3:6] = r["w"]; rec[i, 6] = r["k"]; rec[i, 7] = r["summary"]["iterations"]
+        results.extend(out)
+    return lo, rec, results
+
+
 def gather_records(local, num_pairs, dist=None, device="cpu"):
     """The final gather: every rank receives the records of all pairs, in pair order.
     `dist` is torch.distributed (initialised) or None for a single process."""

@@ -781,3 +781,28 @@ def test_negative_mean_depth_is_sign_fixed_in_the_fused_driver(ctx, oracle, case
     assert np.array_equal(np.asarray(dm).reshape(-1), got["depth_map"].reshape(-1))
     diff = np.abs(got["rectified"].astype(np.int32) - ref["rectified"].astype(np.int32)).max(axis=2)
     assert (diff <= 1).mean() >= 0.999
+
+
+def test_sharded_sequence_driver(ctx, oracle, synth, pkg):
+    """sequence.run_shard_sequence: a rank's block of pairs through the pipelined entry point in batches;
+    two 'ranks' together produce the records of the whole sequence."""
+    import importlib
+    seq = importlib.import_module("rs-aware-differential-sfm_b200.sequence")
+    cases = _seq_pairs(oracle, synth, 5, False)
+
+    def make_pair(i):
+        c = cases[i]
+        R = c["ransac"]
+        return dict(flow=c["flow"][:2 * c["m"]], inliers3=c["inliers3"], alpha=c["alpha_in"], alpha_k=c["alpha_k_in"],
+                    image=c["P"]["image"], m=c["m"], v=R["v"], w=R["w"], k=R["k"])
+
+    whole = ctx.refine_rectify_sequence([make_pair(i) for i in range(5)], False, False, cases[0]["K4"], cases[0]["gamma"])
+    full = np.zeros((5, seq.RECORD))
+    for rank in range(2):
+        lo, rec, res = seq.run_shard_sequence(ctx, make_pair, 5, rank, 2, False, False, cases[0]["K4"], cases[0]["gamma"], batch=2)
+        full[lo:lo + rec.shape[0]] = rec
+        for j, r in enumerate(res):
+            assert np.array_equal(r["rectified"], whole[lo + j]["rectified"])
+    for i in range(5):
+        assert np.array_equal(full[i, 0:3], whole[i]["v"]) and np.array_equal(full[i, 3:6], whole[i]["w"])
+        assert full[i, 7] == whole[i]["summary"]["iterations"]

@@ -69,3 +69,31 @@ def test_two_rank_gloo_sharding_and_final_gather(tmp_path, oracle, synth):
     t0 = np.load(tmp_path / "t_0.npy"); t1 = np.load(tmp_path / "t_1.npy")
     assert t0[0] == 11.0 and t1[0] == 11.0                             # max over ranks
     assert (t0[1], t1[1]) == (0, 3)                                    # contiguous blocks [0,3) and [3,5)
+
+
+def test_run_shard_sequence_batches_and_records(pkg):
+    """Host logic of sequence.run_shard_sequence with a stand-in context: every pair of the rank's block is
+    submitted exactly once, in order, in batches of at most `batch`, and the records carry v, w, k, iterations."""
+    import importlib
+    seq = importlib.import_module("rs-aware-differential-sfm_b200.sequence")
+
+    class FakeCtx:
+        def __init__(self):
+            self.calls = []
+
+        def refine_rectify_sequence(self, pairs, const_acc, gs_mode, K4, gamma, layout=0):
+            self.calls.append([p["id"] for p in pairs])
+            return [dict(v=np.full(3, p["id"]), w=np.full(3, -p["id"]), k=0.5 * p["id"], summary=dict(iterations=10 + p["id"])) for p in pairs]
+
+    for world in (1, 2, 3):
+        seen = []
+        for rank in range(world):
+            ctx = FakeCtx()
+            lo, rec, res = seq.run_shard_sequence(ctx, lambda i: dict(id=i), 11, rank, world, True, False, None, 0.95, batch=4)
+            assert all(len(c) <= 4 for c in ctx.calls)
+            ids = [i for c in ctx.calls for i in c]
+            assert ids == list(range(lo, lo + rec.shape[0])) and len(res) == rec.shape[0]
+            assert np.array_equal(rec[:, 0], np.array(ids, dtype=float)) and np.array_equal(rec[:, 6], 0.5 * np.array(ids))
+            assert np.array_equal(rec[:, 7], 10.0 + np.array(ids))
+            seen += ids
+        assert seen == list(range(11))
