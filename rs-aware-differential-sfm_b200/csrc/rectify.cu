@@ -104,22 +104,39 @@ __global__ void k_glue_raster(double *z, int zs, const double *__restrict__ xyz,
 {
     const double sign = stats[3], z_min = stats[4], z_max = stats[5];
     const double multiplier = 244.0 / (z_max - z_min);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-        double zi = z[(size_t)i * zs];
-        if (sign < 0) { zi = zi * -1.0; z[(size_t)i * zs] = zi; }
-        const double xd = fx * xyz[(size_t)i * xs] + cx + 0.5;
-        const double yd = fy * xyz[(size_t)i * xs + 1] + cy + 0.5;
-        int x, y;
-        if (!to_int_trunc(xd, x) || !to_int_trunc(yd, y)) continue;
-        if (x < 0 || x >= cols || y < 0 || y >= rows) continue;   // UB in the reference (Q3): skipped
-        if (depth_img) {
-            const double zz = (zi - z_min) * multiplier;
-            int zq = 10;
-            if (fabs(zz) < 2147483000.0) zq = 10 + (int)zz;
-            depth_img[(size_t)y * cols + x] = (uint8_t)zq;
+    // four inliers per thread and round: all loads first (independent), then the scatters
+    constexpr int kU = 4;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < m; i0 += kU * stride) {
+        double zz4[kU], xx4[kU], yy4[kU];
+#pragma unroll
+        for (int r = 0; r < kU; ++r) {
+            const int i = i0 + r * stride;
+            const bool in = i < m;
+            zz4[r] = in ? z[(size_t)i * zs] : 0.0;
+            xx4[r] = in ? xyz[(size_t)i * xs] : 0.0;
+            yy4[r] = in ? xyz[(size_t)i * xs + 1] : 0.0;
         }
-        const size_t idx = (layout == RSDSFM_DEPTH_COLMAJOR) ? ((size_t)y + (size_t)x * rows) : ((size_t)y * cols + x);
-        depth_map[idx] = zi;
+#pragma unroll
+        for (int r = 0; r < kU; ++r) {
+            const int i = i0 + r * stride;
+            if (i >= m) break;
+            double zi = zz4[r];
+            if (sign < 0) { zi = zi * -1.0; z[(size_t)i * zs] = zi; }
+            const double xd = fx * xx4[r] + cx + 0.5;
+            const double yd = fy * yy4[r] + cy + 0.5;
+            int x, y;
+            if (!to_int_trunc(xd, x) || !to_int_trunc(yd, y)) continue;
+            if (x < 0 || x >= cols || y < 0 || y >= rows) continue;   // UB in the reference (Q3): skipped
+            if (depth_img) {
+                const double zz = (zi - z_min) * multiplier;
+                int zq = 10;
+                if (fabs(zz) < 2147483000.0) zq = 10 + (int)zz;
+                depth_img[(size_t)y * cols + x] = (uint8_t)zq;
+            }
+            const size_t idx = (layout == RSDSFM_DEPTH_COLMAJOR) ? ((size_t)y + (size_t)x * rows) : ((size_t)y * cols + x);
+            depth_map[idx] = zi;
+        }
     }
 }
 
@@ -254,14 +271,24 @@ __global__ void __launch_bounds__(kThreads) k_gather_fill(const uint8_t *__restr
 {
     __shared__ uchar4 tile[kFH + 2][kFW + 2];
     const int x0 = blockIdx.x * kFW, y0 = blockIdx.y * kFH;
-    for (int idx = threadIdx.x; idx < (kFH + 2) * (kFW + 2); idx += kThreads) {
+    // two dependent gathers per tile entry (winner -> source pixel): issue all winner loads of this thread
+    // before the first colour load so that their latencies overlap instead of adding up
+    constexpr int kEntries = (kFH + 2) * (kFW + 2), kPer = (kEntries + kThreads - 1) / kThreads;
+    unsigned int wv[kPer];
+#pragma unroll
+    for (int r = 0; r < kPer; ++r) {
+        const int idx = threadIdx.x + r * kThreads;
         const int ty = idx / (kFW + 2), tx = idx - ty * (kFW + 2);
         const int y = y0 - 1 + ty, x = x0 - 1 + tx;
+        wv[r] = (idx < kEntries && y >= 0 && y < rows && x >= 0 && x < cols) ? winner[(size_t)y * cols + x] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < kPer; ++r) {
+        const int idx = threadIdx.x + r * kThreads;
+        if (idx >= kEntries) break;
+        const int ty = idx / (kFW + 2), tx = idx - ty * (kFW + 2);
         uchar4 px = make_uchar4(0, 0, 0, 0);
-        if (y >= 0 && y < rows && x >= 0 && x < cols) {
-            const unsigned int wv = winner[(size_t)y * cols + x];
-            if (wv) { const size_t q = (size_t)(wv - 1) * 3; px = make_uchar4(image[q], image[q + 1], image[q + 2], 0); }
-        }
+        if (wv[r]) { const size_t q = (size_t)(wv[r] - 1) * 3; px = make_uchar4(image[q], image[q + 1], image[q + 2], 0); }
         tile[ty][tx] = px;
     }
     __syncthreads();
