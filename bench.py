@@ -128,6 +128,7 @@ def prepare_pair_gpu(ctx, synth, torch, seed, H=16, tol=0.05):
         keep.append(t)
         return t.numpy()
 
+    # (write-combined pinned inputs -- capi.HostBuffer(write_combined=True) -- were measured: no difference)
     h = dict(flow=pin(d["flow"][:2 * m]), inliers3=pin(d["inliers3"]), alpha=pin(d["alpha"]), alpha_k=pin(d["alpha_k"]),
              image=pin(image))
     h["out"] = (pin(d["out"][0]), pin(d["out"][1]), pin(d["out"][2]))

@@ -25,6 +25,7 @@
 #ifndef RSDSFM_H
 #define RSDSFM_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -111,6 +112,12 @@ RSDSFM_API int rsdsfm_profile_read(rsdsfm_ctx *ctx, double *out8);
  * the same three for pass B; then the controller logic alone (after the row reduction) for pass A
  * and pass B -- measured by CTA 0 / the controller CTA with %globaltimer. */
 RSDSFM_API int rsdsfm_profile_detail(rsdsfm_ctx *ctx, double *out8);
+
+/* Page-locked host buffers for the RSDSFM_HOST paths (asynchronous copies need them; the pipelined
+ * sequence entry points overlap nothing with pageable memory).  write_combined: for buffers the CPU
+ * only writes and the GPU only reads (inputs) -- uncached on the CPU side, no snoop on the DMA read. */
+RSDSFM_API int rsdsfm_host_alloc(size_t bytes, int write_combined, void **out);
+RSDSFM_API int rsdsfm_host_free(void *p);
 
 /* ---- a2: flatten + normalise glue (main.cc:398-432, errorMeasure.cpp:66-97) --------------- */
 /* flow_img: rows*cols*2.  Outputs (each 2*rows*cols doubles) are pre-filled like the reference

@@ -21,7 +21,7 @@ EXPORTS = [
     "rsdsfm_ransac_score", "rsdsfm_ransac", "rsdsfm_gather_inliers", "rsdsfm_estimate_inverse_depths",
     "rsdsfm_refine", "rsdsfm_depth_glue", "rsdsfm_set_relative_pose", "rsdsfm_backproject", "rsdsfm_fill_cracks",
     "rsdsfm_refine_rectify", "rsdsfm_refine_rectify_sequence", "rsdsfm_pipeline_pair", "rsdsfm_pipeline_sequence",
-    "rsdsfm_relocate_pose", "rsdsfm_reprojection_error", "rsdsfm_true_flow",
+    "rsdsfm_relocate_pose", "rsdsfm_reprojection_error", "rsdsfm_true_flow", "rsdsfm_host_alloc", "rsdsfm_host_free",
 ]
 
 
@@ -527,6 +527,27 @@ class Context:
     def pipeline_pair(self, flow_img, image, K4, gamma, tol, const_acc, samples=None, draws=None, **kw):
         return self.pipeline_sequence([dict(flow_img=flow_img, image=image, samples=samples, draws=draws, out=kw.pop("out", None))],
                                       K4, gamma, tol, const_acc, **kw)[0]
+
+
+class HostBuffer:
+    """A page-locked host array from rsdsfm_host_alloc (optionally write-combined), viewed as numpy."""
+
+    def __init__(self, shape, dtype, write_combined=False):
+        self.lib = load()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        rc = self.lib.rsdsfm_host_alloc(C.c_size_t(max(n, 1)), int(write_combined), C.byref(p))
+        if rc != 0:
+            raise RsdsfmError("rsdsfm_host_alloc failed: %d" % rc)
+        self.ptr = p
+        buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            self.lib.rsdsfm_host_free(self.ptr)
+            self.ptr = None
 
 
 def relocate_pose(R_gt, t_gt):

@@ -509,4 +509,19 @@ int rsdsfm_true_flow(rsdsfm_ctx *ctx, int mem, const double *unproj_x, const dou
     return RSDSFM_OK;
 }
 
+int rsdsfm_host_alloc(size_t bytes, int write_combined, void **out)
+{
+    if (!out || bytes == 0) return RSDSFM_ERR_ARG;
+    *out = nullptr;
+    const cudaError_t e = cudaHostAlloc(out, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(nullptr, RSDSFM_ERR_NOMEM, "cudaHostAlloc", e);
+    return RSDSFM_OK;
+}
+
+int rsdsfm_host_free(void *p)
+{
+    if (!p) return RSDSFM_OK;
+    return cudaFreeHost(p) == cudaSuccess ? RSDSFM_OK : RSDSFM_ERR_CUDA;
+}
+
 }  // extern "C"

@@ -806,3 +806,28 @@ def test_sharded_sequence_driver(ctx, oracle, synth, pkg):
     for i in range(5):
         assert np.array_equal(full[i, 0:3], whole[i]["v"]) and np.array_equal(full[i, 3:6], whole[i]["w"])
         assert full[i, 7] == whole[i]["summary"]["iterations"]
+
+
+def test_host_buffers_from_the_library(capi, ctx, oracle, case_cv):
+    """rsdsfm_host_alloc: page-locked (optionally write-combined) host arrays are ordinary inputs / outputs of
+    the RSDSFM_HOST paths."""
+    c = case_cv
+    R = c["ransac"]
+    bufs = []
+
+    def pinned(a, wc):
+        hb = capi.HostBuffer(a.shape, a.dtype, write_combined=wc)
+        hb.array[...] = a
+        bufs.append(hb)
+        return hb.array
+
+    want = ctx.refine_rectify(c["flow"], c["inliers3"], c["alpha_in"], c["alpha_k_in"], c["m"], R["v"], R["w"], R["k"], False, False,
+                              c["P"]["image"], c["K4"], c["gamma"])
+    out = (pinned(np.zeros(c["m"]), False), pinned(np.zeros(c["rows"] * c["cols"]), False), pinned(np.zeros_like(c["P"]["image"]), False))
+    got = ctx.refine_rectify(pinned(c["flow"][:2 * c["m"]], True), pinned(c["inliers3"], True), pinned(c["alpha_in"], True),
+                             pinned(c["alpha_k_in"], True), c["m"], R["v"], R["w"], R["k"], False, False, pinned(c["P"]["image"], True),
+                             c["K4"], c["gamma"], out=out)
+    assert np.array_equal(got["v"], want["v"]) and np.array_equal(got["z"], want["z"])
+    assert np.array_equal(got["rectified"], want["rectified"]) and np.array_equal(got["depth_map"], want["depth_map"])
+    for hb in bufs:
+        hb.free()
