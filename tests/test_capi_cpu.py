@@ -99,3 +99,19 @@ def test_host_shim_headers_compile():
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", host, probe],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_host_relocate_pose_matches_oracle(capi, oracle):
+    """rsdsfm_relocate_pose is a host computation (no GPU): bit-identical to the oracle's restatement of
+    RsFrame::relocatePose, including the untouched scanline 0 and Eigen's cofactor 3x3 inverse."""
+    rng = np.random.default_rng(4)
+    rows = 37
+    a = 0.3
+    R0 = np.array([[np.cos(a), -np.sin(a), 0.0], [np.sin(a), np.cos(a), 0.0], [0.0, 0.0, 1.0]]) + 1e-3 * rng.standard_normal((3, 3))
+    R = np.stack([R0 + 1e-2 * i * rng.standard_normal((3, 3)) for i in range(rows)])
+    t = rng.standard_normal((rows, 3))
+    Rr, tr = capi.relocate_pose(R, t)
+    Ro, to = oracle.relocate_pose(R, t)
+    assert np.array_equal(Rr, Ro) and np.array_equal(tr, to)
+    assert np.array_equal(Rr[0], R[0]) and np.array_equal(tr[0], t[0])
+    assert np.allclose(Rr[1], np.linalg.inv(R[0]) @ R[1], rtol=1e-12, atol=1e-14) and np.allclose(tr[5], t[5] - t[0])
