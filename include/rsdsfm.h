@@ -291,6 +291,12 @@ typedef struct rsdsfm_pipeline_params {
     int repair_pairing;         /* 0 = reference behaviour (residual i reads flow(:, i));
                                  * 1 = residual i reads the flow of inlier i */
     int layout;                 /* depth_map layout, RSDSFM_DEPTH_* */
+    int emulate_padding;        /* 0 = the point set is the n kept flow vectors (errorMeasure.cpp:96-97 truncates);
+                                 * 1 = main.cc:398-447 as written: the arrays stay rows*cols long and the tail
+                                 *     (coord = (1,1), flow = 0, alpha = 1) is sampled, scored and can join the
+                                 *     consensus set.  `samples` / `draws` then index / are reduced
+                                 *     modulo rows*cols points; the out-of-image raster writes of the reference
+                                 *     (main.cc:501-508) are dropped. */
 } rsdsfm_pipeline_params;
 
 typedef struct rsdsfm_pipeline_io {
@@ -298,7 +304,8 @@ typedef struct rsdsfm_pipeline_io {
     const uint8_t *image;       /* rows*cols*3 BGR, in `mem` */
     const int32_t *samples;     /* host, H*9 indices into the flattened order, or NULL */
     const uint32_t *draws;      /* host, H*9 raw rand() values mapped to indices exactly like
-                                 * minimal.cc:226-244 (rand() % n_temp on a persistent index vector);
+                                 * minimal.cc:226-244 (rand() % n_temp on a persistent index vector of the
+                                 * point set: n kept vectors, or rows*cols with emulate_padding);
                                  * used when samples == NULL */
     double *depth_map;          /* out, rows*cols, in `mem` */
     uint8_t *rectified;         /* out, rows*cols*3, in `mem` */

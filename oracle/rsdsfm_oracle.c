@@ -579,12 +579,13 @@ static int orc_lm_solve(const LmProblem *P, const OrcLmOptions *opt, double *v_i
     S->initial_cost = x_cost;
     S->trace_cost[0] = x_cost;
     S->trace_radius[0] = radius;
+    /* IterationZero ends with step_is_valid = step_is_successful = true (trust_region_minimizer.cc): iteration 0
+     * is counted among the successful steps and the gradient tolerance IS tested before the first step */
+    step_is_successful = 1;
 
     for (;;) {
         /* ---- FinalizeIterationAndCheckIfMinimizerCanContinue ---- */
-        if (iteration > 0) {
-            if (step_is_successful) S->num_successful++; else S->num_unsuccessful++;
-        }
+        if (step_is_successful) S->num_successful++; else S->num_unsuccessful++;
         if (iteration >= opt->max_num_iterations) { termination = ORC_NO_CONVERGENCE; reason = ORC_REASON_MAX_ITER; break; }
         if (step_is_successful && gmax <= opt->gradient_tolerance) { termination = ORC_CONVERGENCE; reason = ORC_REASON_GRADIENT_TOL; break; }
         if (radius <= opt->min_trust_region_radius) { termination = ORC_CONVERGENCE; reason = ORC_REASON_MIN_RADIUS; break; }

@@ -14,11 +14,14 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
           "-Xcompiler", "-Wall"]
 # Translation units and extra flags.  --fmad=false where results must be bit-identical to the
 # reference's scalar IEEE arithmetic (RANSAC inlier sets, integer splat targets, alpha factors).
+# api.cu / ransac.cu also hold HOST arithmetic (solve9.h: the 9-point fit): the host compiler must not
+# contract a*b+c into an FMA either, or the hypotheses -- and with them the "bit-exact inlier sets" --
+# would depend on the host ISA (the oracle is built with -ffp-contract=off too).
 UNITS = [
-    ("api.cu", []),
+    ("api.cu", ["-Xcompiler", "-ffp-contract=off"]),
     ("pipeline.cu", []),
     ("refine.cu", []),
-    ("ransac.cu", ["--fmad=false"]),
+    ("ransac.cu", ["--fmad=false", "-Xcompiler", "-ffp-contract=off"]),
     ("rectify.cu", ["--fmad=false"]),
     ("preproc.cu", ["--fmad=false"]),
 ]

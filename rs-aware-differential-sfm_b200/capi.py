@@ -58,7 +58,7 @@ class PipelineParams(C.Structure):
     _fields_ = [("rows", C.c_int), ("cols", C.c_int), ("K4", C.c_double * 4), ("gamma", C.c_double),
                 ("flow_threshold", C.c_double), ("ransac_tolerance", C.c_double), ("num_hypotheses", C.c_int),
                 ("const_acceleration", C.c_int), ("gs_mode", C.c_int), ("use_refinement", C.c_int),
-                ("repair_pairing", C.c_int), ("layout", C.c_int)]
+                ("repair_pairing", C.c_int), ("layout", C.c_int), ("emulate_padding", C.c_int)]
 
 
 class PipelineIO(C.Structure):
@@ -461,7 +461,8 @@ class Context:
 
     # ---- a2..a15 in one call
     @staticmethod
-    def _pipeline_params(rows, cols, K4, gamma, H, tol, const_acc, gs_mode, use_refinement, repair_pairing, layout, thr):
+    def _pipeline_params(rows, cols, K4, gamma, H, tol, const_acc, gs_mode, use_refinement, repair_pairing, layout, thr,
+                         emulate_padding=False):
         P = PipelineParams()
         P.rows, P.cols = int(rows), int(cols)
         P.K4[:] = list(_small(K4, 4))
@@ -469,10 +470,11 @@ class Context:
         P.num_hypotheses = int(H)
         P.const_acceleration, P.gs_mode, P.use_refinement = int(const_acc), int(gs_mode), int(use_refinement)
         P.repair_pairing, P.layout = int(repair_pairing), int(layout)
+        P.emulate_padding = int(emulate_padding)
         return P
 
     def pipeline_sequence(self, pairs, K4, gamma, tol, const_acc, gs_mode=False, use_refinement=True, repair_pairing=False,
-                          layout=DEPTH_COLMAJOR, thr=1e-10):
+                          layout=DEPTH_COLMAJOR, thr=1e-10, emulate_padding=False):
         """rsdsfm_pipeline_sequence (len(pairs) == 1: rsdsfm_pipeline_pair).  `pairs`: list of dicts with
         flow_img (rows x cols x 2 f64), image (rows x cols x 3 u8), and samples (H x 9 int32) or draws
         (H x 9 uint32); optionally out=(depth_map, rectified).  Returns one dict per pair."""
@@ -508,7 +510,8 @@ class Context:
         if len(mems) > 1:
             raise ValueError("mixing host and device pairs in one sequence")
         mem = mems.pop() if mems else HOST
-        P = self._pipeline_params(rows, cols, K4, gamma, H, tol, const_acc, gs_mode, use_refinement, repair_pairing, layout, thr)
+        P = self._pipeline_params(rows, cols, K4, gamma, H, tol, const_acc, gs_mode, use_refinement, repair_pairing, layout, thr,
+                                  emulate_padding)
         if n == 1:
             rc = self.lib.rsdsfm_pipeline_pair(self.h, mem, C.byref(P), C.byref(arr[0]))
         else:

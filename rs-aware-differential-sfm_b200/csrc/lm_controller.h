@@ -132,6 +132,9 @@ struct LmController {
             // s_e = 1/(1+|e(x0)|) >= 1/(1+sqrt(ee_max)):  e^Te >= min_diag (1+sqrt(ee_max))^2  =>  s_e^2 e^Te >= min_diag
             const double t = 1.0 + sqrt(e.ee_max);
             ee_fast_min = opt.min_lm_diagonal * t * t;
+            // IterationZero ends with step_is_valid = step_is_successful = true: iteration 0 counts as a
+            // successful step and the gradient tolerance is tested before the first step is computed
+            step_is_successful = 1;
         } else {
             // HandleSuccessfulStep: evaluation at the new x
             if (bad) return finish(RSDSFM_FAILURE, RSDSFM_REASON_EVAL_FAILED);
@@ -153,7 +156,7 @@ struct LmController {
     // FinalizeIterationAndCheckIfMinimizerCanContinue + start of the next iteration.
     RS_HD LmNext begin_iteration()
     {
-        if (iteration > 0) { if (step_is_successful) num_successful++; else num_unsuccessful++; }
+        if (step_is_successful) num_successful++; else num_unsuccessful++;
         if (iteration >= opt.max_num_iterations) return finish(RSDSFM_NO_CONVERGENCE, RSDSFM_REASON_MAX_ITER);
         if (step_is_successful && gmax <= opt.gradient_tolerance) return finish(RSDSFM_CONVERGENCE, RSDSFM_REASON_GRADIENT_TOL);
         if (radius <= opt.min_trust_region_radius) return finish(RSDSFM_CONVERGENCE, RSDSFM_REASON_MIN_RADIUS);

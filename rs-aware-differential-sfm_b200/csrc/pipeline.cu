@@ -170,6 +170,9 @@ static int pipeline_device(rsdsfm_ctx *ctx, const rsdsfm_pipeline_params &P, con
     RS_TRY(flatten_device(ctx, d_flow_img, P.rows, P.cols, P.K4, P.gamma, P.flow_threshold, coord, flow, cpx, fpx,
                           (int32_t *)B[4].p, &n));
     io->n = n;
+    // main.cc never truncates (Q3): with emulate_padding the point set is all rows*cols columns, the tail
+    // being what k_flat_tail wrote (coord = 1, flow = 0  =>  alpha = 1, alpha_k = the reference's value at y = 1)
+    if (P.emulate_padding) n = (int)tot;
     if (n < 9) return fail(ctx, RSDSFM_ERR_ARG, "pipeline: fewer than 9 valid flow vectors");
     const size_t nn = (size_t)n;
     RS_TRY(ensure(ctx, B[5], sizeof(double) * nn));        // alpha

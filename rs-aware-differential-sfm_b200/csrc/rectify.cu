@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kThreads) k_gather_fill(const uint8_t *__restr
         o[3 * j] = o0; o[3 * j + 1] = o1; o[3 * j + 2] = o2;
     }
     const size_t base = 3 * ((size_t)y * cols + x0 + lx);
-    if (nvalid == 4 && (base & 3) == 0) {
+    if (nvalid == 4 && (reinterpret_cast<uintptr_t>(out + base) & 3) == 0) {       // the caller's pointer need not be word aligned
         unsigned int *w = reinterpret_cast<unsigned int *>(out + base);
         w[0] = o[0] | (o[1] << 8) | (o[2] << 16) | ((unsigned int)o[3] << 24);
         w[1] = o[4] | (o[5] << 8) | (o[6] << 16) | ((unsigned int)o[7] << 24);

@@ -539,6 +539,7 @@ __device__ __noinline__ int ctl_on_eval(LmController &c)
                 c.x_cost = c.ev.cost; c.initial_cost = c.ev.cost;
                 const double t = 1.0 + sqrt(c.ev.ee_max);
                 c.ee_fast_min = c.opt.min_lm_diagonal * t * t;
+                c.step_is_successful = 1;            // IterationZero counts as a successful step (lm_controller.h)
             }
         }
     } else {

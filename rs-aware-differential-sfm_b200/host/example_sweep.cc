@@ -1,0 +1,116 @@
+// example_sweep.cc -- the per-task body of the reference's sweep driver evaluateSyntheticResults()
+// (main.cc:245 and :271-287) compiled against the host shim: TrueValues(w, v), evaluateVelocities(...)
+// with the reference's argument list, and the VelocityErrors access pattern of the result writers.
+// The frames, cached flow and ground truth that setupCameraSynthetic() (main.cc:260-265) loads from the
+// example tarballs are synthesised here (exact constant-velocity RS data).
+//
+//   g++ -std=c++17 -O2 -I include -I rs-aware-differential-sfm_b200/host
+//       rs-aware-differential-sfm_b200/host/example_sweep.cc
+//       -L rs-aware-differential-sfm_b200 -lrsdsfm -Wl,-rpath,'$ORIGIN/..' -o rs-aware-differential-sfm_b200/host/example_sweep
+//
+// argv[1]: directory for the artefacts (results files, depth PNGs, point clouds).  Exit code 0 when the
+// motion is recovered and every artefact round-trips.
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <iomanip>
+#include <string>
+
+#include "camera.h"
+#include "errorMeasure.h"
+#include "minimal.h"
+#include "nonlinearRefinement.h"
+
+static Camera setupCameraSynthetic(int rows, int cols, double gamma, const Eigen::Vector3d &v_true, const Eigen::Vector3d &w_true)
+{
+    Camera camera;
+    Eigen::Matrix3d K;
+    K(0, 0) = 300.0; K(1, 1) = 299.0; K(0, 2) = 120.0; K(1, 2) = 90.0; K(2, 2) = 1.0;
+    camera.setIntrinsics(K);
+    cv::Mat rs1(rows, cols, CV_8UC3), rs2(rows, cols, CV_8UC3);
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x)
+            rs1.at<cv::Vec3b>(y, x) = cv::Vec3b((unsigned char)(30 + (5 * x + y) % 210), (unsigned char)(50 + (x + 3 * y) % 190), (unsigned char)(80 + (x * y) % 160));
+    camera.addFrameReal(rs1);
+    camera.addFrameReal(rs2);
+    const double f_x = K(0, 0), f_y = K(1, 1), c_x = K(0, 2), c_y = K(1, 2);
+    cv::Mat_<cv::Point_<double>> flow_image(rows, cols);
+    Eigen::MatrixXd ux = Eigen::MatrixXd::Zero(rows, cols), uy = ux, uz = ux;
+    for (int j = 0; j < rows; ++j) {
+        const double beta = gamma * j / rows;                          // scanline pose of the small-motion model, k = 0
+        Eigen::Matrix3d Rj = Eigen::Matrix3d::Identity();
+        Rj(0, 1) = -beta * w_true(2); Rj(0, 2) = beta * w_true(1); Rj(1, 0) = beta * w_true(2);
+        Rj(1, 2) = -beta * w_true(0); Rj(2, 0) = -beta * w_true(1); Rj(2, 1) = beta * w_true(0);
+        const Eigen::Vector3d tj = v_true * beta;
+        camera.setScanlinePose(1, j, Rj, tj);
+        for (int i = 0; i < cols; ++i) {
+            const double x = (i - c_x) / f_x, y = (j - c_y) / f_y;
+            const double d = 0.09 + 0.04 * std::sin(0.05 * i) * std::cos(0.03 * j) + 0.02 * y;
+            const double gx = (v_true(0) - x * v_true(2)) * d + (-x * y * w_true(0) + (1 + x * x) * w_true(1) - y * w_true(2));
+            const double gy = (v_true(1) - y * v_true(2)) * d + (-(1 + y * y) * w_true(0) + x * y * w_true(1) + x * w_true(2));
+            const double fy = gy / (1.0 - gy * f_y / rows), a = 1.0 + fy * f_y / rows;
+            flow_image(j, i) = cv::Point_<double>(a * gx * f_x / gamma, fy * f_y / gamma);
+            const Eigen::Vector3d Xw = Rj.transpose() * (Eigen::Vector3d(x / d, y / d, 1.0 / d) - tj);
+            ux(j, i) = Xw(0); uy(j, i) = Xw(1); uz(j, i) = Xw(2);
+        }
+    }
+    camera.setCachedFlow(flow_image);
+    camera.setUnprojectionMaps(1, ux, uy, uz);
+    return camera;
+}
+
+int main(int argc, char **argv)
+{
+    const std::string PATH_RESULTS = argc > 1 ? argv[1] : "/tmp/rsdsfm_sweep";
+    const int rows = 180, cols = 240;
+    const int RANSAC_TRIALS = 6, NUM_EVALUATIONS = 2;
+    const bool USE_DEEP_FLOW = true, USE_CONST_ACC = false, USE_GLOBAL_SHUTTER = false, OPTIMIZE_RESULTS = true, SHOW_MSG = false;
+    double gamma = 0.9;
+    const double v[3] = {0.25, -0.04, 0.03}, w[3] = {0.003, -0.002, 0.006};
+
+    std::ofstream file_errors_out(PATH_RESULTS + "/errors.csv"), file_w_out(PATH_RESULTS + "/w.csv"), file_v_out(PATH_RESULTS + "/v.csv"),
+        file_k_out(PATH_RESULTS + "/k.csv"), file_reproject_error_out(PATH_RESULTS + "/reproject.csv"),
+        file_v_error_out(PATH_RESULTS + "/v_error.csv"), file_w_error_out(PATH_RESULTS + "/w_error.csv");
+    const std::string task = "synthetic_pair";
+
+    // ---- main.cc:245
+    error_measure::TrueValues true_values(Eigen::Vector3d(w[0], w[1], w[2]), Eigen::Vector3d(v[0], v[1], v[2]));
+    // ---- main.cc:262-265
+    Camera camera = setupCameraSynthetic(rows, cols, gamma, true_values.v, true_values.w);
+    camera.setGamma(gamma);
+    std::string image_path = PATH_RESULTS + "/depth_";
+    // ---- main.cc:271-273
+    error_measure::VelocityErrors errors = error_measure::evaluateVelocities(camera, true_values, gamma, RANSAC_TRIALS,
+                                                                             NUM_EVALUATIONS, USE_DEEP_FLOW,
+                                                                             USE_CONST_ACC, USE_GLOBAL_SHUTTER, OPTIMIZE_RESULTS, SHOW_MSG, image_path);
+    // ---- main.cc:275-283
+    file_errors_out << task << "," << errors.error_w << "," << errors.error_v << "," << errors.error_reproject << std::endl;
+    for (int j = 0; j < NUM_EVALUATIONS; j++) {
+        file_w_out << errors.w.col(j).transpose() << ",";
+        file_v_out << errors.v.col(j).transpose() << ",";
+        file_k_out << errors.k(j) << ",";
+        file_reproject_error_out << errors.error_reproject_vec(j) << ",";
+        file_v_error_out << errors.error_v_vec.col(j).transpose() << ",";
+        file_w_error_out << errors.error_w_vec.col(j).transpose() << ",";
+    }
+    file_w_out << std::endl;
+    file_errors_out.close(); file_w_out.close(); file_v_out.close(); file_k_out.close();
+    file_reproject_error_out.close(); file_v_error_out.close(); file_w_error_out.close();
+
+    // ---- checks: motion recovered on exact data, artefacts written and readable
+    bool ok = errors.error_w < 1e-6 && errors.error_v < 1e-4 && std::isfinite(errors.error_reproject) && errors.error_reproject < 0.5;
+    for (int j = 0; j < NUM_EVALUATIONS; ++j) {
+        ok = ok && errors.error_w_vec(0, j) < 1e-6 && errors.error_v_vec(0, j) < 1e-4 && errors.k(j) == 0.0;
+        cv::Mat depth_png = cv::imread(image_path + std::to_string(j) + ".png", 0);
+        ok = ok && depth_png.rows == rows && depth_png.cols == cols;
+        long painted = 0;
+        for (int y = 0; ok && y < rows; ++y) for (int x = 0; x < cols; ++x) painted += depth_png.at<unsigned char>(y, x) >= 10;
+        ok = ok && painted > (long)rows * cols * 9 / 10;
+        std::ifstream ply(image_path + std::to_string(j) + ".ply");
+        std::string first;
+        std::getline(ply, first);
+        ok = ok && first == "ply";
+    }
+    std::printf("error_w %.3e error_v %.3e error_reproject %.4e -> %s\n", errors.error_w, errors.error_v, errors.error_reproject, ok ? "ok" : "FAILED");
+    return ok ? 0 : 1;
+}

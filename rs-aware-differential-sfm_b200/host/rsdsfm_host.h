@@ -229,26 +229,47 @@ inline RansacValues ransacWithSamples(const Eigen::Array2Xd &q, const Eigen::Arr
                         best7[6]);
 }
 
-// Same draw as minimal.cc:226-244: srand(time(NULL)) before every trial, partial Fisher-Yates on a
-// persistent index vector with rand() % n_temp (Q5) -- then all trials are scored in one batch.
+// The 9-subsets of minimal.cc:226-244.  The reference keeps ONE permutation of 0..n-1 alive across all
+// trials and, per trial, moves 9 entries picked with rand() % (slots left) to the shrinking tail (Q5).
+// Given the same rand() stream the picks below are the same indices in the same order.  The stream
+// is seeded ONCE per call: the reference reseeds with time(NULL) before every trial, which only works
+// there because a trial takes seconds -- here all trials are drawn within microseconds and a per-trial
+// reseed would hand every trial the same nine values.
+class SubsetDrawer {
+public:
+    explicit SubsetDrawer(int n) : perm_((size_t)n) { for (int i = 0; i < n; ++i) perm_[(size_t)i] = i; }
+    // appends one trial (9 distinct point indices) to `out`; next_random() plays the role of rand()
+    template <class Rng>
+    void draw(Rng &&next_random, std::vector<int32_t> &out)
+    {
+        for (size_t left = perm_.size(), taken = 0; taken < 9; ++taken, --left) {
+            const size_t slot = (size_t)next_random() % left;
+            const int picked = perm_[slot];
+            perm_[slot] = perm_[left - 1];
+            perm_[left - 1] = picked;
+            out.push_back(picked);
+        }
+    }
+
+private:
+    std::vector<int> perm_;
+};
+
+// iterations x 9 point indices for minimal::ransac, drawn from the C library generator
+inline std::vector<int32_t> drawSamples(int n, int iterations)
+{
+    std::vector<int32_t> samples;
+    samples.reserve((size_t)9 * (iterations > 0 ? iterations : 0));
+    SubsetDrawer drawer(n);
+    srand((unsigned)time(NULL));
+    for (int trial = 0; trial < iterations; ++trial) drawer.draw([] { return rand(); }, samples);
+    return samples;
+}
+
 inline RansacValues ransac(const Eigen::Array2Xd &q, const Eigen::Array2Xd &u, const Eigen::ArrayXd &alpha,
                            const Eigen::ArrayXd &alpha_k, bool use_alpha_k, int iterations, double tolerance, bool show_messages)
 {
-    const int n = (int)q.cols();
-    std::vector<int> indices((size_t)n);
-    for (int i = 0; i < n; ++i) indices[(size_t)i] = i;
-    std::vector<int32_t> samples;
-    for (int i = 0; i < iterations; ++i) {
-        srand((unsigned)time(NULL));
-        int n_temp = n;
-        for (int j = 0; j < 9; ++j) {
-            const int random_choice = rand() % n_temp;
-            std::swap(indices[(size_t)n_temp - 1], indices[(size_t)random_choice]);
-            samples.push_back(indices[(size_t)n_temp - 1]);
-            n_temp--;
-        }
-    }
-    return ransacWithSamples(q, u, alpha, alpha_k, use_alpha_k, samples, tolerance, show_messages);
+    return ransacWithSamples(q, u, alpha, alpha_k, use_alpha_k, drawSamples((int)q.cols(), iterations), tolerance, show_messages);
 }
 inline RansacValues ransac(const Eigen::Array2Xd &q, const Eigen::Array2Xd &u, const Eigen::ArrayXd &alpha, int iterations,
                            double tolerance, bool show_messages)
@@ -542,36 +563,28 @@ public:
         return f1.trueFlowTo(frames_[(size_t)frameNr2 - 1]);
     }
 
-    // camera.cc:423-491: ASCII PLY of the back-projected 3D points (world frame) coloured by the RS image,
-    // row-major vertex order, 9 significant digits, BGR written as RGB
+    // camera.cc:423-491: ASCII PLY of the back-projected 3D points (world frame) coloured by the RS image.
+    // File format (fixed by the reference's output): the 11 header lines below, then one vertex per pixel
+    // in raster order as "x y z r g b": coordinates with 9 significant digits, each followed by a blank,
+    // colour as decimal RGB (the image is BGR) separated by single blanks.
     void createPointCloud(const int frameNr, const std::string fileName)
     {
         RsFrame frame = frames_[(size_t)frameNr - 1];
-        cv::Mat coordinates = frame.get3dCoordinates();
-        cv::Mat colors = frame.getRsImage();
-        const int rows = frame.getRows(), cols = frame.getCols();
-        if (coordinates.rows != rows || coordinates.cols != cols) throw std::runtime_error("createPointCloud: backProject has not run");
-        const float *pData = reinterpret_cast<const float *>(coordinates.data);
-        const unsigned char *pColor = colors.data;
-        const unsigned long number_iterations = 3ul * (unsigned long)rows * (unsigned long)cols;
-        std::ofstream outputfile(fileName);
-        outputfile << "ply" << std::endl
-                   << "format ascii 1.0" << std::endl
-                   << "comment PLY File created by RS aware SfM wrapper" << std::endl
-                   << "element vertex " << (unsigned long)rows * (unsigned long)cols << std::endl
-                   << "property float x" << std::endl
-                   << "property float y" << std::endl
-                   << "property float z" << std::endl
-                   << "property uchar red" << std::endl
-                   << "property uchar green" << std::endl
-                   << "property uchar blue" << std::endl
-                   << "end_header" << std::endl;
-        for (unsigned long i = 0; i < number_iterations; i += 3) {
-            for (unsigned int j = 0; j < 3; j++) outputfile << std::setprecision(9) << pData[i + j] << " ";
-            for (int j = 2; j >= 0; j--) outputfile << (unsigned short)pColor[i + j] << (j == 0 ? "" : " ");
-            outputfile << "\n";
-        }
-        outputfile.close();
+        const cv::Mat xyz = frame.get3dCoordinates(), bgr = frame.getRsImage();
+        const size_t vertices = (size_t)frame.getRows() * (size_t)frame.getCols();
+        if ((size_t)xyz.rows * (size_t)xyz.cols != vertices) throw std::runtime_error("createPointCloud: backProject has not run");
+        static const char *const properties[] = {"float x", "float y", "float z", "uchar red", "uchar green", "uchar blue"};
+        std::ofstream ply(fileName);
+        ply << "ply\nformat ascii 1.0\ncomment PLY File created by RS aware SfM wrapper\nelement vertex " << vertices << "\n";
+        for (const char *p : properties) ply << "property " << p << "\n";
+        ply << "end_header" << std::endl;
+        ply << std::setprecision(9);
+        const float *point = reinterpret_cast<const float *>(xyz.data);
+        const unsigned char *colour = bgr.data;
+        for (size_t vtx = 0; vtx < vertices; ++vtx, point += 3, colour += 3)
+            ply << point[0] << ' ' << point[1] << ' ' << point[2] << ' ' << (unsigned)colour[2] << ' ' << (unsigned)colour[1] << ' '
+                << (unsigned)colour[0] << '\n';
+        ply.close();
         std::cout << "Point cloud file " << fileName << " created." << std::endl;
     }
     // camera.cc:99-176: A.csv, the 3 x 3 intrinsic matrix
@@ -647,16 +660,32 @@ private:
 // ---------------------------------------------------------------------------- errorMeasure.h:18-64
 namespace error_measure {
 
+// errorMeasure.h:18-24 (constructed as TrueValues(w, v), main.cc:245)
 struct TrueValues {
-    Eigen::Vector3d v, w;
-    double k;
-    TrueValues(Eigen::Vector3d v_init, Eigen::Vector3d w_init, double k_init) : v(v_init), w(w_init), k(k_init) {}
+    Eigen::Vector3d w;
+    Eigen::Vector3d v;
+    TrueValues(Eigen::Vector3d w_init, Eigen::Vector3d v_init) : w(w_init), v(v_init) {}
 };
 
+// errorMeasure.h:29-44: same members, same constructor (read by main.cc:275-283 as .col(j) / (j)).
+// The reference hands its per-evaluation scalar errors (ArrayXd) to the Array3Xd members (Q23, a shape
+// bug: only column 0 is defined there).  evaluateVelocities below fills well-formed 3 x num_evaluations
+// arrays instead: column j = (error of evaluation j, 0, 0).
 struct VelocityErrors {
-    std::vector<Eigen::Vector3d> w, v;          // per evaluation
-    Eigen::ArrayXd k, mean_error, v_error, w_error;   // stored as ArrayXd (Q23)
-    double average_w_error = 0, average_v_error = 0, average_mean_error = 0;
+    Eigen::Array3Xd w;
+    Eigen::Array3Xd v;
+    Eigen::ArrayXd k;
+    Eigen::ArrayXd error_reproject_vec;
+    Eigen::Array3Xd error_v_vec;
+    Eigen::Array3Xd error_w_vec;
+    double error_w;
+    double error_v;
+    double error_reproject;
+    VelocityErrors(Eigen::Array3Xd w_init, Eigen::Array3Xd v_init, Eigen::ArrayXd k_init, Eigen::ArrayXd error_reproject_vec_init,
+                   Eigen::Array3Xd error_v_vec_init, Eigen::Array3Xd error_w_vec_init, double error_w_init, double error_v_init,
+                   double error_reproject_init)
+        : w(w_init), v(v_init), k(k_init), error_reproject_vec(error_reproject_vec_init), error_v_vec(error_v_vec_init),
+          error_w_vec(error_w_vec_init), error_w(error_w_init), error_v(error_v_init), error_reproject(error_reproject_init) {}
 };
 
 // The flatten + normalise glue both reference drivers share (main.cc:398-432, errorMeasure.cpp:66-97).
@@ -679,11 +708,13 @@ inline Flattened flattenFlow(const cv::Mat_<cv::Point_<double>> &flow_image, con
     return F;
 }
 
-// errorMeasure.cpp:41-254 with the GT reprojection metric (section 8f, not on the hot path) left out:
-// mean_error entries are NaN.
+// errorMeasure.cpp:41-254.  image_path: prefix of the per-evaluation artefacts "<prefix><eval>.png" (8-bit depth
+// image, :191-206) and "<prefix><eval>.ply" (:229-230); an EMPTY prefix writes no files (the reference has no
+// such switch: it always writes).  The reprojection error (:229) needs the frame's ground truth (unprojection
+// maps and scanline poses, attached or loaded from the fixture CSVs); without it the entry is NaN.
 inline VelocityErrors evaluateVelocities(Camera camera, TrueValues true_values, double gamma, int ransac_trials, int num_evaluations,
                                          bool use_deep_flow, bool constant_acceleration, bool global_shutter,
-                                         bool optimize_results, bool show_messages, std::string /*image_path*/)
+                                         bool optimize_results, bool show_messages, std::string image_path)
 {
     const double THRESHOLD_FLOW = 0.0000000001, TOL_RANSAC = 0.05;
     cv::Mat_<cv::Point_<double>> flow_image = use_deep_flow ? camera.calculateDeepFlow(1, 2) : camera.calculateTrueFlow(1, 2);
@@ -692,12 +723,22 @@ inline VelocityErrors evaluateVelocities(Camera camera, TrueValues true_values, 
     const double f_x = K(0, 0), f_y = K(1, 1), c_x = K(0, 2), c_y = K(1, 2);
     camera.setGamma(gamma);
     Flattened F = flattenFlow(flow_image, K, gamma, THRESHOLD_FLOW, true);
+    // alpha factors from the un-truncated pixel-unit arrays (errorMeasure.cpp:104-105); entries >= n are never read
     Eigen::ArrayXd alpha = minimal::getAlpha(F.flow_pixel, rows, gamma);
     Eigen::ArrayXd alphaK = minimal::getAlphaK(F.coord_pixel, F.flow_pixel, rows, gamma);
     if (global_shutter) { alpha *= 0; alpha += 1; constant_acceleration = false; }
-    VelocityErrors E;
-    E.k = Eigen::ArrayXd::Zero(num_evaluations); E.mean_error = E.k; E.v_error = E.k; E.w_error = E.k;
+    Eigen::ArrayXd v_errors = Eigen::ArrayXd::Zero(num_evaluations), w_errors = Eigen::ArrayXd::Zero(num_evaluations),
+                   mean_errors = Eigen::ArrayXd::Zero(num_evaluations), k = Eigen::ArrayXd::Zero(num_evaluations);
+    Eigen::Array3Xd w = Eigen::Array3Xd::Zero(3, num_evaluations), v = Eigen::Array3Xd::Zero(3, num_evaluations);
     const double true_v_norm = true_values.v.norm();
+    // first-order "rotations" I + [w]x of errorMeasure.cpp:127-129, :180-183
+    auto rot = [](const Eigen::Vector3d &r) {
+        Eigen::Matrix3d R = Eigen::Matrix3d::Identity();
+        R(0, 1) = -r(2); R(0, 2) = r(1); R(1, 0) = r(2); R(1, 2) = -r(0); R(2, 0) = -r(1); R(2, 1) = r(0);
+        return R;
+    };
+    const Eigen::Matrix3d true_rot_t = rot(true_values.w).transpose();
+    const bool have_ground_truth = camera.getFrame(1).hasUnprojectionMaps();
     for (int eval_num = 0; eval_num < num_evaluations; eval_num++) {
         RansacValues ransac_results = minimal::ransac(F.coord, F.flow, alpha, alphaK, constant_acceleration, ransac_trials, TOL_RANSAC, show_messages);
         RansacValues results = ransac_results;
@@ -705,29 +746,49 @@ inline VelocityErrors evaluateVelocities(Camera camera, TrueValues true_values, 
         double z_count = 0;
         for (int i = 0; i < results.num_inliers; i++) z_count += results.inliers(2, i);
         if (z_count * 1.0 / results.num_inliers < 0) { results.inliers.row(2) *= -1.0; results.v *= -1.0; }
-        E.w.push_back(results.w); E.v.push_back(results.v); E.k(eval_num) = results.k;
-        // rotation error |vee(R_est R_true^T)|, translation angle (errorMeasure.cpp:173-186)
-        auto rot = [](const Eigen::Vector3d &w) {
-            Eigen::Matrix3d R = Eigen::Matrix3d::Identity();
-            R(0, 1) = -w(2); R(0, 2) = w(1); R(1, 0) = w(2); R(1, 2) = -w(0); R(2, 0) = -w(1); R(2, 1) = w(0);
-            return R;
-        };
-        const Eigen::Matrix3d Re = rot(results.w), Rt = rot(true_values.w).transpose();
-        auto mm = [&](int r, int c) { return Re(r, 0) * Rt(0, c) + Re(r, 1) * Rt(1, c) + Re(r, 2) * Rt(2, c); };
-        E.w_error(eval_num) = Eigen::Vector3d(mm(2, 1), mm(0, 2), mm(1, 0)).norm();
-        E.v_error(eval_num) = std::acos(results.v.dot(true_values.v) / (results.v.norm() * true_v_norm));
+        for (int a = 0; a < 3; ++a) { w(a, eval_num) = results.w(a); v(a, eval_num) = results.v(a); }
+        k(eval_num) = results.k;
+        const Eigen::Matrix3d Re = rot(results.w);
+        auto err_rot = [&](int r, int c) { return Re(r, 0) * true_rot_t(0, c) + Re(r, 1) * true_rot_t(1, c) + Re(r, 2) * true_rot_t(2, c); };
+        w_errors(eval_num) = Eigen::Vector3d(err_rot(2, 1), err_rot(0, 2), err_rot(1, 0)).norm();
+        v_errors(eval_num) = std::acos(results.v.dot(true_values.v) / (results.v.norm() * true_v_norm));
+        // depth range with the reference's start values (errorMeasure.cpp:187-197), 8-bit depth image, depth map
+        double z_min = 100000, z_max = 0;
+        for (int i = 0; i < results.num_inliers; ++i) {
+            if (results.inliers(2, i) < z_min) z_min = results.inliers(2, i);
+            if (results.inliers(2, i) > z_max) z_max = results.inliers(2, i);
+        }
+        const double multiplier = 244.0 / (z_max - z_min);
+        cv::Mat depth_est(rows, cols, CV_8UC1, cv::Scalar(0));
         Eigen::MatrixXd depth_map = Eigen::MatrixXd::Zero(rows, cols);
         for (int i = 0; i < results.num_inliers; i++) {
             const int x = int(f_x * results.inliers(0, i) + c_x + 0.5), y = int(f_y * results.inliers(1, i) + c_y + 0.5);
-            if (x >= 0 && x < cols && y >= 0 && y < rows) depth_map(y, x) = results.inliers(2, i);
+            if (x < 0 || x >= cols || y < 0 || y >= rows) continue;       // the reference writes out of bounds here
+            depth_est.at<unsigned char>(y, x) = (unsigned char)(10 + int((results.inliers(2, i) - z_min) * multiplier));
+            depth_map(y, x) = results.inliers(2, i);
         }
+        if (!image_path.empty()) cv::imwrite(image_path + std::to_string(eval_num) + ".png", depth_est);
         camera.setPose(1, results.k, results.v, results.w);
         camera.setDepthMap(1, depth_map);
         if (global_shutter) camera.backProjectGs(1); else camera.backProject(1);
-        E.mean_error(eval_num) = std::nan("");
+        mean_errors(eval_num) = have_ground_truth ? camera.meanReprojectionError(1) : std::nan("");
+        if (!image_path.empty()) camera.createPointCloud(1, image_path + std::to_string(eval_num) + ".ply");
+        if (show_messages)
+            std::cout << std::endl << "The rotation error for the current evaluation is " << w_errors(eval_num) << std::endl
+                      << "The translation error for the current evaluation is " << v_errors(eval_num) << std::endl
+                      << "The reprojection error for the current evaluation is " << mean_errors(eval_num) << std::endl;
+        else
+            std::cout << "Finished evaluation " << eval_num + 1 << "/" << num_evaluations << ". error_w = " << w_errors(eval_num)
+                      << ". error_v = " << v_errors(eval_num) << ". reprojection error = " << mean_errors(eval_num) << std::endl;
     }
-    E.average_v_error = E.v_error.mean(); E.average_w_error = E.w_error.mean(); E.average_mean_error = std::nan("");
-    return E;
+    const double ave_v_error = v_errors.mean(), ave_w_error = w_errors.mean(), ave_mean_error = mean_errors.mean();
+    std::cout << std::endl << "The average rotation error is " << ave_w_error << std::endl
+              << "The average translation error is " << ave_v_error << std::endl
+              << "The average reprojection error is " << ave_mean_error << std::endl;
+    // Q23: the Array3Xd error members get one well-formed column per evaluation
+    Eigen::Array3Xd v_err3 = Eigen::Array3Xd::Zero(3, num_evaluations), w_err3 = Eigen::Array3Xd::Zero(3, num_evaluations);
+    for (int j = 0; j < num_evaluations; ++j) { v_err3(0, j) = v_errors(j); w_err3(0, j) = w_errors(j); }
+    return VelocityErrors(w, v, k, mean_errors, v_err3, w_err3, ave_w_error, ave_v_error, ave_mean_error);
 }
 
 }  // namespace error_measure

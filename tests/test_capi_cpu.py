@@ -115,3 +115,23 @@ def test_host_relocate_pose_matches_oracle(capi, oracle):
     assert np.array_equal(Rr, Ro) and np.array_equal(tr, to)
     assert np.array_equal(Rr[0], R[0]) and np.array_equal(tr[0], t[0])
     assert np.allclose(Rr[1], np.linalg.inv(R[0]) @ R[1], rtol=1e-12, atol=1e-14) and np.allclose(tr[5], t[5] - t[0])
+
+
+def _build_host_program(capi, name):
+    host = os.path.join(ROOT, "rs-aware-differential-sfm_b200", "host")
+    exe = os.path.join(host, name)
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", host, os.path.join(host, name + ".cc"),
+           "-L", os.path.dirname(capi.LIB_PATH), "-lrsdsfm", "-Wl,-rpath," + os.path.dirname(capi.LIB_PATH), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_host_shim_pieces_that_need_no_gpu(capi, tmp_path):
+    """minimal::drawSamples gives every trial its own sample (ADVICE r1: a per-trial srand(time) repeated
+    one), SubsetDrawer follows minimal.cc:226-244 for a given rand() stream, the stand-in
+    cv::imwrite / cv::imread round-trip, TrueValues / VelocityErrors have the errorMeasure.h:18-44 shape."""
+    exe = _build_host_program(capi, "host_cpu_check")
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok" in r.stdout

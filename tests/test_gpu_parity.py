@@ -107,6 +107,20 @@ def test_estimate_inverse_depths(ctx, oracle, case_cv):
     _depth_close(got, ref)
 
 
+def test_zero_start_gradient_converges_at_iteration_zero(ctx, oracle, case_cv):
+    """Ceres' IterationZero ends with step_is_successful = true, so the gradient tolerance is tested before
+    any step: with v = 0 the depth column e = -beta A v vanishes, the gradient is exactly 0 and the solve
+    stops with CONVERGENCE / gradient tolerance, 0 iterations, depths at their start value 1."""
+    c = case_cv
+    z3 = np.zeros(3)
+    ref, sref = oracle.estimate_inverse_depths(c["coord"], c["flow"], c["n"], z3, c["ransac"]["w"], 0.0, c["alpha"], c["alpha_k"])
+    got, sgot = ctx.estimate_inverse_depths(c["coord"], c["flow"], c["n"], z3, c["ransac"]["w"], 0.0, c["alpha"], c["alpha_k"])
+    assert sref["termination"] == 0 and sref["reason"] == 3 and sref["iterations"] == 0 and sref["num_successful"] == 1
+    for key in ("termination", "reason", "iterations", "num_successful", "num_unsuccessful"):
+        assert sgot[key] == sref[key], key
+    assert np.array_equal(np.asarray(got), np.ones(c["n"])) and np.array_equal(ref, np.ones(c["n"]))
+
+
 # ---------------------------------------------------------------------------- refinement
 @pytest.mark.parametrize("which,pairing", [("cv", "reference"), ("cv", "fixed"), ("ca", "reference"), ("ca", "fixed")])
 def test_refine_matches_oracle(ctx, oracle, case_cv, case_ca, which, pairing):
@@ -258,6 +272,28 @@ def test_cpp_host_shim_single_run(capi):
     assert "rectified image" in r.stdout
 
 
+def test_cpp_sweep_driver_evaluate_velocities(capi, tmp_path):
+    """host/example_sweep.cc: the body of the reference's sweep driver (main.cc:245, :271-287) -- TrueValues(w, v),
+    error_measure::evaluateVelocities with the reference's argument list, VelocityErrors read member by member
+    -- compiled against the shim and run on the GPU: motion recovered on exact data, reprojection error
+    wired (errorMeasure.cpp:229), depth PNGs and point clouds written per evaluation."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "rs-aware-differential-sfm_b200", "host")
+    exe = os.path.join(host, "example_sweep")
+    cmd = ["g++", "-std=c++17", "-O2", "-I", os.path.join(root, "include"), "-I", host, os.path.join(host, "example_sweep.cc"),
+           "-L", os.path.dirname(capi.LIB_PATH), "-lrsdsfm", "-Wl,-rpath," + os.path.dirname(capi.LIB_PATH), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    errs = open(os.path.join(str(tmp_path), "errors.csv")).read().strip().split(",")
+    assert errs[0] == "synthetic_pair" and len(errs) == 4 and all(np.isfinite(float(x)) for x in errs[1:])
+    # two evaluations, three values each: "a b c,a b c,"
+    assert len(open(os.path.join(str(tmp_path), "w.csv")).read().strip().strip(",").split(",")) == 2
+
+
 # ---------------------------------------------------------------------------- sequence / whole-pipeline drivers
 def _seq_pairs(oracle, synth, n_pairs, const_acc):
     cases = []
@@ -369,6 +405,38 @@ def test_pipeline_pair_equals_stagewise_calls(ctx, oracle, case_cv, case_ca, whi
         assert np.array_equal(got["v"], ref["v"]) and np.array_equal(got["w"], ref["w"]) and got["k"] == ref["k"]
         assert np.array_equal(host(got["depth_map"]), ref["depth_map"].cpu().numpy())
         assert np.array_equal(host(got["rectified"]), ref["rectified"].cpu().numpy())
+
+
+def test_pipeline_emulate_padding_follows_main_cc(ctx, oracle, synth):
+    """main.cc:398-447 never truncates the flattened arrays: the rows*cols - n tail columns
+    (coord = (1,1), flow = 0, alpha = 1) are sampled, scored and can become inliers.  With emulate_padding
+    the one-call driver works on that point set; compared with the oracle stages run on the padded arrays."""
+    rows, cols = 96, 128
+    K4 = helpers.small_K(12)
+    gamma = 0.95
+    P = synth.make_pair(rows, cols, K4, gamma=gamma, seed=31, k=0.0, noise_sigma_px=0.1, outlier_frac=0.05, zero_flow_frac=0.3)
+    tot = rows * cols
+    n, coord, flow, cpx, fpx = oracle.flatten(P["flow_img"], K4, gamma)
+    assert n < tot
+    alpha = oracle.get_alpha(fpx, tot, rows, gamma)
+    alpha_k = oracle.get_alpha_k(cpx, fpx, tot, rows, gamma)
+    samples = synth.sample_list(tot, 8, seed=5)
+    samples[3, :4] = [tot - 1, tot - 2, n, n + 1]            # a trial that draws phantom points
+    R = oracle.ransac(coord, flow, alpha, alpha_k, tot, False, 0.01, samples=samples)
+    inl, a_in, ak_in = oracle.gather_inliers(coord, alpha, alpha_k, tot, R["mask"], R["inv_depth"])
+    m = len(a_in)
+    ref = oracle.refine_rectify(flow, inl, a_in, ak_in, m, R["v"], R["w"], R["k"], False, False, P["image"], K4, gamma)
+    got = ctx.pipeline_pair(P["flow_img"], P["image"], K4, gamma, 0.01, False, samples=samples, emulate_padding=True)
+    assert got["n"] == n and got["m"] == m and got["best_idx"] == R["best_idx"]
+    assert np.array_equal(got["ransac_v"], R["v"]) and np.array_equal(got["ransac_w"], R["w"])
+    _motion_close(got["w"], ref["w"], "w")
+    _motion_close(got["v"], ref["v"], "v")
+    assert got["summary"]["iterations"] == ref["summary"]["iterations"]
+    diff = np.abs(got["rectified"].astype(np.int32) - ref["rectified"].astype(np.int32)).max(axis=2)
+    assert (diff <= 1).mean() >= 0.999
+    # and without the flag the point set is the n kept vectors
+    plain = ctx.pipeline_pair(P["flow_img"], P["image"], K4, gamma, 0.01, False, samples=synth.sample_list(n, 8, seed=5))
+    assert plain["n"] == n and plain["m"] <= n
 
 
 def test_pipeline_no_refinement_and_gs_mode(ctx, oracle, case_cv):
