@@ -98,9 +98,12 @@ int main(int argc, char **argv)
     file_reproject_error_out.close(); file_v_error_out.close(); file_w_error_out.close();
 
     // ---- checks: motion recovered on exact data, artefacts written and readable
-    bool ok = errors.error_w < 1e-6 && errors.error_v < 1e-4 && std::isfinite(errors.error_reproject) && errors.error_reproject < 0.5;
+    // (the reference's rotation error |vee((I + [w]x)(I + [w_true]x)^T)| is of second order in |w| even for the exact
+    //  w -- about 2e-5 here -- so the recovered w is compared with the truth directly as well)
+    bool ok = errors.error_w < 1e-4 && errors.error_v < 1e-4 && std::isfinite(errors.error_reproject) && errors.error_reproject < 0.5;
     for (int j = 0; j < NUM_EVALUATIONS; ++j) {
-        ok = ok && errors.error_w_vec(0, j) < 1e-6 && errors.error_v_vec(0, j) < 1e-4 && errors.k(j) == 0.0;
+        for (int a = 0; a < 3; ++a) ok = ok && std::fabs(errors.w.col(j)(a) - w[a]) < 1e-6;
+        ok = ok && errors.error_w_vec(0, j) < 1e-4 && errors.error_v_vec(0, j) < 1e-4 && errors.k(j) == 0.0;
         cv::Mat depth_png = cv::imread(image_path + std::to_string(j) + ".png", 0);
         ok = ok && depth_png.rows == rows && depth_png.cols == cols;
         long painted = 0;
