@@ -277,6 +277,36 @@ RSDSFM_API int rsdsfm_refine_rectify_sequence(rsdsfm_ctx *ctx, int mem, int n_pa
                           int const_acceleration, int gs_mode, int rows, int cols, const double *K4,
                           double gamma, int layout);
 
+/* ---- the same step fed with what minimal::ransac returned: the compact host interface --------- */
+/* The inputs of the step are the cached flow field, the RS frame and the RANSAC result.  The expanded arrays
+ * the reference passes around between main.cc:398 and :457 (normalised coordinates, gamma-scaled flow,
+ * alpha / alpha_k, the consensus set as x, y, z triples) are functions of the flow field and of the winner's
+ * consensus mask and inverse depths, so this entry point takes those -- exactly the outputs of rsdsfm_ransac --
+ * and rebuilds the rest on the device, bit-identical to the stage-wise calls (same residual pairing as
+ * nonlinearRefinement.cc:209-216).  Per 1080p pair 58 MB cross the host link upwards instead of 122 MB
+ * (42 MB with float32 flow), and 23 MB come back instead of 39 MB when the depth map is not requested. */
+typedef struct rsdsfm_compact_pair_io {
+    const void *flow_img;          /* rows*cols*2 (dx, dy) row-major: doubles, or floats with flow_f32 (DeepFlow's
+                                    * output is float32 widened to double, camera.cc:262-274: lossless) */
+    const uint8_t *image;          /* rows*cols*3 */
+    const uint8_t *mask;           /* n: consensus mask over the flattened points (rsdsfm_ransac mask_best) */
+    const double *inv_depth;       /* n: the winner's inverse depths (rsdsfm_ransac inv_depth_best) */
+    int n, m;                      /* flattened points (rsdsfm_flatten *n_out), consensus-set size (number of mask
+                                    * entries set); checked on the device: a mismatch fails the pair with RSDSFM_ERR_ARG */
+    int status;                    /* out */
+    double v[3], w[3], k;          /* in: the RANSAC winner; out: refined, sign-fixed */
+    double *z_out;                 /* m: refined, sign-fixed depths in consensus-set order */
+    double *depth_map;             /* rows*cols, or NULL: not wanted */
+    uint8_t *rectified;            /* rows*cols*3 */
+    rsdsfm_lm_summary summary;     /* out */
+} rsdsfm_compact_pair_io;
+
+/* Pipelined like rsdsfm_refine_rectify_sequence (host buffers: upload i+1 | compute i | download i-1; device
+ * buffers: two compute lanes).  flow_threshold: the |flow|^2 cut of the flattening (1e-10 in the reference). */
+RSDSFM_API int rsdsfm_refine_rectify_compact_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm_compact_pair_io *pairs,
+                          int flow_f32, double flow_threshold, int const_acceleration, int gs_mode, int rows, int cols,
+                          const double *K4, double gamma, int layout);
+
 /* ---- a2..a15 in one call: evaluateSingleRun's compute (main.cc:398-523) --------------------- */
 typedef struct rsdsfm_pipeline_params {
     int rows, cols;

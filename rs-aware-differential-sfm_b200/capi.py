@@ -20,7 +20,7 @@ EXPORTS = [
     "rsdsfm_synchronize", "rsdsfm_launch_count", "rsdsfm_profile_enable", "rsdsfm_profile_read", "rsdsfm_profile_detail", "rsdsfm_flatten", "rsdsfm_alpha", "rsdsfm_solve9",
     "rsdsfm_ransac_score", "rsdsfm_ransac", "rsdsfm_gather_inliers", "rsdsfm_estimate_inverse_depths",
     "rsdsfm_refine", "rsdsfm_depth_glue", "rsdsfm_set_relative_pose", "rsdsfm_backproject", "rsdsfm_fill_cracks",
-    "rsdsfm_refine_rectify", "rsdsfm_refine_rectify_sequence", "rsdsfm_pipeline_pair", "rsdsfm_pipeline_sequence",
+    "rsdsfm_refine_rectify", "rsdsfm_refine_rectify_sequence", "rsdsfm_refine_rectify_compact_sequence", "rsdsfm_pipeline_pair", "rsdsfm_pipeline_sequence",
     "rsdsfm_relocate_pose", "rsdsfm_reprojection_error", "rsdsfm_true_flow", "rsdsfm_host_alloc", "rsdsfm_host_free",
 ]
 
@@ -48,6 +48,15 @@ class PairIO(C.Structure):
     """rsdsfm_pair_io (include/rsdsfm.h)."""
     _fields_ = [("flow", C.c_void_p), ("inliers3", C.c_void_p), ("alpha", C.c_void_p), ("alpha_k", C.c_void_p),
                 ("image", C.c_void_p), ("m", C.c_int), ("status", C.c_int),
+                ("v", C.c_double * 3), ("w", C.c_double * 3), ("k", C.c_double),
+                ("z_out", C.c_void_p), ("depth_map", C.c_void_p), ("rectified", C.c_void_p),
+                ("summary", LmSummary)]
+
+
+class CompactPairIO(C.Structure):
+    """rsdsfm_compact_pair_io (include/rsdsfm.h)."""
+    _fields_ = [("flow_img", C.c_void_p), ("image", C.c_void_p), ("mask", C.c_void_p), ("inv_depth", C.c_void_p),
+                ("n", C.c_int), ("m", C.c_int), ("status", C.c_int),
                 ("v", C.c_double * 3), ("w", C.c_double * 3), ("k", C.c_double),
                 ("z_out", C.c_void_p), ("depth_map", C.c_void_p), ("rectified", C.c_void_p),
                 ("summary", LmSummary)]
@@ -409,6 +418,61 @@ class Context:
             e = arr[i]
             z, dm, rect = outs[i]
             res.append(dict(v=np.array(e.v[:]), w=np.array(e.w[:]), k=float(e.k), z=z, depth_map=dm, rectified=rect,
+                            summary=e.summary.as_dict(), status=int(e.status)))
+        self._ck(rc)
+        return res
+
+    def refine_rectify_compact_sequence(self, pairs, const_acc, gs_mode, K4, gamma, layout=DEPTH_COLMAJOR, thr=1e-10,
+                                        want_depth_map=True):
+        """rsdsfm_refine_rectify_compact_sequence.  `pairs`: list of dicts with flow_img (rows x cols x 2, float64 or
+        float32 -- all pairs alike), image, mask (n, uint8), inv_depth (n), n, m, v, w, k and optionally
+        out=(z, depth_map or None, rectified).  numpy (pinned) = host, torch CUDA = device."""
+        n = len(pairs)
+        arr = (CompactPairIO * max(n, 1))()
+        keep, outs, mems = [], [], set()
+        rows = cols = 0
+        f32 = None
+        for i, p in enumerate(pairs):
+            fi, image, mask, invd = p["flow_img"], p["image"], p["mask"], _f64(p["inv_depth"])
+            is32 = str(fi.dtype).endswith("float32")
+            f32 = is32 if f32 is None else f32
+            assert is32 == f32, "all pairs must store the flow alike"
+            rows, cols = int(image.shape[0]), int(image.shape[1])
+            m = int(p["m"])
+            if _is_torch(fi):
+                import torch
+                assert fi.is_cuda and fi.is_contiguous() and mask.is_contiguous() and str(mask.dtype) == "torch.uint8"
+            else:
+                fi = np.ascontiguousarray(fi); image = np.ascontiguousarray(image, dtype=np.uint8)
+                mask = np.ascontiguousarray(mask, dtype=np.uint8)
+            if p.get("out") is not None:
+                z, dm, rect = p["out"]
+            elif _is_torch(fi):
+                import torch
+                z = torch.empty(max(m, 1), dtype=torch.float64, device=fi.device)
+                dm = torch.empty(rows * cols, dtype=torch.float64, device=fi.device) if want_depth_map else None
+                rect = torch.empty_like(image)
+            else:
+                z = np.empty(max(m, 1)); dm = np.empty(rows * cols) if want_depth_map else None; rect = np.empty_like(image)
+            mems.add(_mem(fi, image, mask, invd, z, dm, rect))
+            keep.append((fi, image, mask, invd))
+            outs.append((z, dm, rect))
+            e = arr[i]
+            e.flow_img, e.image, e.mask, e.inv_depth = (_ptr(x).value for x in (fi, image, mask, invd))
+            e.n, e.m = int(p["n"]), m
+            e.v[:] = list(_small(p["v"], 3)); e.w[:] = list(_small(p["w"], 3)); e.k = float(p["k"])
+            e.z_out, e.rectified = _ptr(z).value, _ptr(rect).value
+            e.depth_map = _ptr(dm).value if dm is not None else None
+        if len(mems) > 1:
+            raise ValueError("mixing host and device pairs in one sequence")
+        K4 = _small(K4, 4)
+        rc = self.lib.rsdsfm_refine_rectify_compact_sequence(self.h, mems.pop() if mems else HOST, n, arr, int(bool(f32)), C.c_double(thr),
+                                                             int(const_acc), int(gs_mode), rows, cols, _ptr(K4), C.c_double(gamma), int(layout))
+        res = []
+        for i in range(n):
+            e = arr[i]
+            z, dm, rect = outs[i]
+            res.append(dict(v=np.array(e.v[:]), w=np.array(e.w[:]), k=float(e.k), z=z[:e.m], depth_map=dm, rectified=rect,
                             summary=e.summary.as_dict(), status=int(e.status)))
         self._ck(rc)
         return res

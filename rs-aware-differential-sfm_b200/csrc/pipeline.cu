@@ -6,6 +6,7 @@
 // Everything here composes the stage functions of stages.h; there is no arithmetic in this file
 // apart from the reference's sample draw (minimal.cc:226-244) on the host.
 #include <unordered_map>
+#include <vector>
 
 #include "stages.h"
 
@@ -21,6 +22,13 @@ struct StepArgs {
     double gamma;
     double *z, *depth_map;
     uint8_t *rectified;
+    // compact inputs (rsdsfm_refine_rectify_compact*): set flow_img and leave flow .. alpha_k NULL
+    const void *flow_img = nullptr;
+    int flow_f32 = 0;
+    const uint8_t *mask = nullptr;
+    const double *inv_depth = nullptr;
+    int n = 0;
+    double flow_threshold = 0.0;
 };
 
 // Queues the whole step on ctx->stream, including the small read-backs (LM control block, depth
@@ -37,9 +45,26 @@ static int queue_step(rsdsfm_ctx *ctx, const StepArgs &a, const double *v, const
     // (the solve's epilogue also leaves the per-CTA sums of z the sign fix needs)
     RS_TRY(ensure(ctx, ctx->sums, sizeof(double) * 3 * (size_t)ctx->num_sms));
     double *zrows = (double *)ctx->sums.p;
-    RS_TRY(refine_async(ctx, a.flow, a.inliers3, a.alpha, a.alpha_k, a.m, v, w, k, a.const_acc, a.flow_index, nullptr, a.z, zrows));
+    const double *xyz = a.inliers3;
+    int xs = 3;
+    if (a.flow_img) {
+        // compact inputs: coordinates, alpha factors, pairing and start depths are rebuilt on the device, straight
+        // into the solver's layout (no expanded arrays ever exist)
+        const size_t mm = (size_t)(a.m > 0 ? a.m : 1);
+        RS_TRY(ensure(ctx, ctx->pipe[14], sizeof(double) * mm));          // start depths z (restored on FAILURE)
+        RS_TRY(ensure(ctx, ctx->pipe[15], sizeof(double) * 2 * mm));      // normalised coordinates of the inliers
+        void *blk = nullptr; double *d0 = nullptr; int *flag = nullptr;
+        RS_TRY(lm_input_buffers(ctx, a.m, &blk, &d0, &flag));
+        RS_TRY(compact_build_device(ctx, a.flow_img, a.flow_f32, a.rows, a.cols, a.K4, a.gamma, a.flow_threshold, a.mask, a.inv_depth,
+                                    a.n, a.m, blk, d0, (double *)ctx->pipe[14].p, (double *)ctx->pipe[15].p, flag));
+        RS_TRY(refine_prepared_async(ctx, a.m, v, w, k, a.const_acc, nullptr, (const double *)ctx->pipe[14].p, a.z, zrows));
+        xyz = (const double *)ctx->pipe[15].p;
+        xs = 2;
+    } else {
+        RS_TRY(refine_async(ctx, a.flow, a.inliers3, a.alpha, a.alpha_k, a.m, v, w, k, a.const_acc, a.flow_index, nullptr, a.z, zrows));
+    }
     // sign fix + depth raster (main.cc:466-509)
-    RS_TRY(glue_device(ctx, a.z, 1, a.inliers3, 3, a.m, a.K4, a.rows, a.cols, INFINITY, a.layout, a.depth_map, nullptr, stats,
+    RS_TRY(glue_device(ctx, a.z, 1, xyz, xs, a.m, a.K4, a.rows, a.cols, INFINITY, a.layout, a.depth_map, nullptr, stats,
                        zrows, lm_grid_size(ctx)));
     // setPose (main.cc:516) -> per-scanline poses, with the sign-fixed v
     RS_TRY(poses_device(ctx, lm_motion_device(ctx), stats, a.gamma, a.rows, dR, dt));
@@ -83,47 +108,279 @@ static void drain(rsdsfm_ctx *ctx)
     if (ctx->s_out) cudaStreamSynchronize(ctx->s_out);
 }
 
-// Synchronous step with the caller's buffers in `mem` (I/O slot `slot`).
-static int step_sync(rsdsfm_ctx *ctx, int mem, int slot, const double *flow, const double *inliers3, const double *alpha,
-                     const double *alpha_k, int m, double *v, double *w, double *k, int const_acc, int gs_mode,
-                     const uint8_t *image, int rows, int cols, const double *K4, double gamma, int layout, double *z_out,
-                     double *depth_map, uint8_t *rectified, rsdsfm_lm_summary *summary)
+// ---- one frame pair of either host interface, as the sequence driver sees it -----------------------
+// in[0..4]: expanded inputs flow, inliers3, alpha, alpha_k, image  |  compact inputs flow_img, mask, inv_depth, -, image
+struct SeqPair {
+    const void *in[5];
+    size_t in_bytes[5];
+    int m, n;
+    double *v, *w, *k;
+    double *z_out, *depth_map;           // depth_map may be NULL with the compact interface (not downloaded / not kept)
+    uint8_t *rectified;
+    rsdsfm_lm_summary *summary;
+    int *status;
+};
+struct SeqCommon {
+    int compact, flow_f32;
+    double flow_threshold;
+    int const_acc, gs_mode, rows, cols, layout;
+    const double *K4;
+    double gamma;
+};
+
+static StepArgs step_args(const SeqCommon &C, const SeqPair &p, const void *const in[5], double *z, double *depth_map, uint8_t *rectified)
 {
-    const size_t mm = (size_t)m, tot = (size_t)rows * cols;
+    StepArgs a{};
+    a.image = (const uint8_t *)in[4];
+    a.m = p.m; a.const_acc = C.const_acc; a.gs_mode = C.gs_mode; a.rows = C.rows; a.cols = C.cols; a.layout = C.layout;
+    a.K4 = C.K4; a.gamma = C.gamma;
+    a.z = z; a.depth_map = depth_map; a.rectified = rectified;
+    if (C.compact) {
+        a.flow_img = in[0]; a.flow_f32 = C.flow_f32; a.mask = (const uint8_t *)in[1]; a.inv_depth = (const double *)in[2];
+        a.n = p.n; a.flow_threshold = C.flow_threshold;
+    } else {
+        a.flow = (const double *)in[0]; a.inliers3 = (const double *)in[1]; a.alpha = (const double *)in[2]; a.alpha_k = (const double *)in[3];
+    }
+    return a;
+}
+
+// Synchronous step with the caller's buffers in `mem` (I/O slot `slot`).
+static int step_sync(rsdsfm_ctx *ctx, int mem, int slot, const SeqCommon &C, const SeqPair &p)
+{
+    const size_t mm = (size_t)p.m, tot = (size_t)C.rows * C.cols;
     const int b = 8 * slot;
     ctx->io_slot = slot;
-    const void *d_f = nullptr, *d_i = nullptr, *d_a = nullptr, *d_ak = nullptr, *d_img = nullptr;
+    const void *d_in[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     void *d_z = nullptr, *d_dm = nullptr, *d_out = nullptr;
-    RS_TRY(stage_in(ctx, mem, b + 0, flow, sizeof(double) * 2 * mm, &d_f));
-    RS_TRY(stage_in(ctx, mem, b + 1, inliers3, sizeof(double) * 3 * mm, &d_i));
-    RS_TRY(stage_in(ctx, mem, b + 2, alpha, sizeof(double) * mm, &d_a));
-    RS_TRY(stage_in(ctx, mem, b + 3, alpha_k, sizeof(double) * mm, &d_ak));
-    RS_TRY(stage_in(ctx, mem, b + 4, image, tot * 3, &d_img));
-    RS_TRY(stage_out_reserve(ctx, mem, b + 5, z_out, sizeof(double) * mm, &d_z));
-    RS_TRY(stage_out_reserve(ctx, mem, b + 6, depth_map, sizeof(double) * tot, &d_dm));
-    RS_TRY(stage_out_reserve(ctx, mem, b + 7, rectified, tot * 3, &d_out));
+    for (int j = 0; j < 5; ++j) RS_TRY(stage_in(ctx, mem, b + j, p.in[j], p.in_bytes[j], &d_in[j]));
+    RS_TRY(stage_out_reserve(ctx, mem, b + 5, p.z_out, sizeof(double) * mm, &d_z));
+    if (p.depth_map) RS_TRY(stage_out_reserve(ctx, mem, b + 6, p.depth_map, sizeof(double) * tot, &d_dm));
+    else { RS_TRY(ensure(ctx, ctx->stage[b + 6], sizeof(double) * tot)); d_dm = ctx->stage[b + 6].p; }   // the splat still reads it
+    RS_TRY(stage_out_reserve(ctx, mem, b + 7, p.rectified, tot * 3, &d_out));
     rsdsfm_lm_summary local;
-    if (!summary) summary = &local;
+    rsdsfm_lm_summary *summary = p.summary ? p.summary : &local;
     memset(summary, 0, sizeof *summary);
-    StepArgs a{(const double *)d_f, (const double *)d_i, (const double *)d_a, (const double *)d_ak, nullptr,
-               (const uint8_t *)d_img, m, const_acc, gs_mode, rows, cols, layout, K4, gamma,
-               (double *)d_z, (double *)d_dm, (uint8_t *)d_out};
+    const StepArgs a = step_args(C, p, d_in, (double *)d_z, (double *)d_dm, (uint8_t *)d_out);
     for (int attempt = 0; attempt < 2; ++attempt) {
-        RS_TRY(queue_step(ctx, a, v, w, *k));
-        RS_TRY(stage_out(ctx, mem, z_out, d_z, sizeof(double) * mm));
-        RS_TRY(stage_out(ctx, mem, depth_map, d_dm, sizeof(double) * tot));
-        RS_TRY(stage_out(ctx, mem, rectified, d_out, tot * 3));
+        RS_TRY(queue_step(ctx, a, p.v, p.w, *p.k));
+        RS_TRY(stage_out(ctx, mem, p.z_out, d_z, sizeof(double) * mm));
+        RS_TRY(stage_out(ctx, mem, p.depth_map, d_dm, sizeof(double) * tot));
+        RS_TRY(stage_out(ctx, mem, p.rectified, d_out, tot * 3));
         RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));               // the one synchronisation of the step
         bool overflow = false;
-        RS_TRY(finish_step(ctx, const_acc ? 7 : 6, m, v, w, k, summary, &overflow));
+        RS_TRY(finish_step(ctx, C.const_acc ? 7 : 6, p.m, p.v, p.w, p.k, summary, &overflow));
         if (!overflow) return RSDSFM_OK;                                 // else: exception list enlarged, run again
     }
     return fail(ctx, RSDSFM_ERR_INTERNAL, "refine_rectify: exception list overflow persisted");
 }
 
-static bool pair_args_ok(const rsdsfm_pair_io &p)
+static bool seq_pair_ok(const SeqCommon &C, const SeqPair &p)
 {
-    return p.m > 0 && p.flow && p.inliers3 && p.alpha && p.alpha_k && p.image && p.z_out && p.depth_map && p.rectified;
+    if (!(p.m > 0 && p.in[0] && p.in[1] && p.in[2] && p.in[4] && p.z_out && p.rectified)) return false;
+    if (C.compact) return p.n >= p.m;
+    return p.in[3] && p.depth_map;
+}
+
+// The sequence driver behind rsdsfm_refine_rectify_sequence and rsdsfm_refine_rectify_compact_sequence
+// (see include/rsdsfm.h for the pipeline it implements).
+static int sequence_core(rsdsfm_ctx *ctx, int mem, std::vector<SeqPair> &pairs, const SeqCommon &C)
+{
+    const int n_pairs = (int)pairs.size();
+    if (n_pairs == 0) return RSDSFM_OK;
+    RS_TRY(ensure_io(ctx));
+    const size_t tot = (size_t)C.rows * C.cols;
+    const int nf = C.const_acc ? 7 : 6;
+    const bool host = (mem == RSDSFM_HOST);
+    int first_err = RSDSFM_OK;
+    int max_m = 0, n_ok = 0;
+    size_t max_in[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < n_pairs; ++i) {
+        SeqPair &p = pairs[i];
+        *p.status = seq_pair_ok(C, p) ? RSDSFM_OK : RSDSFM_ERR_ARG;
+        memset(p.summary, 0, sizeof *p.summary);
+        if (*p.status == RSDSFM_OK) {
+            ++n_ok;
+            if (p.m > max_m) max_m = p.m;
+            for (int j = 0; j < 5; ++j) if (p.in_bytes[j] > max_in[j]) max_in[j] = p.in_bytes[j];
+        } else if (first_err == RSDSFM_OK)
+            first_err = fail(ctx, RSDSFM_ERR_ARG, "refine_rectify sequence: bad pair argument");
+    }
+    if (max_m == 0) return first_err;
+
+    // Two compute lanes (see common.cuh): pair j runs on lane j&1 = I/O slot j&1.  Lane 1 is a second
+    // context of its own; with both lanes busy each LM solve takes half of the SMs.
+    // Host buffers, expanded interface: the sequence is PCIe-bound and a lane holds its staging slot for the whole
+    // (twice as long) half-GPU compute, which would starve the upload stream -- one lane, full-GPU solves.
+    const bool two_lanes = !host && n_ok >= 2 && ctx->num_sms >= 2 && !getenv("RSDSFM_SINGLE_LANE");
+    if (two_lanes && !ctx->lane1) {
+        if (rsdsfm_create(ctx->device, nullptr, &ctx->lane1) != RSDSFM_OK)
+            return fail(ctx, RSDSFM_ERR_CUDA, rsdsfm_last_error(nullptr));
+    }
+    rsdsfm_ctx *lane[2] = {ctx, two_lanes ? ctx->lane1 : ctx};
+    auto drain_all = [&]() { drain(ctx); if (ctx->lane1) cudaStreamSynchronize(ctx->lane1->stream); };
+    const long long launches1_before = ctx->lane1 ? ctx->lane1->launches : 0;
+    if (two_lanes) {
+        // lane 1 has a stream of its own: whatever the caller queued on the context's stream before this call
+        // (e.g. the kernels that produced the device inputs) must be ordered before lane 1's work too
+        RS_CUDA(ctx, cudaEventRecord(ctx->ev_in[0], ctx->stream));
+        RS_CUDA(ctx, cudaStreamWaitEvent(ctx->lane1->stream, ctx->ev_in[0], 0));
+        ctx->lm_grid = ctx->num_sms / 2; ctx->lane1->lm_grid = ctx->num_sms - ctx->num_sms / 2;
+        ctx->lane1->profile = ctx->profile;
+        ctx->lane1->exc_cap = ctx->exc_cap > ctx->lane1->exc_cap ? ctx->exc_cap : ctx->lane1->exc_cap;
+    }
+    // staging buffer j of I/O slot s (one lane: both slots live in this context; two lanes: slot = lane)
+    auto stg = [&](int s, int j) -> DevBuf & { return two_lanes ? lane[s]->stage[j] : ctx->stage[8 * s + j]; };
+
+    // size every buffer once, before anything is in flight
+    drain_all();
+    int rc0 = lm_reserve(lane[0], max_m);
+    if (rc0 == RSDSFM_OK && two_lanes) rc0 = lm_reserve(lane[1], max_m);
+    for (int s = 0; s < 2 && rc0 == RSDSFM_OK; ++s) {
+        const size_t sz[8] = {max_in[0], max_in[1], max_in[2], max_in[3], max_in[4], sizeof(double) * (size_t)max_m, sizeof(double) * tot, tot * 3};
+        for (int j = (host ? 0 : 6); j < (host ? 8 : 7) && rc0 == RSDSFM_OK; ++j)       // device buffers: only the optional depth scratch
+            if (sz[j]) rc0 = ensure(lane[s], stg(s, j), sz[j]);
+        if (rc0 == RSDSFM_OK && C.compact) {
+            rc0 = ensure(lane[s], lane[s]->pipe[14], sizeof(double) * (size_t)max_m);
+            if (rc0 == RSDSFM_OK) rc0 = ensure(lane[s], lane[s]->pipe[15], sizeof(double) * 2 * (size_t)max_m);
+        }
+    }
+    if (rc0 != RSDSFM_OK) {
+        if (two_lanes) { ctx->lm_grid = 0; ctx->lane1->lm_grid = 0; if (lane[1]->err.size()) ctx->err = lane[1]->err; }
+        return rc0;
+    }
+
+    // In flight at any time: upload of pair i (s_in), compute of pairs <= i (one stream per lane, in order
+    // within a lane), download of pairs < i (s_out).  The upload of pair i starts as soon as the compute of
+    // pair i-2 has released the slot's staging buffers (stream-side wait, the host does not block for it);
+    // pair i-2 is finished (results parsed on the host) before the compute of pair i is queued, because that
+    // compute overwrites the slot's read-back area.
+    int submitted[2] = {-1, -1};                 // pair occupying each slot, not yet finished
+    bool retried = false;
+    auto finish = [&](int slot) -> int {
+        const int j = submitted[slot];
+        if (j < 0) return RSDSFM_OK;
+        submitted[slot] = -1;
+        SeqPair &p = pairs[j];
+        rsdsfm_ctx *L = lane[slot];
+        RS_CUDA(ctx, cudaEventSynchronize(ctx->ev_out[slot]));
+        L->io_slot = two_lanes ? 0 : slot;
+        bool overflow = false;
+        int rc = finish_step(L, nf, p.m, p.v, p.w, p.k, p.summary, &overflow);
+        if (rc == RSDSFM_OK && overflow) {
+            // Exception list too small for this pair (it has been enlarged): let everything in
+            // flight complete, keep the other slot's read-backs, and redo this pair synchronously.
+            drain_all();
+            rc = step_sync(L, mem, two_lanes ? 0 : slot, C, p);
+            retried = true;                       // the slot's staging buffers were reused
+        }
+        if (rc != RSDSFM_OK && L != ctx) ctx->err = L->err;
+        *p.status = rc;
+        return rc;
+    };
+    auto upload = [&](const SeqPair &p, int s) -> int {
+        for (int j = 0; j < 5; ++j)
+            if (p.in[j] && p.in_bytes[j])
+                RS_CUDA(ctx, cudaMemcpyAsync(stg(s, j).p, p.in[j], p.in_bytes[j], cudaMemcpyHostToDevice, ctx->s_in));
+        RS_CUDA(ctx, cudaEventRecord(ctx->ev_in[s], ctx->s_in));
+        return RSDSFM_OK;
+    };
+
+    for (int i = 0; i < n_pairs; ++i) {
+        SeqPair &p = pairs[i];
+        if (*p.status != RSDSFM_OK) continue;
+        const int s = i & 1;
+        rsdsfm_ctx *L = lane[s];
+        const size_t mm = (size_t)p.m;
+        int rc = [&]() -> int {
+            if (host) {
+                // the slot's input staging was last read by the compute of its previous occupant
+                if (submitted[s] >= 0) RS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_cdone[s], 0));
+                RS_TRY(upload(p, s));
+            }
+            retried = false;
+            const int frc = finish(s);            // the previous occupant: blocks until its download is complete
+            if (frc != RSDSFM_OK && first_err == RSDSFM_OK) first_err = frc;
+            const void *in[5] = {p.in[0], p.in[1], p.in[2], p.in[3], p.in[4]};
+            double *z = p.z_out, *dm = p.depth_map;
+            uint8_t *rect = p.rectified;
+            if (host) {
+                if (retried) RS_TRY(upload(p, s));
+                RS_CUDA(ctx, cudaStreamWaitEvent(L->stream, ctx->ev_in[s], 0));
+                for (int j = 0; j < 5; ++j) in[j] = stg(s, j).p;
+                z = (double *)stg(s, 5).p; dm = (double *)stg(s, 6).p; rect = (uint8_t *)stg(s, 7).p;
+            } else if (!dm) {
+                dm = (double *)stg(s, 6).p;       // nobody wants the depth map, but the splat reads it
+            }
+            const StepArgs a = step_args(C, p, in, z, dm, rect);
+            L->io_slot = two_lanes ? 0 : s;
+            const int qrc = queue_step(L, a, p.v, p.w, *p.k);
+            if (qrc != RSDSFM_OK) { if (L != ctx) ctx->err = L->err; return qrc; }
+            RS_CUDA(ctx, cudaEventRecord(ctx->ev_cdone[s], L->stream));
+            RS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_cdone[s], 0));
+            if (host) {
+                RS_CUDA(ctx, cudaMemcpyAsync(p.z_out, a.z, sizeof(double) * mm, cudaMemcpyDeviceToHost, ctx->s_out));
+                if (p.depth_map)
+                    RS_CUDA(ctx, cudaMemcpyAsync(p.depth_map, a.depth_map, sizeof(double) * tot, cudaMemcpyDeviceToHost, ctx->s_out));
+                RS_CUDA(ctx, cudaMemcpyAsync(p.rectified, a.rectified, tot * 3, cudaMemcpyDeviceToHost, ctx->s_out));
+            }
+            RS_CUDA(ctx, cudaEventRecord(ctx->ev_out[s], ctx->s_out));
+            return RSDSFM_OK;
+        }();
+        if (rc != RSDSFM_OK) {
+            drain_all();
+            *p.status = rc;
+            if (first_err == RSDSFM_OK) first_err = rc;
+            continue;
+        }
+        submitted[s] = i;
+    }
+    // finish in submission order (older pair first)
+    int order[2] = {0, 1};
+    if (submitted[0] >= 0 && submitted[1] >= 0 && submitted[1] < submitted[0]) { order[0] = 1; order[1] = 0; }
+    for (int q = 0; q < 2; ++q) {
+        int rc = finish(order[q]);
+        if (rc != RSDSFM_OK && first_err == RSDSFM_OK) first_err = rc;
+    }
+    drain_all();
+    ctx->io_slot = 0;
+    if (two_lanes) {
+        rsdsfm_ctx *L1 = ctx->lane1;
+        ctx->lm_grid = 0; L1->lm_grid = 0; L1->io_slot = 0;
+        ctx->launches += L1->launches - launches1_before;
+        if (ctx->profile) {                       // lane 1's timers join the caller-visible ones
+            for (int j = 0; j < 8; ++j) { ctx->prof[j] += L1->prof[j]; ctx->prof_detail[j] += L1->prof_detail[j]; L1->prof[j] = 0.0; L1->prof_detail[j] = 0.0; }
+        }
+        if (L1->exc_cap > ctx->exc_cap) ctx->exc_cap = L1->exc_cap;
+    }
+    return first_err;
+}
+
+static SeqPair expanded_view(rsdsfm_pair_io &p, size_t tot)
+{
+    const size_t mm = (size_t)(p.m > 0 ? p.m : 0);
+    SeqPair q{};
+    q.in[0] = p.flow; q.in[1] = p.inliers3; q.in[2] = p.alpha; q.in[3] = p.alpha_k; q.in[4] = p.image;
+    q.in_bytes[0] = sizeof(double) * 2 * mm; q.in_bytes[1] = sizeof(double) * 3 * mm; q.in_bytes[2] = sizeof(double) * mm;
+    q.in_bytes[3] = sizeof(double) * mm; q.in_bytes[4] = tot * 3;
+    q.m = p.m; q.n = p.m;
+    q.v = p.v; q.w = p.w; q.k = &p.k;
+    q.z_out = p.z_out; q.depth_map = p.depth_map; q.rectified = p.rectified;
+    q.summary = &p.summary; q.status = &p.status;
+    return q;
+}
+
+static SeqPair compact_view(rsdsfm_compact_pair_io &p, size_t tot, int flow_f32)
+{
+    const size_t nn = (size_t)(p.n > 0 ? p.n : 0);
+    SeqPair q{};
+    q.in[0] = p.flow_img; q.in[1] = p.mask; q.in[2] = p.inv_depth; q.in[3] = nullptr; q.in[4] = p.image;
+    q.in_bytes[0] = (flow_f32 ? sizeof(float) : sizeof(double)) * 2 * tot; q.in_bytes[1] = nn; q.in_bytes[2] = sizeof(double) * nn;
+    q.in_bytes[3] = 0; q.in_bytes[4] = tot * 3;
+    q.m = p.m; q.n = p.n;
+    q.v = p.v; q.w = p.w; q.k = &p.k;
+    q.z_out = p.z_out; q.depth_map = p.depth_map; q.rectified = p.rectified;
+    q.summary = &p.summary; q.status = &p.status;
+    return q;
 }
 
 // ---- a2..a15 on device pointers ------------------------------------------------------------------
@@ -276,8 +533,13 @@ int rsdsfm_refine_rectify(rsdsfm_ctx *ctx, int mem, const double *flow, const do
     if (m <= 0 || rows <= 0 || cols <= 0 || !flow || !inliers3 || !alpha || !alpha_k || !v || !w || !k || !image || !K4 ||
         !z_out || !depth_map || !rectified)
         return fail(ctx, RSDSFM_ERR_ARG, "rsdsfm_refine_rectify: bad argument");
-    return step_sync(ctx, mem, 0, flow, inliers3, alpha, alpha_k, m, v, w, k, const_acceleration, gs_mode, image, rows, cols,
-                     K4, gamma, layout, z_out, depth_map, rectified, summary);
+    rsdsfm_pair_io io{};
+    io.flow = flow; io.inliers3 = inliers3; io.alpha = alpha; io.alpha_k = alpha_k; io.image = image; io.m = m;
+    io.z_out = z_out; io.depth_map = depth_map; io.rectified = rectified;
+    SeqPair p = expanded_view(io, (size_t)rows * cols);
+    p.v = v; p.w = w; p.k = k; p.summary = summary;
+    const SeqCommon C{0, 0, 0.0, const_acceleration, gs_mode, rows, cols, layout, K4, gamma};
+    return step_sync(ctx, mem, 0, C, p);
 }
 
 int rsdsfm_refine_rectify_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm_pair_io *pairs, int const_acceleration,
@@ -286,168 +548,29 @@ int rsdsfm_refine_rectify_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm
     RS_ENTER(ctx);
     if (n_pairs < 0 || (n_pairs > 0 && !pairs) || rows <= 0 || cols <= 0 || !K4)
         return fail(ctx, RSDSFM_ERR_ARG, "rsdsfm_refine_rectify_sequence: bad argument");
-    if (n_pairs == 0) return RSDSFM_OK;
-    RS_TRY(ensure_io(ctx));
-    const size_t tot = (size_t)rows * cols;
-    const int nf = const_acceleration ? 7 : 6;
-    const bool host = (mem == RSDSFM_HOST);
-    int first_err = RSDSFM_OK;
-    int max_m = 0, n_ok = 0;
-    for (int i = 0; i < n_pairs; ++i) {
-        pairs[i].status = pair_args_ok(pairs[i]) ? RSDSFM_OK : RSDSFM_ERR_ARG;
-        memset(&pairs[i].summary, 0, sizeof pairs[i].summary);
-        if (pairs[i].status == RSDSFM_OK) { ++n_ok; if (pairs[i].m > max_m) max_m = pairs[i].m; }
-        else if (first_err == RSDSFM_OK)
-            first_err = fail(ctx, RSDSFM_ERR_ARG, "rsdsfm_refine_rectify_sequence: bad pair argument");
-    }
-    if (max_m == 0) return first_err;
+    std::vector<SeqPair> views;
+    for (int i = 0; i < n_pairs; ++i) views.push_back(expanded_view(pairs[i], (size_t)rows * cols));
+    const SeqCommon C{0, 0, 0.0, const_acceleration, gs_mode, rows, cols, layout, K4, gamma};
+    return sequence_core(ctx, mem, views, C);
+}
 
-    // Two compute lanes (see common.cuh): pair j runs on lane j&1 = I/O slot j&1.  Lane 1 is a second
-    // context of its own; with both lanes busy each LM solve takes half of the SMs.
-    // Host buffers: the sequence is PCIe-bound and a lane holds its staging slot for the whole (twice as
-    // long) half-GPU compute, which would starve the upload stream -- one lane, full-GPU solves.
-    const bool two_lanes = !host && n_ok >= 2 && ctx->num_sms >= 2 && !getenv("RSDSFM_SINGLE_LANE");
-    if (two_lanes && !ctx->lane1) {
-        if (rsdsfm_create(ctx->device, nullptr, &ctx->lane1) != RSDSFM_OK)
-            return fail(ctx, RSDSFM_ERR_CUDA, rsdsfm_last_error(nullptr));
+int rsdsfm_refine_rectify_compact_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm_compact_pair_io *pairs, int flow_f32,
+                                           double flow_threshold, int const_acceleration, int gs_mode, int rows, int cols,
+                                           const double *K4, double gamma, int layout)
+{
+    RS_ENTER(ctx);
+    if (n_pairs < 0 || (n_pairs > 0 && !pairs) || rows <= 0 || cols <= 0 || !K4)
+        return fail(ctx, RSDSFM_ERR_ARG, "rsdsfm_refine_rectify_compact_sequence: bad argument");
+    std::vector<SeqPair> views;
+    for (int i = 0; i < n_pairs; ++i) views.push_back(compact_view(pairs[i], (size_t)rows * cols, flow_f32));
+    const SeqCommon C{1, flow_f32 ? 1 : 0, flow_threshold, const_acceleration, gs_mode, rows, cols, layout, K4, gamma};
+    if (n_pairs == 1) {                          // a one-pair sequence is the synchronous call
+        SeqPair &p = views[0];
+        *p.status = seq_pair_ok(C, p) ? RSDSFM_OK : fail(ctx, RSDSFM_ERR_ARG, "rsdsfm_refine_rectify_compact_sequence: bad pair argument");
+        if (*p.status == RSDSFM_OK) *p.status = step_sync(ctx, mem, 0, C, p);
+        return *p.status;
     }
-    rsdsfm_ctx *lane[2] = {ctx, two_lanes ? ctx->lane1 : ctx};
-    auto drain_all = [&]() { drain(ctx); if (ctx->lane1) cudaStreamSynchronize(ctx->lane1->stream); };
-    const long long launches1_before = ctx->lane1 ? ctx->lane1->launches : 0;
-    if (two_lanes) {
-        // lane 1 has a stream of its own: whatever the caller queued on the context's stream before this call
-        // (e.g. the kernels that produced the device inputs) must be ordered before lane 1's work too
-        RS_CUDA(ctx, cudaEventRecord(ctx->ev_in[0], ctx->stream));
-        RS_CUDA(ctx, cudaStreamWaitEvent(ctx->lane1->stream, ctx->ev_in[0], 0));
-        ctx->lm_grid = ctx->num_sms / 2; ctx->lane1->lm_grid = ctx->num_sms - ctx->num_sms / 2;
-        ctx->lane1->profile = ctx->profile;
-        ctx->lane1->exc_cap = ctx->exc_cap > ctx->lane1->exc_cap ? ctx->exc_cap : ctx->lane1->exc_cap;
-    }
-    // staging buffer j of I/O slot s (one lane: both slots live in this context; two lanes: slot = lane)
-    auto stg = [&](int s, int j) -> DevBuf & { return two_lanes ? lane[s]->stage[j] : ctx->stage[8 * s + j]; };
-
-    // size every buffer once, before anything is in flight
-    drain_all();
-    int rc0 = lm_reserve(lane[0], max_m);
-    if (rc0 == RSDSFM_OK && two_lanes) rc0 = lm_reserve(lane[1], max_m);
-    if (rc0 == RSDSFM_OK && host)
-        for (int s = 0; s < 2 && rc0 == RSDSFM_OK; ++s) {
-            const size_t sz[8] = {sizeof(double) * 2 * (size_t)max_m, sizeof(double) * 3 * (size_t)max_m,
-                                  sizeof(double) * (size_t)max_m, sizeof(double) * (size_t)max_m, tot * 3,
-                                  sizeof(double) * (size_t)max_m, sizeof(double) * tot, tot * 3};
-            for (int j = 0; j < 8 && rc0 == RSDSFM_OK; ++j) rc0 = ensure(lane[s], stg(s, j), sz[j]);
-        }
-    if (rc0 != RSDSFM_OK) {
-        if (two_lanes) { ctx->lm_grid = 0; ctx->lane1->lm_grid = 0; if (lane[1]->err.size()) ctx->err = lane[1]->err; }
-        return rc0;
-    }
-
-    // In flight at any time: upload of pair i (s_in), compute of pairs <= i (one stream per lane, in order
-    // within a lane), download of pairs < i (s_out).  The upload of pair i starts as soon as the compute of
-    // pair i-2 has released the slot's staging buffers (stream-side wait, the host does not block for it);
-    // pair i-2 is finished (results parsed on the host) before the compute of pair i is queued, because that
-    // compute overwrites the slot's read-back area.
-    int submitted[2] = {-1, -1};                 // pair occupying each slot, not yet finished
-    bool retried = false;
-    auto finish = [&](int slot) -> int {
-        const int j = submitted[slot];
-        if (j < 0) return RSDSFM_OK;
-        submitted[slot] = -1;
-        rsdsfm_pair_io &p = pairs[j];
-        rsdsfm_ctx *L = lane[slot];
-        RS_CUDA(ctx, cudaEventSynchronize(ctx->ev_out[slot]));
-        L->io_slot = two_lanes ? 0 : slot;
-        bool overflow = false;
-        int rc = finish_step(L, nf, p.m, p.v, p.w, &p.k, &p.summary, &overflow);
-        if (rc == RSDSFM_OK && overflow) {
-            // Exception list too small for this pair (it has been enlarged): let everything in
-            // flight complete, keep the other slot's read-backs, and redo this pair synchronously.
-            drain_all();
-            rc = step_sync(L, mem, two_lanes ? 0 : slot, p.flow, p.inliers3, p.alpha, p.alpha_k, p.m, p.v, p.w, &p.k,
-                           const_acceleration, gs_mode, p.image, rows, cols, K4, gamma, layout, p.z_out, p.depth_map, p.rectified,
-                           &p.summary);
-            retried = true;                       // the slot's staging buffers were reused
-        }
-        if (rc != RSDSFM_OK && L != ctx) ctx->err = L->err;
-        p.status = rc;
-        return rc;
-    };
-    auto upload = [&](const rsdsfm_pair_io &p, int s) -> int {
-        const size_t mm = (size_t)p.m;
-        const void *src[5] = {p.flow, p.inliers3, p.alpha, p.alpha_k, p.image};
-        const size_t sz[5] = {sizeof(double) * 2 * mm, sizeof(double) * 3 * mm, sizeof(double) * mm, sizeof(double) * mm, tot * 3};
-        for (int j = 0; j < 5; ++j)
-            RS_CUDA(ctx, cudaMemcpyAsync(stg(s, j).p, src[j], sz[j], cudaMemcpyHostToDevice, ctx->s_in));
-        RS_CUDA(ctx, cudaEventRecord(ctx->ev_in[s], ctx->s_in));
-        return RSDSFM_OK;
-    };
-
-    for (int i = 0; i < n_pairs; ++i) {
-        rsdsfm_pair_io &p = pairs[i];
-        if (p.status != RSDSFM_OK) continue;
-        const int s = i & 1;
-        rsdsfm_ctx *L = lane[s];
-        const size_t mm = (size_t)p.m;
-        StepArgs a{p.flow, p.inliers3, p.alpha, p.alpha_k, nullptr, p.image, p.m, const_acceleration, gs_mode, rows, cols,
-                   layout, K4, gamma, p.z_out, p.depth_map, p.rectified};
-        int rc = [&]() -> int {
-            if (host) {
-                // the slot's input staging was last read by the compute of its previous occupant
-                if (submitted[s] >= 0) RS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_cdone[s], 0));
-                RS_TRY(upload(p, s));
-            }
-            retried = false;
-            const int frc = finish(s);            // the previous occupant: blocks until its download is complete
-            if (frc != RSDSFM_OK && first_err == RSDSFM_OK) first_err = frc;
-            if (host) {
-                if (retried) RS_TRY(upload(p, s));
-                RS_CUDA(ctx, cudaStreamWaitEvent(L->stream, ctx->ev_in[s], 0));
-                a.flow = (const double *)stg(s, 0).p; a.inliers3 = (const double *)stg(s, 1).p;
-                a.alpha = (const double *)stg(s, 2).p; a.alpha_k = (const double *)stg(s, 3).p;
-                a.image = (const uint8_t *)stg(s, 4).p;
-                a.z = (double *)stg(s, 5).p; a.depth_map = (double *)stg(s, 6).p;
-                a.rectified = (uint8_t *)stg(s, 7).p;
-            }
-            L->io_slot = two_lanes ? 0 : s;
-            const int qrc = queue_step(L, a, p.v, p.w, p.k);
-            if (qrc != RSDSFM_OK) { if (L != ctx) ctx->err = L->err; return qrc; }
-            RS_CUDA(ctx, cudaEventRecord(ctx->ev_cdone[s], L->stream));
-            RS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_cdone[s], 0));
-            if (host) {
-                RS_CUDA(ctx, cudaMemcpyAsync(p.z_out, a.z, sizeof(double) * mm, cudaMemcpyDeviceToHost, ctx->s_out));
-                RS_CUDA(ctx, cudaMemcpyAsync(p.depth_map, a.depth_map, sizeof(double) * tot, cudaMemcpyDeviceToHost, ctx->s_out));
-                RS_CUDA(ctx, cudaMemcpyAsync(p.rectified, a.rectified, tot * 3, cudaMemcpyDeviceToHost, ctx->s_out));
-            }
-            RS_CUDA(ctx, cudaEventRecord(ctx->ev_out[s], ctx->s_out));
-            return RSDSFM_OK;
-        }();
-        if (rc != RSDSFM_OK) {
-            drain_all();
-            p.status = rc;
-            if (first_err == RSDSFM_OK) first_err = rc;
-            continue;
-        }
-        submitted[s] = i;
-    }
-    // finish in submission order (older pair first)
-    int order[2] = {0, 1};
-    if (submitted[0] >= 0 && submitted[1] >= 0 && submitted[1] < submitted[0]) { order[0] = 1; order[1] = 0; }
-    for (int q = 0; q < 2; ++q) {
-        int rc = finish(order[q]);
-        if (rc != RSDSFM_OK && first_err == RSDSFM_OK) first_err = rc;
-    }
-    drain_all();
-    ctx->io_slot = 0;
-    if (two_lanes) {
-        rsdsfm_ctx *L1 = ctx->lane1;
-        ctx->lm_grid = 0; L1->lm_grid = 0; L1->io_slot = 0;
-        ctx->launches += L1->launches - launches1_before;
-        if (ctx->profile) {                       // lane 1's timers join the caller-visible ones
-            for (int j = 0; j < 8; ++j) { ctx->prof[j] += L1->prof[j]; ctx->prof_detail[j] += L1->prof_detail[j]; L1->prof[j] = 0.0; L1->prof_detail[j] = 0.0; }
-        }
-        if (L1->exc_cap > ctx->exc_cap) ctx->exc_cap = L1->exc_cap;
-    }
-    return first_err;
+    return sequence_core(ctx, mem, views, C);
 }
 
 int rsdsfm_pipeline_pair(rsdsfm_ctx *ctx, int mem, const rsdsfm_pipeline_params *params, rsdsfm_pipeline_io *io)

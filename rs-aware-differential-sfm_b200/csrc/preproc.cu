@@ -7,6 +7,7 @@
 //   a4  minimal::getAlphaK   minimal.cc:188-197       k_alpha
 //   a6  tail of minimal::ransac  minimal.cc:291-305   k_gather_*  (ascending point index)
 #include "common.cuh"
+#include "lm_layout.h"
 
 namespace rsdsfm {
 
@@ -235,6 +236,154 @@ int gather_inliers_device(rsdsfm_ctx *ctx, const double *q, const double *alpha,
     RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *m_out = *(int *)ctx->pinned;
     return RSDSFM_OK;
+}
+
+// ---------------------------------------------------------------- compact step inputs -> solver layout
+// The "refine + rectify" step fed with what minimal::ransac returned (the winner's consensus mask and inverse
+// depths over the flattened points) and the cached flow field itself.  Everything else the reference passes
+// around between main.cc:398 and :457 -- normalised coordinates, gamma-scaled flow, alpha / alpha_k, the
+// consensus set as (x, y, z) triples -- is a function of those and is rebuilt here, straight into the LM
+// solver's tile-blocked layout (lm_layout.h), with the operation order of k_flat_scatter / k_alpha /
+// k_mask_scatter (bit-identical values).  Residual block i takes the coordinates and alpha factors of the
+// i-th inlier and the flow of flattened POINT i (the reference's pairing, nonlinearRefinement.cc:209-216, Q1).
+template <typename F>
+__device__ __forceinline__ bool flow_kept_t(const F *__restrict__ flow_img, int rows, int cols, long long p, long long total,
+                                            double thr, double &dx, double &dy, int &i, int &j)
+{
+    if (p >= total) return false;
+    i = (int)(p / rows);
+    j = (int)(p - (long long)i * rows);
+    const size_t at = ((size_t)j * cols + i) * 2;
+    dx = (double)flow_img[at]; dy = (double)flow_img[at + 1];      // float32 flow is widened exactly (camera.cc:262-274)
+    const double norm = dx * dx + dy * dy;
+    return norm > thr;
+}
+
+template <typename F>
+__global__ void __launch_bounds__(kThreads) k_compact_count_kept(const F *__restrict__ flow_img, int rows, int cols, double thr,
+                                                                 int *block_counts)
+{
+    const long long total = (long long)rows * cols;
+    int cnt = 0;
+    for (int s = 0; s < 4; ++s) {
+        const long long p = (long long)blockIdx.x * kChunk + s * kThreads + threadIdx.x;
+        double dx, dy; int i, j;
+        cnt += flow_kept_t(flow_img, rows, cols, p, total, thr, dx, dy, i, j) ? 1 : 0;
+    }
+    __shared__ int sh[kWarps];
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w2 = 0; w2 < kWarps; ++w2) t += sh[w2];
+        block_counts[blockIdx.x] = t;
+    }
+}
+
+// second level: inliers among the kept pixels of each chunk (mask is indexed by flattened point)
+template <typename F>
+__global__ void __launch_bounds__(kThreads) k_compact_count_inliers(const F *__restrict__ flow_img, int rows, int cols, double thr,
+                                                                    const int *__restrict__ kept_offsets,
+                                                                    const uint8_t *__restrict__ mask, int n, int *block_counts)
+{
+    const long long total = (long long)rows * cols;
+    int base = kept_offsets[blockIdx.x];
+    int cnt = 0;
+    for (int s = 0; s < 4; ++s) {
+        const long long p = (long long)blockIdx.x * kChunk + s * kThreads + threadIdx.x;
+        double dx, dy; int i, j;
+        const bool keep = flow_kept_t(flow_img, rows, cols, p, total, thr, dx, dy, i, j);
+        int tot;
+        const int point = base + block_rank(keep, tot);
+        cnt += (keep && point < n && mask[point]) ? 1 : 0;
+        base += tot;
+    }
+    __shared__ int sh[kWarps];
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w2 = 0; w2 < kWarps; ++w2) t += sh[w2];
+        block_counts[blockIdx.x] = t;
+    }
+}
+
+template <typename F>
+__global__ void __launch_bounds__(kThreads) k_compact_scatter(const F *__restrict__ flow_img, int rows, int cols, double thr,
+                                                              double fx, double fy, double cx, double cy, double gamma,
+                                                              const int *__restrict__ kept_offsets,
+                                                              const int *__restrict__ inl_offsets, int nb,
+                                                              const uint8_t *__restrict__ mask,
+                                                              const double *__restrict__ inv_depth, int n, int m, double2 *blk,
+                                                              double *d0, double *z_in, double2 *xy, int *input_flag)
+{
+    const long long total = (long long)rows * cols;
+    // the caller's n / m must be what the flow field and the mask really hold
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (kept_offsets[nb] != n || inl_offsets[nb] != m)) atomicOr(input_flag, 2);
+    int base = kept_offsets[blockIdx.x], ibase = inl_offsets[blockIdx.x];
+    const double h = (double)rows;
+    int bad = 0;
+    for (int s = 0; s < 4; ++s) {
+        const long long p = (long long)blockIdx.x * kChunk + s * kThreads + threadIdx.x;
+        double dx = 0, dy = 0; int i = 0, j = 0;
+        const bool keep = flow_kept_t(flow_img, rows, cols, p, total, thr, dx, dy, i, j);
+        int tot, itot;
+        const int point = base + block_rank(keep, tot);
+        const bool inl = keep && point < n && mask[point];
+        const int pos = ibase + block_rank(inl, itot);
+        if (keep && point < m)                                               // flow of flattened point `point` -> residual block `point`
+            blk[blk_index(point, 1)] = make_double2(dx * gamma / fx, dy * gamma / fy);          // main.cc:424-425
+        if (inl && pos < m) {
+            const double2 q = make_double2((i - cx) * 1.0 / fx, (j - cy) * 1.0 / fy);           // main.cc:426-427
+            blk[blk_index(pos, 0)] = q;
+            xy[pos] = q;
+            const double qy = (double)j;
+            const double alpha = 1 + gamma * dy / h;                                            // minimal.cc:183
+            const double part1 = gamma * qy / h;                                                // minimal.cc:192-194
+            const double part2 = 1.0 + gamma * (qy + dy) / h;
+            blk[blk_index(pos, 2)] = make_double2(alpha, 0.5 * (part2 * part2 - part1 * part1));
+            const double z = 1.0 / inv_depth[point];                                            // minimal.cc:299
+            z_in[pos] = z;
+            const double d = 1.0 / z;                                                           // nonlinearRefinement.cc:213
+            d0[pos] = d;
+            if (!isfinite(d)) bad = 1;
+        }
+        base += tot; ibase += itot;
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(input_flag, 1);
+}
+
+template <typename F>
+static int compact_build_t(rsdsfm_ctx *ctx, const F *flow_img, int rows, int cols, const double *K4, double gamma, double thr,
+                           const uint8_t *mask, const double *inv_depth, int n, int m, double2 *blk, double *d0, double *z_in,
+                           double2 *xy, int *input_flag)
+{
+    const long long total = (long long)rows * cols;
+    const int nb = (int)((total + kChunk - 1) / kChunk);
+    RS_TRY(ensure(ctx, ctx->scan, sizeof(int) * (4 * (size_t)nb + 4)));
+    int *counts = (int *)ctx->scan.p, *offsets = counts + nb, *icounts = offsets + nb + 1, *ioffsets = icounts + nb;
+    k_compact_count_kept<F><<<nb, kThreads, 0, ctx->stream>>>(flow_img, rows, cols, thr, counts);
+    k_scan_counts<<<1, 1024, 0, ctx->stream>>>(counts, nb, offsets);
+    k_compact_count_inliers<F><<<nb, kThreads, 0, ctx->stream>>>(flow_img, rows, cols, thr, offsets, mask, n, icounts);
+    k_scan_counts<<<1, 1024, 0, ctx->stream>>>(icounts, nb, ioffsets);
+    k_compact_scatter<F><<<nb, kThreads, 0, ctx->stream>>>(flow_img, rows, cols, thr, K4[0], K4[1], K4[2], K4[3], gamma, offsets,
+                                                          ioffsets, nb, mask, inv_depth, n, m, blk, d0, z_in, xy, input_flag);
+    ctx->launches += 5;
+    RS_CUDA(ctx, cudaGetLastError());
+    return RSDSFM_OK;
+}
+
+int compact_build_device(rsdsfm_ctx *ctx, const void *flow_img, int flow_f32, int rows, int cols, const double *K4, double gamma,
+                         double thr, const uint8_t *mask, const double *inv_depth, int n, int m, void *blk, double *d0,
+                         double *z_in, double *xy, int *input_flag)
+{
+    if (flow_f32)
+        return compact_build_t<float>(ctx, (const float *)flow_img, rows, cols, K4, gamma, thr, mask, inv_depth, n, m, (double2 *)blk,
+                                      d0, z_in, (double2 *)xy, input_flag);
+    return compact_build_t<double>(ctx, (const double *)flow_img, rows, cols, K4, gamma, thr, mask, inv_depth, n, m, (double2 *)blk, d0,
+                                   z_in, (double2 *)xy, input_flag);
 }
 
 }  // namespace rsdsfm

@@ -32,11 +32,10 @@
 // minimum, SURVEY.md 8d: 24 B / 56 B -- x, y, alpha, alpha_k are inputs of the C ABI).
 #include "common.cuh"
 #include "lm_controller.h"
+#include "lm_layout.h"
 #include "rs_math.cuh"
 
 namespace rsdsfm {
-
-constexpr int kTile = 512;                      // residual blocks per tile (two per thread)
 
 // Tile-blocked SoA: tile t holds xy[kTile], uu[kTile], aa[kTile] (double2 each) contiguously, so a
 // whole tile arrives with ONE TMA bulk copy (the per-copy issue cost, not bandwidth, limits small
@@ -45,7 +44,6 @@ struct RefineData {
     const double2 *blk;      // [num_tiles][3][kTile]
     int m;
 };
-__host__ __device__ inline size_t blk_index(int i, int field) { return (size_t)(i / kTile) * (3 * kTile) + (size_t)field * kTile + (size_t)(i % kTile); }
 
 struct ExcEntry {            // a pixel whose LM diagonal is (possibly) clamped, or whose e-column is degenerate:
     double ees, se2;         // s_e^2 e^Te, s_e^2     (the whole pixel is handled by the controller CTA)
@@ -74,7 +72,7 @@ struct LmShared {
     unsigned long long t_phase[12];
     // ---- grid synchronisation
     unsigned int arrive, generation;
-    unsigned int n_exc[2], exc_overflow, pad1;   // two exception lists: current point / speculative candidate
+    unsigned int n_exc[4], exc_overflow, pad1;   // exception lists (k_lm_persistent: 2, k_lm_solve: 3 rotating: current / speculative / being cleared)
     int error;
     int nonfinite_input;     // LAST field: raised by the gather kernel, preserved by the control-block upload
 };
@@ -1060,19 +1058,698 @@ k_lm_persistent(RefineData D, double *d0, double *d1, LmShared *sh, double *part
     if (zstats) block_reduce_store<1, 2>(zs, zm, zstats);
 }
 
+// ==========================================================================================
+// k_lm_solve -- second-generation persistent solver (replaces k_lm_persistent above, which is
+// kept for A/B measurements: RSDSFM_LM_VARIANT=1).
+//
+//  * REPLICATED CONTROLLER.  Every CTA publishes its row of partial sums, arrives ONCE on a grid
+//    counter, then reads all rows itself, sums them in the same fixed order and runs the same
+//    Ceres logic on its own shared-memory copy of the controller state.  All CTAs take bit-identical
+//    decisions; there is no "last CTA", no serial publish/release step and no control block
+//    round trip through global memory between phases.  (It is also what a multi-GPU row split
+//    needs: peers only have to make their rows visible.)
+//  * PREFETCH ACROSS THE BARRIER.  Right after arriving, a CTA queues the TMA loads of the next
+//    phase's first tiles: the 24 KB static part unconditionally, the 4 KB inverse-depth part from the
+//    buffer the next phase reads IF THE STEP IS ACCEPTED (this CTA wrote those depths itself).  A
+//    rejected step drains the ring and reloads (rare).
+//  * EMPTY/FULL MBARRIER RING.  Consumers release a stage by arriving on its `empty` mbarrier (one
+//    arrival per warp); the producer thread refills one tile behind the consumers with a
+//    non-blocking test, so no warp ever waits at a CTA-wide barrier inside the sweep.
+//  * ONE PIXEL PER THREAD PER STEP, SOFTWARE-PIPELINED.  The rank-1 Schur updates of step i-1 (70
+//    independent FMAs on vectors held in registers) are issued together with the latency-bound
+//    residual / Jacobian chain of step i, which is what keeps the FP64 pipe fed with two warps per
+//    sub-partition.  Fewer FP64 instructions per residual block, too: the candidate's A v and B w
+//    are updated from the step's increments, the two projected Jacobian vectors share their
+//    products, flags and maxima are tracked with integer instructions.
+// ==========================================================================================
+constexpr int kExcSlots = 3;
+
+template <int NF>
+struct Held {                                   // projected, 1/|e|-scaled Jacobian vectors of the previous step
+    double kv[NF > 0 ? NF : 1], pv[NF > 0 ? NF : 1], ks, ps;
+};
+
+struct SweepScalars {                           // per-thread non-FP64 accumulators of a sweep
+    unsigned long long gmax, eemax;             // bit patterns of max |e^T r|, max e^Te (non-negative doubles order like integers)
+    unsigned flags;                             // 1: residual not finite, 2: residual or Jacobian not finite, 4: depth step not finite
+};
+
+__device__ __forceinline__ bool not_finite(double x) { return (__double2hiint(x) & 0x7ff00000) == 0x7ff00000; }
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Evaluation of one residual block at the point described by (ak, beta, a, b, d): residual, depth
+// column, cost / gradient sums, and the two projected Jacobian vectors of the lane-pair scheme:
+// H.kv / H.ks = this lane's direction (even lanes n, odd lanes e), sv / ss = the direction the partner keeps.
+template <int NF>
+__device__ __forceinline__ void eval_pixel(const Loaded &L, bool valid, int index, double xy, double xx1, double yy1, double ak,
+                                           double beta, double c2, double a0, double a1, double b0, double b1, double d_in,
+                                           bool first, const PhaseParams &P, const Motion &mot, double (&acc)[TAcc<NF>::NV],
+                                           SweepScalars &S, double (&kv)[NF > 0 ? NF : 1], double (&sv)[NF > 0 ? NF : 1], double &ks,
+                                           double &ss, unsigned int *n_exc, unsigned int *overflow, ExcEntry *exc, unsigned int exc_cap)
+{
+    const double x = L.p.x, y = L.p.y;
+    double d = d_in;
+    const double p0 = fma(d, a0, b0), p1 = fma(d, a1, b1);
+    double r0 = fma(-beta, p0, L.u.x), r1 = fma(-beta, p1, L.u.y);
+    double e0 = -beta * a0, e1 = -beta * a1;
+    double ee = fma(e0, e0, e1 * e1);
+    if (!valid) { r0 = 0.0; r1 = 0.0; e0 = 0.0; e1 = 0.0; ee = 0.0; d = 0.0; }
+    acc[0] = fma(r0, r0, fma(r1, r1, acc[0]));
+    acc[1] = fma(d, d, acc[1]);
+    const double re = fma(e0, r0, e1 * r1);                           // e^T r
+    S.gmax = umax64(S.gmax, (unsigned long long)__double_as_longlong(fabs(re)));
+    S.eemax = umax64(S.eemax, (unsigned long long)__double_as_longlong(ee));
+    if (not_finite(r0 + r1)) S.flags |= 3u;
+    if (not_finite(ee)) S.flags |= 2u;
+    // is the LM diagonal of this depth certainly not clamped?  (first evaluation: the Jacobi scale is
+    // 1/(1+|e|) of this very point; later: global lower bound of the scales)
+    bool fast;
+    if (first) {
+        const double se = 1.0 / (1.0 + sqrt(ee));
+        const double ees = ee * se * se;
+        fast = (ees >= P.min_diag && ees <= P.max_diag);
+    } else {
+        fast = (ee >= P.ee_fast_min && ee <= P.max_diag);
+    }
+    ks = 0.0; ss = 0.0;
+    if (NF > 0) {
+        const double mu = (valid && fast) ? fast_rsqrt(ee) : 0.0;       // 1/|e|
+        const double c = mu * e0, s = mu * e1;                          // unit depth-column direction
+        const bool e_role = (threadIdx.x & 1) != 0;
+        const double mc = e_role ? c : -s, ms = e_role ? s : c;         // the direction this lane keeps: e or n = (-s, c)
+        // F^T (mc, ms) and F^T (-ms, mc) share their products (F = -beta [d A | B | (dbeta/beta) p])
+        const double P0 = beta * mc, P1 = beta * ms;
+        const double dP0 = d * P0, dP1 = d * P1;
+        const double t1 = fma(x, P0, y * P1), t2 = fma(y, P0, -x * P1);
+        kv[0] = -dP0;            sv[0] = dP1;
+        kv[1] = -dP1;            sv[1] = -dP0;
+        kv[2] = d * t1;          sv[2] = d * t2;
+        kv[3] = fma(y, t1, P1);  sv[3] = fma(y, t2, P0);
+        kv[4] = -fma(x, t1, P0); sv[4] = fma(-x, t2, P1);
+        kv[5] = t2;              sv[5] = -t1;
+        if (NF == 7) {
+            const double dbeta = c2 * fma(-ak, 0.5 * c2, L.a.y);
+            kv[6] = -dbeta * fma(p0, mc, p1 * ms);
+            sv[6] = -dbeta * fma(p1, mc, -p0 * ms);
+        }
+        ks = fma(mc, r0, ms * r1);
+        ss = fma(mc, r1, -ms * r0);
+        if (valid && !fast) {
+            // rare: the pixel is listed and handled exactly by the controller (see eval_slow); its vectors are 0 here.
+            // The out-of-line call takes the pixel by address: hand it a copy made HERE.
+            const Loaded Lc = L;
+            eval_slow<NF>(Lc, d_in, index, mot, c2, first, P.base, n_exc, overflow, exc, exc_cap);
+        }
+    }
+}
+
+// INIT phase: evaluation at the start point.
+template <int NF>
+__device__ __forceinline__ void init_pixel(const Loaded &L, bool valid, int index, const PhaseParams &P, double c2,
+                                           double (&acc)[TAcc<NF>::NV], SweepScalars &S, double (&kv)[NF > 0 ? NF : 1],
+                                           double (&sv)[NF > 0 ? NF : 1], double &ks, double &ss, unsigned int *n_exc,
+                                           unsigned int *overflow, ExcEntry *exc, unsigned int exc_cap)
+{
+    const double x = L.p.x, y = L.p.y;
+    const double xy = x * y, xx1 = fma(x, x, 1.0), yy1 = fma(y, y, 1.0);
+    const double ak = fma(P.mot.k, L.a.y, L.a.x), beta = c2 * ak;
+    const double a0 = fma(-x, P.mot.v[2], P.mot.v[0]), a1 = fma(-y, P.mot.v[2], P.mot.v[1]);
+    const double b0 = fma(-xy, P.mot.w[0], fma(xx1, P.mot.w[1], -y * P.mot.w[2]));
+    const double b1 = fma(-yy1, P.mot.w[0], fma(xy, P.mot.w[1], x * P.mot.w[2]));
+    eval_pixel<NF>(L, valid, index, xy, xx1, yy1, ak, beta, c2, a0, a1, b0, b1, L.d, P.first != 0, P, P.mot, acc, S, kv, sv, ks, ss,
+                   n_exc, overflow, exc, exc_cap);
+}
+
+// FUSED phase: candidate step at x (depth back-substitution delta_d = -q e^T (r + F delta_f), model cost
+// change, |step|^2, candidate depth written to d_cand) followed by the evaluation at the candidate.
+template <int NF>
+__device__ __forceinline__ void fused_pixel(const Loaded &L, bool valid, int index, const PhaseParams &P, double c2, double c2c,
+                                            double rfac, double inv_radius, double (&acc)[TAcc<NF>::NV], SweepScalars &S,
+                                            double *__restrict__ d_cand, double (&kv)[NF > 0 ? NF : 1],
+                                            double (&sv)[NF > 0 ? NF : 1], double &ks, double &ss, unsigned int *n_exc,
+                                            unsigned int *overflow, ExcEntry *exc, unsigned int exc_cap)
+{
+    using T = TAcc<NF>;
+    const double x = L.p.x, y = L.p.y, d = L.d;
+    const double xy = x * y, xx1 = fma(x, x, 1.0), yy1 = fma(y, y, 1.0);
+    // ---- at x
+    const double ak = fma(P.mot.k, L.a.y, L.a.x), beta = c2 * ak;
+    const double a0 = fma(-x, P.mot.v[2], P.mot.v[0]), a1 = fma(-y, P.mot.v[2], P.mot.v[1]);
+    const double b0 = fma(-xy, P.mot.w[0], fma(xx1, P.mot.w[1], -y * P.mot.w[2]));
+    const double b1 = fma(-yy1, P.mot.w[0], fma(xy, P.mot.w[1], x * P.mot.w[2]));
+    const double p0 = fma(d, a0, b0), p1 = fma(d, a1, b1);
+    const double r0 = fma(-beta, p0, L.u.x), r1 = fma(-beta, p1, L.u.y);
+    const double e0 = -beta * a0, e1 = -beta * a1;
+    const double ee = fma(e0, e0, e1 * e1);
+    // q = s_e^2 / (s_e^2 e^Te + clamp(s_e^2 e^Te)/radius)  ( = radius/((radius+1) e^Te) when not clamped )
+    double q = fast_rcp(ee) * rfac;
+    if (!(ee >= P.ee_fast_min && ee <= P.max_diag)) {
+        const double se = depth_scale_at_start(L, P.base);
+        const double se2 = se * se, ees = ee * se2;
+        q = se2 / (ees + fmin(fmax(ees, P.min_diag), P.max_diag) * inv_radius);
+    }
+    // F delta_f = -beta (d A dv + B dw) - dbeta p dk; the increments of A v and B w are reused for the candidate
+    double da0 = 0.0, da1 = 0.0, db0 = 0.0, db1 = 0.0, m0 = 0.0, m1 = 0.0;
+    if (NF >= 6) {
+        const double *df = P.delta_f;
+        da0 = fma(-x, df[2], df[0]); da1 = fma(-y, df[2], df[1]);
+        db0 = fma(-xy, df[3], fma(xx1, df[4], -y * df[5]));
+        db1 = fma(-yy1, df[3], fma(xy, df[4], x * df[5]));
+        m0 = -beta * fma(d, da0, db0);
+        m1 = -beta * fma(d, da1, db1);
+        if (NF == 7) {
+            const double dbk = c2 * fma(-ak, 0.5 * c2, L.a.y) * df[6];
+            m0 = fma(-dbk, p0, m0);
+            m1 = fma(-dbk, p1, m1);
+        }
+    }
+    const double delta_e = -q * fma(e0, r0 + m0, e1 * (r1 + m1));
+    const double j0 = fma(e0, delta_e, m0), j1 = fma(e1, delta_e, m1);                    // J delta
+    double dc = d + delta_e;
+    const double dd = d - dc;
+    if (valid) {
+        d_cand[index] = dc;
+        acc[T::oMCC] += fma(j0, fma(0.5, j0, r0), j1 * fma(0.5, j1, r1));
+        acc[T::oSTEP] = fma(dd, dd, acc[T::oSTEP]);
+        if (not_finite(delta_e)) S.flags |= 4u;
+    } else {
+        dc = 1.0;
+    }
+    // ---- at the candidate
+    const double akc = fma(P.cand.k, L.a.y, L.a.x), betac = c2c * akc;
+    eval_pixel<NF>(L, valid, index, xy, xx1, yy1, akc, betac, c2c, a0 + da0, a1 + da1, b0 + db0, b1 + db1, dc, false, P, P.cand, acc, S,
+                   kv, sv, ks, ss, n_exc, overflow, exc, exc_cap);
+}
+
+template <int NF>
+__device__ __forceinline__ void accumulate_held(const Held<NF> &h, double (&acc)[TAcc<NF>::NV])
+{
+    using T = TAcc<NF>;
+    int t = 0;
+#pragma unroll
+    for (int j = 0; j < NF; ++j) {
+        acc[T::oH + j] = fma(h.kv[j], h.ks, fma(h.pv[j], h.ps, acc[T::oH + j]));
+#pragma unroll
+        for (int c = j; c < NF; ++c, ++t) acc[T::oK + t] = fma(h.kv[j], h.kv[c], fma(h.pv[j], h.pv[c], acc[T::oK + t]));
+    }
+}
+
+struct SolveArgs {
+    RefineData D;
+    double *d0, *d1;
+    LmShared *sh;
+    double *partials;            // [2][gridDim.x][Acc<NF>::NV]: rows of even / odd phases
+    ExcEntry *exc;               // [kExcSlots][exc_cap]
+    unsigned int exc_cap;
+    const double *z_in;
+    int z_stride;
+    double *out;
+    int invert_out;
+    double *zstats;
+};
+
+template <int NF>
+__global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
+{
+    using A = Acc<NF>;
+    using T = TAcc<NF>;
+    constexpr int LD = kRowVals<NF>;
+    constexpr int NFa = NF > 0 ? NF : 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Stage *stages = reinterpret_cast<Stage *>(smem_raw);
+    __shared__ __align__(8) uint64_t full[kStages], empty[kStages];
+    __shared__ PhaseParams P;
+    __shared__ LmController s_ctl;
+    __shared__ double fin[LD];
+    __shared__ double part[kWarps][LD];
+    __shared__ ExcSums s_exc;
+    __shared__ double s_L[7][8], s_y[8];
+    __shared__ int s_flag[8];     // [1] next, [2] n_exc of the current list, [3] accepted, [4] current slot, [5] error
+    __shared__ unsigned int s_ne[kExcSlots];
+
+    const RefineData D = A_.D;
+    double *const d0 = A_.d0, *const d1 = A_.d1;
+    LmShared *const sh = A_.sh;
+    ExcEntry *const exc = A_.exc;
+    const unsigned int exc_cap = A_.exc_cap;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x;
+    const int NT = (D.m + kTile - 1) / kTile;
+    const int n_my = ((int)blockIdx.x < NT) ? (NT - 1 - (int)blockIdx.x) / G + 1 : 0;
+    const int pre = n_my < kStages ? n_my : kStages;              // tiles queued ahead of a phase
+    unsigned int gen = 0;
+    unsigned int consumed = 0;                                    // tile uses consumed by this CTA since kernel start
+    unsigned int issued = 0;                                      // (thread 0) tile uses queued since kernel start
+    // exception lists: cur = list of the current point, spec = list the FUSED evaluation appends to,
+    // zero = list that thread 0 of CTA 0 clears during this phase (it becomes `spec` of the next phase)
+    int slot_cur = 0, slot_spec = 1, slot_zero = 2;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // replicated controller state + first phase parameters (written by k_lm_begin)
+    for (int w = tid; w < (int)(sizeof(LmController) / sizeof(int)); w += kThreads)
+        reinterpret_cast<int *>(&s_ctl)[w] = __ldcg(reinterpret_cast<const int *>(&sh->ctl) + w);
+    if (tid < (int)(sizeof(Bcast) / sizeof(int)))
+        reinterpret_cast<int *>(&P)[tid] = __ldcg(reinterpret_cast<const int *>(&sh->bc) + tid);
+    if (tid < (int)(sizeof(Motion) / sizeof(int)))
+        reinterpret_cast<int *>(&P.base)[tid] = __ldcg(reinterpret_cast<const int *>(&sh->base) + tid);
+    if (tid == 64) {
+        P.min_diag = __ldcg(&sh->ctl.opt.min_lm_diagonal); P.max_diag = __ldcg(&sh->ctl.opt.max_lm_diagonal);
+        P.error = 0;
+    }
+    __syncthreads();
+
+    // queue tile uses [issued, upto): use u is tile (u - phase_base) of the phase that reads depth buffer `dsrc`
+    auto queue_uses = [&](unsigned int upto, unsigned int phase_base, const double *dsrc, bool blocking) {
+        while (issued < upto) {
+            const int s = (int)(issued % kStages);
+            if (issued >= (unsigned)kStages) {
+                const unsigned par = ((issued / kStages) - 1u) & 1u;           // completion of the stage's previous use
+                if (blocking) mbar_wait(&empty[s], par);
+                else if (!mbar_test(&empty[s], par)) break;
+            }
+            fence_proxy_async();
+            issue_tile(D, dsrc, (int)blockIdx.x + (int)(issued - phase_base) * G, &stages[s], &full[s]);
+            ++issued;
+        }
+    };
+    if (tid == 0 && P.next != LM_DONE) queue_uses((unsigned)pre, 0u, P.which_x ? d1 : d0, true);
+
+    for (;;) {
+        if (P.next == LM_DONE || P.error) break;
+        const bool run_init = (P.next == LM_RUN_A);
+        double *dx = P.which_x ? d1 : d0;
+        double *dcand = P.which_x ? d0 : d1;
+        const int elist = run_init ? slot_cur : slot_spec;
+        unsigned int *n_exc = &sh->n_exc[elist];
+        ExcEntry *elist_p = exc + (size_t)elist * exc_cap;
+        const unsigned long long t_begin = (blockIdx.x == 0 && tid == 0) ? globaltimer() : 0ull;
+        if (blockIdx.x == 0 && tid == 0 && !run_init) sh->n_exc[slot_zero] = 0u;
+        const unsigned int base = consumed;
+
+        double acc[T::NV];
+#pragma unroll
+        for (int j = 0; j < T::NV; ++j) acc[j] = 0.0;
+        SweepScalars S;
+        S.gmax = 0ull; S.eemax = 0ull; S.flags = 0u;
+        Held<NF> held;
+#pragma unroll
+        for (int j = 0; j < NFa; ++j) { held.kv[j] = 0.0; held.pv[j] = 0.0; }
+        held.ks = 0.0; held.ps = 0.0;
+        const double c2 = 2.0 / (2.0 + P.mot.k), c2c = 2.0 / (2.0 + P.cand.k);
+        const double rfac = P.radius / (P.radius + 1.0), inv_radius = 1.0 / P.radius;
+
+        // ---- the sweep: 2 steps per 512-block tile, one residual block per thread and step
+        // (the arrays are padded to whole tiles with whatever the allocation held: blocks past the end are replaced
+        //  by a harmless constant block as they are read)
+        auto load_block = [&](const Stage &st, int j, int index) {
+            Loaded X;
+            X.p = st.xy[j]; X.u = st.uu[j]; X.a = st.aa[j]; X.d = st.d[j];
+            if (index >= D.m) { X.p = make_double2(0.0, 0.0); X.u = X.p; X.a = make_double2(1.0, 0.0); X.d = 1.0; }
+            return X;
+        };
+        Loaded Ln;
+        Ln.p = make_double2(0.0, 0.0); Ln.u = Ln.p; Ln.a = make_double2(1.0, 0.0); Ln.d = 1.0;
+        if (n_my > 0) {
+            const int s = (int)(base % kStages);
+            mbar_wait(&full[s], (base / kStages) & 1u);
+            Ln = load_block(stages[s], tid, (int)blockIdx.x * kTile + tid);
+        }
+        for (int k = 0; k < n_my; ++k) {
+            const unsigned int g = base + (unsigned)k;
+            const int s = (int)(g % kStages);
+            const int base_i = ((int)blockIdx.x + k * G) * kTile;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const Loaded L = Ln;
+                const int idx = base_i + tid + half * kThreads;
+                const bool valid = idx < D.m;
+                // fetch the next step's residual block while this one is computed
+                if (half == 0) {
+                    Ln = load_block(stages[s], tid + kThreads, base_i + tid + kThreads);
+                    // this warp has read both halves of the stage: release it (one arrival per warp)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[s]);
+                } else {
+                    // producer: the next tile must be on its way before anybody waits for it (blocks only if a warp
+                    // still holds the stage that tile needs); beyond that, refill whatever has been released
+                    if (tid == 0) {
+                        const unsigned int lim = base + (unsigned)n_my;
+                        queue_uses(g + 2u < lim ? g + 2u : lim, base, dx, true);
+                        queue_uses(lim, base, dx, false);
+                    }
+                    if (k + 1 < n_my) {
+                        const int s1 = (int)((g + 1u) % kStages);
+                        mbar_wait(&full[s1], ((g + 1u) / kStages) & 1u);
+                        Ln = load_block(stages[s1], tid, base_i + G * kTile + tid);
+                    }
+                }
+                // rank-1 updates of the previous step (independent of everything below) ...
+                accumulate_held<NF>(held, acc);
+                // ... and this step's residual / Jacobian chain
+                double kv[NFa], sv[NFa], ks, ss;
+                if (run_init)
+                    init_pixel<NF>(L, valid, idx, P, c2, acc, S, kv, sv, ks, ss, n_exc, &sh->exc_overflow, elist_p, exc_cap);
+                else
+                    fused_pixel<NF>(L, valid, idx, P, c2, c2c, rfac, inv_radius, acc, S, dcand, kv, sv, ks, ss, n_exc, &sh->exc_overflow,
+                                    elist_p, exc_cap);
+                if (NF > 0) {
+#pragma unroll
+                    for (int j = 0; j < NF; ++j) { held.kv[j] = kv[j]; held.pv[j] = __shfl_xor_sync(0xffffffffu, sv[j], 1); }
+                    held.ks = ks;
+                    held.ps = __shfl_xor_sync(0xffffffffu, ss, 1);
+                }
+            }
+        }
+        accumulate_held<NF>(held, acc);
+        consumed += (unsigned)n_my;
+        acc[T::iGMAX] = __longlong_as_double((long long)S.gmax);
+        acc[T::iEEMAX] = __longlong_as_double((long long)S.eemax);
+        acc[T::iBADRES] = (S.flags & 1u) ? 1.0 : 0.0;
+        acc[T::iBAD] = (S.flags & 2u) ? 1.0 : 0.0;
+        acc[T::iBADSTEP] = (S.flags & 4u) ? 1.0 : 0.0;
+        // the candidate depths written above are read by TMA in the next phase: order them for the async proxy
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __syncthreads();
+        const unsigned long long t_loop = t_begin ? globaltimer() : 0ull;
+        double *row = A_.partials + ((size_t)(gen & 1u) * G + blockIdx.x) * A::NV;
+        cta_reduce_roles<NF, LD>(acc, part, row);
+        // ---- arrive; then queue the next phase's first tiles (depth: from the buffer an ACCEPTED step makes current)
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(&sh->arrive, 1u);
+            if (t_begin) {
+                const unsigned long long t2 = globaltimer();
+                atomicAdd(&sh->t_phase[run_init ? 4 : 7], t_loop - t_begin); atomicAdd(&sh->t_phase[run_init ? 5 : 8], t2 - t_loop);
+            }
+            queue_uses(consumed + (unsigned)pre, consumed, run_init ? dx : dcand, true);
+            const unsigned long long t0 = globaltimer();
+            const unsigned int target = (gen + 1u) * (unsigned)G;
+            int err = 0;
+            while ((int)(ld_acquire(&sh->arrive) - target) < 0) {
+                __nanosleep(20);
+                if (globaltimer() - t0 > kWatchdogNs) { err = 1; sh->error = 1; break; }
+            }
+            if (!err && __ldcg(&sh->error)) err = 1;
+            s_flag[5] = err;
+        }
+        __syncthreads();
+        if (s_flag[5]) {                                          // watchdog: give up, but leave no bulk copy in flight
+            for (unsigned int u = consumed; u < consumed + (unsigned)pre; ++u) mbar_wait(&full[(int)(u % kStages)], (u / kStages) & 1u);
+            if (tid == 0) P.error = 1;
+            __syncthreads();
+            break;
+        }
+        const unsigned long long t_ctl = t_begin ? globaltimer() : 0ull;
+
+        // ---- every CTA: sum the G rows in a fixed order (warp w: rows w, w+8, ...; lanes: columns)
+        {
+            constexpr int nv = A::NV, ns = A::NS;
+            const double *rows = A_.partials + (size_t)(gen & 1u) * G * A::NV;
+            if (tid < kExcSlots) s_ne[tid] = __ldcg(&sh->n_exc[tid]);
+            constexpr int kRowsPerWarp = (kNumSMsB200 + kWarps - 1) / kWarps;      // 19
+            double v[3] = {0.0, 0.0, 0.0};
+            if (G <= kNumSMsB200) {
+                double t[kRowsPerWarp][3];
+#pragma unroll
+                for (int u = 0; u < kRowsPerWarp; ++u) {
+                    const int b = u * kWarps + warp;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int j = lane + 32 * c;
+                        t[u][c] = (b < G && j < nv) ? __ldcg(rows + (size_t)b * A::NV + j) : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kRowsPerWarp; ++u)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int j = lane + 32 * c;
+                        v[c] = (j < ns) ? v[c] + t[u][c] : fmax(v[c], t[u][c]);
+                    }
+            } else {
+                for (int b = warp; b < G; b += kWarps)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int j = lane + 32 * c;
+                        const double x = (j < nv) ? __ldcg(rows + (size_t)b * A::NV + j) : 0.0;
+                        v[c] = (j < ns) ? v[c] + x : fmax(v[c], x);
+                    }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { const int j = lane + 32 * c; if (j < nv) part[warp][j] = v[c]; }
+            __syncthreads();
+            if (tid < nv) {
+                double x = part[0][tid];
+                if (tid < ns) for (int w = 1; w < kWarps; ++w) x += part[w][tid];
+                else          for (int w = 1; w < kWarps; ++w) x = fmax(x, part[w][tid]);
+                fin[tid] = x;
+            }
+            __syncthreads();
+        }
+        const unsigned long long t_fin = t_begin ? globaltimer() : 0ull;
+        // ---- FUSED: judge the candidate first
+        if (tid == 0) {
+            int accepted = run_init ? 1 : 0;
+            LmNext nx = LM_RUN_A;
+            if (!run_init) {
+                CandSums c;
+                c.mcc = fin[A::oMCC]; c.step_sq = fin[A::oSTEP]; c.cand_cost = 0.5 * fin[0];
+                c.bad_step = fin[A::iBADSTEP]; c.bad_cand = fin[A::iBADRES];
+                nx = s_ctl.on_candidate(c);
+                accepted = (nx == LM_RUN_A) ? 1 : 0;
+            }
+            s_flag[1] = (int)nx;
+            s_flag[3] = accepted;
+            const int cur = run_init ? slot_cur : (accepted ? slot_spec : slot_cur);
+            s_flag[4] = cur;
+            const unsigned int ne = s_ne[cur];
+            s_flag[2] = (int)(ne < exc_cap ? ne : exc_cap);
+        }
+        __syncthreads();
+        const bool accepted = s_flag[3] != 0;
+        if (!run_init) {
+            // the list that is not current any more is cleared during the next phase and reused after it
+            const int dead = accepted ? slot_cur : slot_spec;
+            slot_cur = s_flag[4];
+            slot_spec = slot_zero;
+            slot_zero = dead;
+        }
+        if (accepted) {
+            // the evaluation sums of this pass describe the (new) current point: EvalSums in place
+            if (tid < kTri) {
+                s_ctl.ev.G1[tid] = (tid < A::TRI) ? fin[A::oG1 + (tid < A::TRI ? tid : 0)] : 0.0;
+                s_ctl.ev.G2[tid] = (tid < A::TRI) ? fin[A::oG2 + (tid < A::TRI ? tid : 0)] : 0.0;
+            }
+            if (tid < kMaxNF) {
+                s_ctl.ev.h1[tid] = (tid < NF) ? fin[A::oH1 + (tid < NF ? tid : 0)] : 0.0;
+                s_ctl.ev.h2[tid] = (tid < NF) ? fin[A::oH2 + (tid < NF ? tid : 0)] : 0.0;
+            }
+            if (tid == 32) {
+                s_ctl.ev.cost = 0.5 * fin[0]; s_ctl.ev.sumsq_d = fin[1]; s_ctl.ev.gmax_e = fin[A::iGMAX];
+                s_ctl.ev.bad = fin[A::iBAD]; s_ctl.ev.ee_max = fin[A::iEEMAX];
+            }
+            __syncthreads();
+        }
+        // the pixel ring may hold prefetched tiles: the sort keys of the (rare) listed pixels live in the row scratch
+        // of the last stage only when the ring is idle, so listed pixels first drain the ring (see below)
+        bool xsorted = false;
+        unsigned long long *xkeys = reinterpret_cast<unsigned long long *>(smem_raw);
+        bool drained = false;
+        if constexpr (NF > 0) if (s_flag[2] > 0) {
+            // listed pixels: the controller needs scratch for their sort keys -- give up the prefetched tiles
+            for (unsigned int u = consumed; u < consumed + (unsigned)pre; ++u) {
+                const int s = (int)(u % kStages);
+                mbar_wait(&full[s], (u / kStages) & 1u);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+            }
+            consumed += (unsigned)pre;
+            drained = true;
+            __syncthreads();
+            xsorted = sort_exceptions(exc + (size_t)s_flag[4] * exc_cap, s_flag[2], xkeys, 16384, tid);
+        }
+        if (accepted) {
+            if constexpr (NF > 0) if (s_flag[2] > 0) {
+                const ExcEntry *cur_exc = exc + (size_t)s_flag[4] * exc_cap;
+                double a[kExcVals];
+#pragma unroll
+                for (int j = 0; j < kExcVals; ++j) a[j] = 0.0;
+                for (int k = tid; k < s_flag[2]; k += kThreads) {
+                    const int slot = xsorted ? (int)(unsigned int)(xkeys[k] & 0xffffffffull) : k;
+                    ExcEntry X;
+                    for (int w = 0; w < (int)(sizeof(ExcEntry) / sizeof(double)); ++w)
+                        reinterpret_cast<double *>(&X)[w] = __ldcg(reinterpret_cast<const double *>(cur_exc + slot) + w);
+                    int t = 0;
+#pragma unroll
+                    for (int j = 0; j < NF; ++j) {
+                        a[kTri + j] += fma(X.F0[j], X.r0, X.F1[j] * X.r1);
+#pragma unroll
+                        for (int c = j; c < NF; ++c, ++t) a[t] += fma(X.F0[j], X.F0[c], X.F1[j] * X.F1[c]);
+                    }
+                }
+                cta_reduce_sums<kExcVals, LD>(a, part, fin);
+                if (tid < A::TRI) s_ctl.ev.G1[tid] += fin[tid];
+                if (tid < NF) s_ctl.ev.h1[tid] += fin[kTri + tid];
+                __syncthreads();
+            }
+            if (warp == 0) {
+                const int nx = ctl_on_eval<NF>(s_ctl);
+                if (lane == 0) s_flag[1] = nx;
+            }
+            __syncthreads();
+        }
+        // ---- (re)solve at the current radius; the clamped-pixel correction is summed by the whole CTA
+        while (s_flag[1] == (int)LM_SOLVE) {
+            const int ne = s_flag[2];
+            if constexpr (NF > 0) if (ne > 0) {
+                const ExcEntry *cur_exc = exc + (size_t)s_flag[4] * exc_cap;
+                const double R = s_ctl.radius, lo = s_ctl.opt.min_lm_diagonal, hi = s_ctl.opt.max_lm_diagonal;
+                double a[kExcVals];
+#pragma unroll
+                for (int j = 0; j < kExcVals; ++j) a[j] = 0.0;
+                for (int k = tid; k < ne; k += kThreads) {
+                    const int slot = xsorted ? (int)(unsigned int)(xkeys[k] & 0xffffffffull) : k;
+                    ExcEntry X;
+                    for (int w = 0; w < (int)(sizeof(ExcEntry) / sizeof(double)); ++w)
+                        reinterpret_cast<double *>(&X)[w] = __ldcg(reinterpret_cast<const double *>(cur_exc + slot) + w);
+                    const double q = X.se2 / (X.ees + fmin(fmax(X.ees, lo), hi) / R);
+                    const double er = fma(X.e0, X.r0, X.e1 * X.r1);
+                    double fe[NFa];
+#pragma unroll
+                    for (int j = 0; j < NF; ++j) fe[j] = fma(X.F0[j], X.e0, X.F1[j] * X.e1);
+                    int t = 0;
+#pragma unroll
+                    for (int j = 0; j < NF; ++j) {
+                        const double qf = q * fe[j];
+                        a[kTri + j] = fma(qf, er, a[kTri + j]);
+#pragma unroll
+                        for (int c = j; c < NF; ++c, ++t) a[t] = fma(qf, fe[c], a[t]);
+                    }
+                }
+                cta_reduce_sums<kExcVals, LD>(a, part, fin);
+                if (tid < kTri) s_exc.S[tid] = fin[tid];
+                if (tid < kMaxNF) s_exc.rhs[tid] = fin[kTri + tid];
+                __syncthreads();
+            }
+            if (warp == 0) {
+                const int nx = ctl_solve<NF>(s_ctl, (NF > 0 && ne > 0) ? &s_exc : nullptr, s_L, s_y);
+                if (lane == 0) s_flag[1] = nx;
+            }
+            __syncthreads();
+        }
+        // ---- next phase parameters (every CTA writes its own copy)
+        const bool which_changed = !run_init && accepted;
+        if (tid == 0) {
+            const LmNext nx = (LmNext)s_flag[1];                     // LM_RUN_B (another fused pass) or LM_DONE
+            if (which_changed) P.which_x ^= 1;                       // the candidate became x
+            Motion mo = P.base, ca = P.base;
+            if (NF >= 6) for (int j = 0; j < 3; ++j) {
+                mo.v[j] = s_ctl.f[j]; mo.w[j] = s_ctl.f[3 + j];
+                ca.v[j] = s_ctl.f[j] + s_ctl.delta_f[j]; ca.w[j] = s_ctl.f[3 + j] + s_ctl.delta_f[3 + j];
+            }
+            if (NF == 7) { mo.k = s_ctl.f[6]; ca.k = s_ctl.f[6] + s_ctl.delta_f[6]; }
+            if (nx == LM_DONE && s_ctl.termination == RSDSFM_FAILURE) mo = P.base;   // Ceres restores the start values
+            P.mot = mo; P.cand = ca;
+            for (int j = 0; j < kMaxNF; ++j) P.delta_f[j] = s_ctl.delta_f[j];
+            P.radius = s_ctl.radius;
+            P.ee_fast_min = s_ctl.ee_fast_min;
+            P.first = 0;
+            P.next = (int)nx;
+            if (t_begin) {
+                const unsigned long long t_end = globaltimer();
+                atomicAdd(&sh->t_phase[run_init ? 10 : 11], t_end - t_fin);
+                atomicAdd(&sh->t_phase[run_init ? 6 : 9], t_end - t_ctl);
+                atomicAdd(&sh->t_phase[run_init ? 0 : 2], t_end - t_begin); atomicAdd(&sh->t_phase[run_init ? 1 : 3], 1ull);
+            }
+        }
+        __syncthreads();
+        gen++;
+        // ---- the depth prefetch assumed "accepted" (or INIT): anything else reloads the first tiles
+        const bool spec_ok = run_init || accepted;
+        if (P.next != LM_DONE && (!spec_ok || drained)) {
+            if (!drained) {
+                for (unsigned int u = consumed; u < consumed + (unsigned)pre; ++u) {
+                    const int s = (int)(u % kStages);
+                    mbar_wait(&full[s], (u / kStages) & 1u);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[s]);
+                }
+                consumed += (unsigned)pre;
+            }
+            if (tid == 0) queue_uses(consumed + (unsigned)pre, consumed, P.which_x ? d1 : d0, true);
+        } else if (P.next == LM_DONE && !drained) {
+            // leave no bulk copy in flight when the CTA exits
+            for (unsigned int u = consumed; u < consumed + (unsigned)pre; ++u) mbar_wait(&full[(int)(u % kStages)], (u / kStages) & 1u);
+        }
+    }
+
+    // ---- the result: CTA 0 publishes the controller state and the final motion
+    if (blockIdx.x == 0) {
+        __syncthreads();
+        for (int w = tid; w < (int)(sizeof(LmController) / sizeof(int)); w += kThreads)
+            reinterpret_cast<int *>(&sh->ctl)[w] = reinterpret_cast<const int *>(&s_ctl)[w];
+        if (tid < (int)(sizeof(Bcast) / sizeof(int)))
+            reinterpret_cast<int *>(&sh->bc)[tid] = reinterpret_cast<const int *>(&P)[tid];
+    }
+    // ---- epilogue: write the result (z = 1/d for a9, d for a8).  On FAILURE Ceres restores the
+    // start values (solver.cc Minimize): 1/z_in for a9 (double reciprocal, :213/:247), 1.0 for a8.
+    const bool failed = (s_ctl.termination == RSDSFM_FAILURE) || P.error;
+    const double *dfin = P.which_x ? d1 : d0;
+    double zs[1] = {0.0}, zm[2] = {-INFINITY, -INFINITY};
+    for (int i = blockIdx.x * kThreads + tid; i < D.m; i += G * kThreads) {
+        double dv;
+        if (failed) dv = A_.z_in ? 1.0 / A_.z_in[(size_t)i * A_.z_stride] : 1.0;
+        else dv = dfin[i];
+        const double o = A_.invert_out ? 1.0 / dv : dv;
+        A_.out[i] = o;
+        zs[0] += o; zm[0] = fmax(zm[0], o); zm[1] = fmax(zm[1], -o);
+    }
+    if (A_.zstats) block_reduce_store<1, 2>(zs, zm, A_.zstats);
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+// RSDSFM_LM_VARIANT=1 selects the first-generation kernel (A/B measurements); default: k_lm_solve
+static int lm_variant()
+{
+    static const int v = [] { const char *e = getenv("RSDSFM_LM_VARIANT"); return e ? atoi(e) : 2; }();
+    return v;
+}
+
 template <int NF>
 static int launch_persistent(rsdsfm_ctx *ctx, RefineData D, double *d0, double *d1, LmShared *sh, double *partials,
                              ExcEntry *exc, unsigned int exc_cap, const double *z_in, int z_stride, double *out,
                              int invert_out, double *zstats, int grid)
 {
     const size_t smem = sizeof(Stage) * (size_t)kStages;
-    RS_CUDA(ctx, cudaFuncSetAttribute(k_lm_persistent<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    void *args[] = {&D, &d0, &d1, &sh, &partials, &exc, &exc_cap, &z_in, &z_stride, &out, &invert_out, &zstats};
     if (ctx->profile) cudaEventRecord(ctx->pe0[ctx->io_slot], ctx->stream);
-    RS_CUDA(ctx, cudaLaunchCooperativeKernel((void *)k_lm_persistent<NF>, dim3(grid), dim3(kThreads), args, smem, ctx->stream));
+    if (lm_variant() == 1) {
+        RS_CUDA(ctx, cudaFuncSetAttribute(k_lm_persistent<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        void *args[] = {&D, &d0, &d1, &sh, &partials, &exc, &exc_cap, &z_in, &z_stride, &out, &invert_out, &zstats};
+        RS_CUDA(ctx, cudaLaunchCooperativeKernel((void *)k_lm_persistent<NF>, dim3(grid), dim3(kThreads), args, smem, ctx->stream));
+    } else {
+        RS_CUDA(ctx, cudaFuncSetAttribute(k_lm_solve<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SolveArgs a{D, d0, d1, sh, partials, exc, exc_cap, z_in, z_stride, out, invert_out, zstats};
+        void *args[] = {&a};
+        RS_CUDA(ctx, cudaLaunchCooperativeKernel((void *)k_lm_solve<NF>, dim3(grid), dim3(kThreads), args, smem, ctx->stream));
+    }
     if (ctx->profile) cudaEventRecord(ctx->pe1[ctx->io_slot], ctx->stream);
     ctx->launches++;
     return RSDSFM_OK;
@@ -1130,9 +1807,9 @@ static int lm_solve_async(rsdsfm_ctx *ctx, const RefineData &D, double *d0, doub
     LmShared *sh = (LmShared *)ctx->lm_shared.p;
     const int grid = lm_grid_size(ctx);                 // one persistent CTA per SM (half of them in a two-lane sequence)
     const int nv = (nf == 0) ? Acc<0>::NV : (nf == 6 ? Acc<6>::NV : Acc<7>::NV);
-    RS_TRY(ensure(ctx, ctx->partials, sizeof(double) * (size_t)grid * nv));
+    RS_TRY(ensure(ctx, ctx->partials, sizeof(double) * 2 * (size_t)grid * nv));   // rows of even / odd phases
     if (ctx->exc_cap < min_exc_cap()) ctx->exc_cap = min_exc_cap();
-    RS_TRY(ensure(ctx, ctx->exc, sizeof(ExcEntry) * 2 * (size_t)ctx->exc_cap));   // current + speculative list
+    RS_TRY(ensure(ctx, ctx->exc, sizeof(ExcEntry) * kExcSlots * (size_t)ctx->exc_cap));   // current + speculative + being cleared
     static_assert(sizeof(LmShared) <= 8192 - 256, "pinned slot layout (common.cuh)");
 
     // initial control block: built on the host, passed by value to k_lm_begin
@@ -1179,6 +1856,8 @@ int lm_collect_finish(rsdsfm_ctx *ctx, int nf, int m, Motion *mot, rsdsfm_lm_sum
 {
     LmShared *h = (LmShared *)pinned_lm_result(ctx);
     if (h->error) return fail(ctx, RSDSFM_ERR_INTERNAL, "LM kernel: grid barrier watchdog tripped");
+    if (h->nonfinite_input & 2)
+        return fail(ctx, RSDSFM_ERR_ARG, "compact input: n / m do not match the flow field and the consensus mask");
     *overflow = h->exc_overflow != 0;
     if (*overflow) { if (ctx->exc_cap < m + 1024) ctx->exc_cap = m + 1024; return RSDSFM_OK; }
     float kms = 0.f;
@@ -1232,9 +1911,9 @@ static int ensure_lm_buffers(rsdsfm_ctx *ctx, size_t mm)
 int lm_reserve(rsdsfm_ctx *ctx, int m)
 {
     RS_TRY(ensure_lm_buffers(ctx, (size_t)(m > 0 ? m : 1)));
-    RS_TRY(ensure(ctx, ctx->partials, sizeof(double) * (size_t)ctx->num_sms * Acc<7>::NV));
+    RS_TRY(ensure(ctx, ctx->partials, sizeof(double) * 2 * (size_t)ctx->num_sms * Acc<7>::NV));
     if (ctx->exc_cap < min_exc_cap()) ctx->exc_cap = min_exc_cap();
-    return ensure(ctx, ctx->exc, sizeof(ExcEntry) * 2 * (size_t)ctx->exc_cap);
+    return ensure(ctx, ctx->exc, sizeof(ExcEntry) * kExcSlots * (size_t)ctx->exc_cap);
 }
 
 // a9 on device pointers: queues gather + solve on the stream, no synchronisation.
@@ -1257,6 +1936,32 @@ int refine_async(rsdsfm_ctx *ctx, const double *flow, const double *inliers3, co
     for (int j = 0; j < 3; ++j) { mot.v[j] = v[j]; mot.w[j] = w[j]; }
     mot.k = k;
     return lm_solve_async(ctx, D, d0, d1, const_acc ? 7 : 6, mot, o, inliers3 + 2, 3, z_out, 1, true, zstats);
+}
+
+// The solver's input buffers for m residual blocks, for a producer that fills them itself
+// (preproc.cu: compact_build_device): tile-blocked blk, the start inverse depths d0, and the
+// device flag the producer raises for bad input (1: non-finite start depth, 2: count mismatch).
+int lm_input_buffers(rsdsfm_ctx *ctx, int m, void **blk, double **d0, int **input_flag)
+{
+    RS_TRY(ensure_lm_buffers(ctx, (size_t)(m > 0 ? m : 1)));
+    LmShared *sh = (LmShared *)ctx->lm_shared.p;
+    RS_CUDA(ctx, cudaMemsetAsync(&sh->nonfinite_input, 0, sizeof(int), ctx->stream));
+    *blk = ctx->pix.p; *d0 = (double *)ctx->dA.p; *input_flag = &sh->nonfinite_input;
+    return RSDSFM_OK;
+}
+
+// a9 on buffers filled through lm_input_buffers: queues the solve, no synchronisation.
+// z_in[m]: the start depths (restored on FAILURE, like Ceres restores its parameter blocks).
+int refine_prepared_async(rsdsfm_ctx *ctx, int m, const double *v, const double *w, double k, int const_acc,
+                          const rsdsfm_lm_options *opts, const double *z_in, double *z_out, double *zstats)
+{
+    rsdsfm_lm_options o;
+    if (opts) o = *opts; else rsdsfm_lm_default_options(&o);
+    RefineData D{(const double2 *)ctx->pix.p, m};
+    Motion mot;
+    for (int j = 0; j < 3; ++j) { mot.v[j] = v[j]; mot.w[j] = w[j]; }
+    mot.k = k;
+    return lm_solve_async(ctx, D, (double *)ctx->dA.p, (double *)ctx->dB.p, const_acc ? 7 : 6, mot, o, z_in, 1, z_out, 1, true, zstats);
 }
 
 // a9, synchronous: returns the refined motion and the summary on the host.

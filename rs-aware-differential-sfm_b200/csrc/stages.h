@@ -37,6 +37,14 @@ int refine_device(rsdsfm_ctx *, const double *flow, const double *inliers3, cons
 int refine_async(rsdsfm_ctx *, const double *flow, const double *inliers3, const double *alpha, const double *alpha_k,
                  int m, const double *v, const double *w, double k, int const_acc, const int32_t *flow_index,
                  const rsdsfm_lm_options *, double *z_out, double *zstats_rows = nullptr);   // zstats_rows: num_sms x 3, see glue_device
+// the same solve on inputs a producer kernel wrote straight into the solver's layout (compact step inputs)
+int lm_input_buffers(rsdsfm_ctx *, int m, void **blk, double **d0, int **input_flag);
+int refine_prepared_async(rsdsfm_ctx *, int m, const double *v, const double *w, double k, int const_acc,
+                          const rsdsfm_lm_options *, const double *z_in, double *z_out, double *zstats_rows);
+// flow field + RANSAC winner (mask, inverse depths over the flattened points) -> solver layout (preproc.cu)
+int compact_build_device(rsdsfm_ctx *, const void *flow_img, int flow_f32, int rows, int cols, const double *K4, double gamma,
+                         double thr, const uint8_t *mask, const double *inv_depth, int n, int m, void *blk, double *d0,
+                         double *z_in, double *xy, int *input_flag);
 int lm_grid_size(const rsdsfm_ctx *);                   // CTAs of the LM kernel = rows of its z statistics
 int lm_reserve(rsdsfm_ctx *, int m);                     // pre-sizes the solver's buffers for up to m residual blocks
 int lm_collect_enqueue(rsdsfm_ctx *, const double *stats_dev8);   // zero-copy read-back into the I/O slot's pinned area

@@ -899,3 +899,67 @@ def test_host_buffers_from_the_library(capi, ctx, oracle, case_cv):
     assert np.array_equal(got["rectified"], want["rectified"]) and np.array_equal(got["depth_map"], want["depth_map"])
     for hb in bufs:
         hb.free()
+
+
+# ---------------------------------------------------------------------------- compact host interface
+@pytest.mark.parametrize("mem", ["host", "device"])
+@pytest.mark.parametrize("f32", [False, True])
+def test_compact_sequence_equals_expanded_calls(ctx, oracle, synth, mem, f32):
+    """rsdsfm_refine_rectify_compact_sequence takes the flow field and rsdsfm_ransac's outputs (mask, inverse depths
+    over the flattened points) and rebuilds coordinates, alpha factors, pairing and start depths on the device:
+    the solver sees bit-identical inputs, so single-lane results are bit-identical to rsdsfm_refine_rectify on the
+    expanded arrays (m < n: the reference's flow pairing is active; zero-flow pixels are dropped)."""
+    import torch
+    rows, cols = 120, 160
+    K4 = helpers.small_K(8)
+    dev = torch.device("cuda", 0)
+    pairs, refs = [], []
+    for i in range(3):
+        P = synth.make_pair(rows, cols, K4, gamma=0.95, seed=60 + i, k=0.5, noise_sigma_px=0.1, outlier_frac=0.05 + 0.02 * i,
+                            zero_flow_frac=0.2, flow_f32=f32)
+        n, coord, flow, cpx, fpx = oracle.flatten(P["flow_img"], K4, 0.95)
+        alpha = oracle.get_alpha(fpx, n, rows, 0.95)
+        alpha_k = oracle.get_alpha_k(cpx, fpx, n, rows, 0.95)
+        R = ctx.ransac(coord[:2 * n], flow[:2 * n], alpha, alpha_k, n, True, synth.sample_list(n, 6, seed=80 + i), 0.01)
+        inl, a_in, ak_in, ix, m = ctx.gather_inliers(coord[:2 * n], alpha, alpha_k, n, R["mask"], R["inv_depth"])
+        assert 0 < m < n < rows * cols
+        refs.append(ctx.refine_rectify(flow[:2 * n], inl, a_in, ak_in, m, R["v"], R["w"], R["k"], True, False, P["image"], K4, 0.95))
+        fi = P["flow_img"].astype(np.float32) if f32 else P["flow_img"]
+        e = dict(flow_img=fi, image=P["image"], mask=R["mask"], inv_depth=R["inv_depth"], n=n, m=m, v=R["v"], w=R["w"], k=R["k"])
+        if mem == "device":
+            e = {k: (torch.from_numpy(np.ascontiguousarray(v)).to(dev) if isinstance(v, np.ndarray) and v.size > 7 else v) for k, v in e.items()}
+        pairs.append(e)
+    host = (lambda a: a.cpu().numpy()) if mem == "device" else (lambda a: a)
+    # one at a time (synchronous single-lane calls): bit-identical
+    for e, ref in zip(pairs, refs):
+        got = ctx.refine_rectify_compact_sequence([e], True, False, K4, 0.95)[0]
+        assert got["status"] == 0 and got["summary"]["iterations"] == ref["summary"]["iterations"]
+        assert np.array_equal(got["v"], ref["v"]) and np.array_equal(got["w"], ref["w"]) and got["k"] == ref["k"]
+        assert np.array_equal(host(got["z"]), ref["z"])
+        assert np.array_equal(host(got["depth_map"]), ref["depth_map"]) and np.array_equal(host(got["rectified"]), ref["rectified"])
+    # pipelined (host: one lane -> still bit-identical; device: two lanes -> to rounding), depth map not requested
+    res = ctx.refine_rectify_compact_sequence(pairs, True, False, K4, 0.95, want_depth_map=False)
+    for got, ref in zip(res, refs):
+        assert got["status"] == 0 and got["depth_map"] is None
+        assert got["summary"]["iterations"] == ref["summary"]["iterations"]
+        _motion_close(got["v"], ref["v"], "v"); _motion_close(got["w"], ref["w"], "w")
+        _depth_close(host(got["z"]), ref["z"])
+        diff = np.abs(host(got["rectified"]).astype(np.int32) - ref["rectified"].astype(np.int32)).max(axis=2)
+        assert (diff <= 1).mean() >= 0.999
+        if mem == "host":
+            assert np.array_equal(host(got["rectified"]), ref["rectified"]) and np.array_equal(host(got["z"]), ref["z"])
+
+
+def test_compact_sequence_rejects_wrong_counts(capi, ctx, oracle, case_cv):
+    """n / m are checked against the flow field and the mask on the device."""
+    c = case_cv
+    R = c["ransac"]
+    e = dict(flow_img=c["P"]["flow_img"], image=c["P"]["image"], mask=R["mask"], inv_depth=R["inv_depth"], n=c["n"], m=c["m"] - 1,
+             v=R["v"], w=R["w"], k=R["k"])
+    with pytest.raises(capi.RsdsfmError):
+        ctx.refine_rectify_compact_sequence([e], False, False, c["K4"], c["gamma"])
+    e["m"] = c["m"]
+    ok = ctx.refine_rectify_compact_sequence([e], False, False, c["K4"], c["gamma"])[0]
+    ref = ctx.refine_rectify(c["flow"], c["inliers3"], c["alpha_in"], c["alpha_k_in"], c["m"], R["v"], R["w"], R["k"], False, False,
+                             c["P"]["image"], c["K4"], c["gamma"])
+    assert ok["status"] == 0 and np.array_equal(ok["rectified"], ref["rectified"]) and np.array_equal(ok["z"], ref["z"])
