@@ -6,8 +6,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "librsdsfm.so")
+OBJ = os.path.join(HERE, "build" + os.environ.get("RSDSFM_BUILD_TAG", ""))
+LIB = os.path.join(HERE, os.environ.get("RSDSFM_LIB_NAME", "librsdsfm.so"))   # experiments: RSDSFM_LIB_NAME + RSDSFM_EXTRA_NVCC build a variant next to the product
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -25,7 +25,7 @@ UNITS = [
     ("rectify.cu", ["--fmad=false"]),
     ("preproc.cu", ["--fmad=false"]),
 ]
-HEADERS = ["common.cuh", "stages.h", "lm_controller.h", "lm_layout.h", "rs_math.cuh", "solve9.h", os.path.join("..", "..", "include", "rsdsfm.h")]
+HEADERS = ["common.cuh", "stages.h", "lm_controller.h", "lm_layout.h", "lm_kernel.cuh", "rs_math.cuh", "solve9.h", os.path.join("..", "..", "include", "rsdsfm.h")]
 
 
 def _nvcc():
@@ -52,7 +52,7 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc] + ARCH + COMMON + extra + ["-Xptxas", "-v"] * int(verbose) + ["-c", s, "-o", o]
+            cmd = [nvcc] + ARCH + COMMON + extra + os.environ.get("RSDSFM_EXTRA_NVCC", "").split() + ["-Xptxas", "-v"] * int(verbose) + ["-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if verbose or r.returncode != 0:
                 print(" ".join(cmd))

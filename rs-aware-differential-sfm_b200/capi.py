@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librsdsfm.so")
+LIB_PATH = os.environ.get("RSDSFM_LIB") or os.path.join(_HERE, "librsdsfm.so")   # RSDSFM_LIB: an experimental build (tools/)
 
 HOST, DEVICE = 0, 1
 DEPTH_COLMAJOR, DEPTH_ROWMAJOR = 0, 1

@@ -3,15 +3,15 @@
 //
 // Tile-blocked structure of arrays, tile = kTile residual blocks:
 //   blk[tile] = { xy[kTile] (x, y) | uu[kTile] (ux, uy) | aa[kTile] (alpha, alpha_k) } as double2,
-// 24 KB contiguous, so that a whole tile arrives with ONE TMA bulk copy; the inverse depths live in
-// separate planes d[2][tiles * kTile] (current point / candidate), 4 KB per tile.
+// 12 KB contiguous, so that a whole tile arrives with ONE TMA bulk copy; the inverse depths live in
+// separate planes d[2][tiles * kTile] (current point / candidate), 2 KB per tile.
 #pragma once
 
 #include <stddef.h>
 
 namespace rsdsfm {
 
-constexpr int kTile = 512;                      // residual blocks per tile (two per thread)
+constexpr int kTile = 256;                      // residual blocks per tile (one per thread of the solver CTA)
 
 #ifdef __CUDACC__
 __host__ __device__

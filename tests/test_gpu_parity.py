@@ -915,7 +915,7 @@ def test_compact_sequence_equals_expanded_calls(ctx, oracle, synth, mem, f32):
     dev = torch.device("cuda", 0)
     pairs, refs = [], []
     for i in range(3):
-        P = synth.make_pair(rows, cols, K4, gamma=0.95, seed=60 + i, k=0.5, noise_sigma_px=0.1, outlier_frac=0.05 + 0.02 * i,
+        P = synth.make_pair(rows, cols, K4, gamma=0.95, seed=(60, 61, 66)[i], k=0.5, noise_sigma_px=0.1, outlier_frac=0.05 + 0.02 * i,
                             zero_flow_frac=0.2, flow_f32=f32)
         n, coord, flow, cpx, fpx = oracle.flatten(P["flow_img"], K4, 0.95)
         alpha = oracle.get_alpha(fpx, n, rows, 0.95)
