@@ -388,7 +388,7 @@ struct __align__(16) SweepU {
 };
 
 template <int NF>
-__device__ __noinline__ void sweep_uniforms(const PhaseParams *Pp, SweepU *Up)
+__device__ __forceinline__ void sweep_uniforms(const PhaseParams *Pp, SweepU *Up)
 {
     const PhaseParams &P = *Pp;
     SweepU U;
@@ -626,7 +626,7 @@ __device__ __forceinline__ void cta_reduce_sums(const double (&v)[NS], double (*
 // LmController::on_eval_stored / solve_step (which the host-stepped RANSAC solver keeps using).
 // ------------------------------------------------------------------------------------------
 template <int NF>
-__device__ __noinline__ int ctl_on_eval(LmController &c)
+__device__ __forceinline__ int ctl_on_eval(LmController &c)
 {
     const int lane = threadIdx.x & 31;
     const bool bad = c.ev.bad > 0.0;
@@ -676,7 +676,7 @@ __device__ __noinline__ int ctl_on_eval(LmController &c)
 // shuffle; the factor's columns are fetched once through the shared scratch Lm for the backward
 // substitution.  Eigen::LLT semantics: the solve fails on a non-positive or NaN pivot.
 template <int NF>
-__device__ __noinline__ int ctl_solve(LmController &c, const ExcSums *exc, double (*Lm)[8])
+__device__ __forceinline__ int ctl_solve(LmController &c, const ExcSums *exc, double (*Lm)[8])
 {
     const int lane = threadIdx.x & 31;
     int nx = 0;
@@ -755,6 +755,96 @@ __device__ __noinline__ int ctl_solve(LmController &c, const ExcSums *exc, doubl
         nx = ok ? (int)LM_RUN_B : (int)c.invalid_step();
     }
     return __shfl_sync(0xffffffffu, nx, 0);
+}
+
+// Next phase parameters from the controller state (one thread).
+template <int NF>
+__device__ __forceinline__ void publish_phase(const LmController &c, PhaseParams &P, SweepU &U, int nx, bool which_changed)
+{
+    if (which_changed) P.which_x ^= 1;                           // the candidate became x
+    Motion mo = P.base, ca = P.base;
+    if (NF >= 6) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            mo.v[j] = c.f[j]; mo.w[j] = c.f[3 + j];
+            ca.v[j] = c.f[j] + c.delta_f[j]; ca.w[j] = c.f[3 + j] + c.delta_f[3 + j];
+        }
+    }
+    if (NF == 7) { mo.k = c.f[6]; ca.k = c.f[6] + c.delta_f[6]; }
+    if (nx == (int)LM_DONE && c.termination == RSDSFM_FAILURE) mo = P.base;   // Ceres restores the start values
+    P.mot = mo; P.cand = ca;
+#pragma unroll
+    for (int j = 0; j < kMaxNF; ++j) P.delta_f[j] = c.delta_f[j];
+    P.radius = c.radius;
+    P.ee_fast_min = c.ee_fast_min;
+    P.first = 0;
+    P.next = nx;
+    sweep_uniforms<NF>(&P, &U);
+}
+
+// The whole controller step of a phase, run by ONE warp as one contiguous, mostly straight-line piece of
+// code (it executes once per phase with a cold instruction cache -- the sweep evicts it -- so taken branches
+// and calls, not arithmetic, are what it costs): judge the candidate (LmController::on_candidate), take
+// over the evaluation sums, the Ceres bookkeeping of the new point, the damped Cholesky solve, and the next
+// phase's parameters.  fin: the combined row.  Returns (and leaves in s_flag[6]) 1 when the current point
+// has listed (clamped) pixels: their sums need the whole CTA, and the caller finishes the step.
+template <int NF>
+__device__ __noinline__ int controller_warp(LmController &c, PhaseParams &P, SweepU &U, const double *fin, int *s_flag,
+                                            const unsigned int *s_ne, int slot_cur, int slot_spec, bool run_init,
+                                            unsigned int exc_cap, double (*Lm)[8])
+{
+    using T = TAcc<NF>;
+    using RW = Row<NF>;
+    constexpr int NS = T::NS;
+    const int lane = threadIdx.x & 31;
+    const unsigned int flags = (unsigned int)dbits(fin[RW::oFLAGS]);
+    int nx = (int)LM_RUN_A;
+    if (!run_init) {
+        if (lane == 0) {
+            CandSums cs;
+            cs.mcc = fin[2] + fin[NS + 2]; cs.step_sq = fin[3] + fin[NS + 3]; cs.cand_cost = 0.5 * (fin[0] + fin[NS]);
+            cs.bad_step = (flags & 4u) ? 1.0 : 0.0; cs.bad_cand = (flags & 1u) ? 1.0 : 0.0;
+            nx = (int)c.on_candidate(cs);
+        }
+        nx = __shfl_sync(0xffffffffu, nx, 0);
+    }
+    const bool accepted = (nx == (int)LM_RUN_A);
+    const int cur = run_init ? slot_cur : (accepted ? slot_spec : slot_cur);
+    unsigned int ne = s_ne[cur];
+    if (ne > exc_cap) ne = exc_cap;
+    const int need_cta = (NF > 0 && ne > 0u) ? 1 : 0;
+    if (lane == 0) { s_flag[1] = nx; s_flag[3] = accepted ? 1 : 0; s_flag[4] = cur; s_flag[2] = (int)ne; s_flag[6] = need_cta; }
+    if (need_cta) return 1;
+    if (accepted) {
+        // the evaluation sums of this pass describe the (new) current point: EvalSums in place
+        if (lane < kTri) {
+            c.ev.G1[lane] = (lane < T::TRI) ? fin[T::oK + (lane < T::TRI ? lane : 0)] : 0.0;
+            c.ev.G2[lane] = (lane < T::TRI) ? fin[NS + T::oK + (lane < T::TRI ? lane : 0)] : 0.0;
+        }
+        if (lane < kMaxNF) {
+            c.ev.h1[lane] = (lane < NF) ? fin[T::oH + (lane < NF ? lane : 0)] : 0.0;
+            c.ev.h2[lane] = (lane < NF) ? fin[NS + T::oH + (lane < NF ? lane : 0)] : 0.0;
+        }
+        if (lane == 31) {
+            c.ev.cost = 0.5 * (fin[0] + fin[NS]); c.ev.sumsq_d = fin[1] + fin[NS + 1];
+            c.ev.gmax_e = fin[RW::oGMAX];
+            c.ev.bad = (flags & 2u) ? 1.0 : 0.0; c.ev.ee_max = fin[RW::oEEMAX];
+        }
+        __syncwarp();
+        nx = ctl_on_eval<NF>(c);
+    }
+    while (nx == (int)LM_SOLVE) nx = ctl_solve<NF>(c, nullptr, Lm);
+    __syncwarp();
+    if (lane == 0) publish_phase<NF>(c, P, U, nx, !run_init && accepted);
+    return 0;
+}
+
+// out-of-line copies for the (rare) CTA-wide path with listed pixels
+template <int NF> __device__ __noinline__ int ctl_on_eval_cold(LmController &c) { return ctl_on_eval<NF>(c); }
+template <int NF> __device__ __noinline__ int ctl_solve_cold(LmController &c, const ExcSums *exc, double (*Lm)[8]) { return ctl_solve<NF>(c, exc, Lm); }
+template <int NF> __device__ __noinline__ void publish_phase_cold(const LmController &c, PhaseParams &P, SweepU &U, int nx, bool which_changed)
+{
+    publish_phase<NF>(c, P, U, nx, which_changed);
 }
 
 constexpr unsigned long long kWatchdogNs = 4000000000ull;   // 4 s: a stuck grid barrier aborts the solve
@@ -935,24 +1025,23 @@ __device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P,
             hps = __shfl_xor_sync(0xffffffffu, ss, 1);
         }
         if (__any_sync(0xffffffffu, slow)) {
-            // rare: some block of this warp needs the exact treatment (it added nothing above, its vectors are zero)
-            PixOut<NF> X;
-#pragma unroll
-            for (int j = 0; j < NFa; ++j) { X.kv[j] = 0.0; X.sv[j] = 0.0; }
-            X.ks = 0.0; X.ss = 0.0;
+            // rare: some block of this warp needs the exact treatment (it added nothing above, its vectors are zero):
+            // its lane replaces the held vectors and the partners exchange again
             if (slow) {
                 const Loaded Lc = L;
+                PixOut<NF> X;
                 pixel_exact<NF, INIT>(&Lc, idx, &P, dcand, n_exc, &A_.sh->exc_overflow, elist_p, A_.exc_cap, &X);
                 acc[0] += X.rr; acc[1] += X.dd2;
                 if (!INIT) { acc[2] += X.mcc; acc[3] += X.stp; }
                 S.gmax = umax64(S.gmax, X.gb); S.eemax = umax64(S.eemax, X.eb); S.flags |= X.flags;
+#pragma unroll
+                for (int j = 0; j < NFa; ++j) { hk[j] = X.kv[j]; sv[j] = X.sv[j]; }
+                hks = X.ks; ss = X.ss;
             }
             if (NF > 0) {
-                double pv[NFa];
 #pragma unroll
-                for (int j = 0; j < NF; ++j) pv[j] = __shfl_xor_sync(0xffffffffu, X.sv[j], 1);
-                const double ps = __shfl_xor_sync(0xffffffffu, X.ss, 1);
-                rank1_update<NF>(X.kv, pv, X.ks, ps, acc);
+                for (int j = 0; j < NF; ++j) hp[j] = __shfl_xor_sync(0xffffffffu, sv[j], 1);
+                hps = __shfl_xor_sync(0xffffffffu, ss, 1);
             }
         }
         // ---- this warp is done with the stage: release it (one arrival per warp)
@@ -1173,24 +1262,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
         }
         const unsigned long long t_fin = t_begin ? globaltimer() : 0ull;
         const unsigned int fin_flags = (unsigned int)dbits(fin[RW::oFLAGS]);
-        // ---- FUSED: judge the candidate first
-        if (tid == 0) {
-            int accepted = run_init ? 1 : 0;
-            LmNext nx = LM_RUN_A;
-            if (!run_init) {
-                CandSums c;
-                c.mcc = fin[2] + fin[NS + 2]; c.step_sq = fin[3] + fin[NS + 3]; c.cand_cost = 0.5 * (fin[0] + fin[NS]);
-                c.bad_step = (fin_flags & 4u) ? 1.0 : 0.0; c.bad_cand = (fin_flags & 1u) ? 1.0 : 0.0;
-                nx = s_ctl.on_candidate(c);
-                accepted = (nx == LM_RUN_A) ? 1 : 0;
-            }
-            s_flag[1] = (int)nx;
-            s_flag[3] = accepted;
-            const int cur = run_init ? slot_cur : (accepted ? slot_spec : slot_cur);
-            s_flag[4] = cur;
-            const unsigned int ne = s_ne[cur];
-            s_flag[2] = (int)(ne < exc_cap ? ne : exc_cap);
-        }
+        // ---- the controller step: one warp, one contiguous piece of code (controller_warp)
+        if (warp == 0)
+            controller_warp<NF>(s_ctl, P, U, fin, s_flag, s_ne, slot_cur, slot_spec, run_init, exc_cap, s_L);
         __syncthreads();
         const bool accepted = s_flag[3] != 0;
         if (!run_init) {
@@ -1200,88 +1274,63 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
             slot_spec = slot_zero;
             slot_zero = dead;
         }
-        if (accepted) {
-            // the evaluation sums of this pass describe the (new) current point: EvalSums in place
-            if (tid < kTri) {
-                s_ctl.ev.G1[tid] = (tid < T::TRI) ? fin[T::oK + (tid < T::TRI ? tid : 0)] : 0.0;
-                s_ctl.ev.G2[tid] = (tid < T::TRI) ? fin[NS + T::oK + (tid < T::TRI ? tid : 0)] : 0.0;
-            } else if (tid >= 32 && tid < 32 + kMaxNF) {
-                const int j = tid - 32;
-                s_ctl.ev.h1[j] = (j < NF) ? fin[T::oH + (j < NF ? j : 0)] : 0.0;
-                s_ctl.ev.h2[j] = (j < NF) ? fin[NS + T::oH + (j < NF ? j : 0)] : 0.0;
-            } else if (tid == 64) {
-                s_ctl.ev.cost = 0.5 * (fin[0] + fin[NS]); s_ctl.ev.sumsq_d = fin[1] + fin[NS + 1];
-                s_ctl.ev.gmax_e = fin[RW::oGMAX];
-                s_ctl.ev.bad = (fin_flags & 2u) ? 1.0 : 0.0; s_ctl.ev.ee_max = fin[RW::oEEMAX];
+        bool drained = false;
+        if constexpr (NF > 0) if (s_flag[6]) {
+            // ---- listed pixels (rare): the whole CTA finishes the step.  Their sort keys live in the pixel ring,
+            // so the prefetched tiles are given up first.
+            if (accepted) {
+                if (tid < kTri) {
+                    s_ctl.ev.G1[tid] = (tid < T::TRI) ? fin[T::oK + (tid < T::TRI ? tid : 0)] : 0.0;
+                    s_ctl.ev.G2[tid] = (tid < T::TRI) ? fin[NS + T::oK + (tid < T::TRI ? tid : 0)] : 0.0;
+                } else if (tid >= 32 && tid < 32 + kMaxNF) {
+                    const int j = tid - 32;
+                    s_ctl.ev.h1[j] = (j < NF) ? fin[T::oH + (j < NF ? j : 0)] : 0.0;
+                    s_ctl.ev.h2[j] = (j < NF) ? fin[NS + T::oH + (j < NF ? j : 0)] : 0.0;
+                } else if (tid == 64) {
+                    s_ctl.ev.cost = 0.5 * (fin[0] + fin[NS]); s_ctl.ev.sumsq_d = fin[1] + fin[NS + 1];
+                    s_ctl.ev.gmax_e = fin[RW::oGMAX];
+                    s_ctl.ev.bad = (fin_flags & 2u) ? 1.0 : 0.0; s_ctl.ev.ee_max = fin[RW::oEEMAX];
+                }
             }
             __syncthreads();
-        }
-        // listed pixels (rare): their sort keys live in the pixel ring, so the prefetched tiles are given up first
-        bool xsorted = false;
-        unsigned long long *xkeys = reinterpret_cast<unsigned long long *>(smem_raw);
-        bool drained = false;
-        if constexpr (NF > 0) if (s_flag[2] > 0) {
+            unsigned long long *xkeys = reinterpret_cast<unsigned long long *>(smem_raw);
             drain_prefetch(full, empty, &cons, &consumed, pre, true);
             drained = true;
             __syncthreads();
-            xsorted = sort_exceptions(exc + (size_t)s_flag[4] * exc_cap, s_flag[2], xkeys, 16384);
-        }
-        if (accepted) {
-            if constexpr (NF > 0) if (s_flag[2] > 0) {
+            const bool xsorted = sort_exceptions(exc + (size_t)s_flag[4] * exc_cap, s_flag[2], xkeys, 16384);
+            if (accepted) {
                 exc_sums<NF>(0, exc + (size_t)s_flag[4] * exc_cap, s_flag[2], xkeys, xsorted, 0.0, 0.0, 0.0, part, fin);
                 if (tid < T::TRI) s_ctl.ev.G1[tid] += fin[tid];
                 if (tid < NF) s_ctl.ev.h1[tid] += fin[kTri + tid];
                 __syncthreads();
+                if (warp == 0) {
+                    const int nx = ctl_on_eval_cold<NF>(s_ctl);
+                    if (lane == 0) s_flag[1] = nx;
+                }
+                __syncthreads();
             }
-            if (warp == 0) {
-                const int nx = ctl_on_eval<NF>(s_ctl);
-                if (lane == 0) s_flag[1] = nx;
-            }
-            __syncthreads();
-        }
-        // ---- (re)solve at the current radius; the clamped-pixel correction is summed by the whole CTA
-        while (s_flag[1] == (int)LM_SOLVE) {
-            const int ne = s_flag[2];
-            if constexpr (NF > 0) if (ne > 0) {
-                exc_sums<NF>(1, exc + (size_t)s_flag[4] * exc_cap, ne, xkeys, xsorted, s_ctl.radius, s_ctl.opt.min_lm_diagonal,
+            // (re)solve at the current radius; the clamped-pixel correction is summed by the whole CTA
+            while (s_flag[1] == (int)LM_SOLVE) {
+                exc_sums<NF>(1, exc + (size_t)s_flag[4] * exc_cap, s_flag[2], xkeys, xsorted, s_ctl.radius, s_ctl.opt.min_lm_diagonal,
                              s_ctl.opt.max_lm_diagonal, part, fin);
                 if (tid < kTri) s_exc.S[tid] = fin[tid];
                 if (tid < kMaxNF) s_exc.rhs[tid] = fin[kTri + tid];
                 __syncthreads();
+                if (warp == 0) {
+                    const int nx = ctl_solve_cold<NF>(s_ctl, &s_exc, s_L);
+                    if (lane == 0) s_flag[1] = nx;
+                }
+                __syncthreads();
             }
-            if (warp == 0) {
-                const int nx = ctl_solve<NF>(s_ctl, (NF > 0 && ne > 0) ? &s_exc : nullptr, s_L);
-                if (lane == 0) s_flag[1] = nx;
-            }
+            if (tid == 0) publish_phase_cold<NF>(s_ctl, P, U, s_flag[1], !run_init && accepted);
             __syncthreads();
         }
-        // ---- next phase parameters (every CTA writes its own copy)
-        const bool which_changed = !run_init && accepted;
-        if (tid == 0) {
-            const LmNext nx = (LmNext)s_flag[1];                     // LM_RUN_B (another fused pass) or LM_DONE
-            if (which_changed) P.which_x ^= 1;                       // the candidate became x
-            Motion mo = P.base, ca = P.base;
-            if (NF >= 6) for (int j = 0; j < 3; ++j) {
-                mo.v[j] = s_ctl.f[j]; mo.w[j] = s_ctl.f[3 + j];
-                ca.v[j] = s_ctl.f[j] + s_ctl.delta_f[j]; ca.w[j] = s_ctl.f[3 + j] + s_ctl.delta_f[3 + j];
-            }
-            if (NF == 7) { mo.k = s_ctl.f[6]; ca.k = s_ctl.f[6] + s_ctl.delta_f[6]; }
-            if (nx == LM_DONE && s_ctl.termination == RSDSFM_FAILURE) mo = P.base;   // Ceres restores the start values
-            P.mot = mo; P.cand = ca;
-            for (int j = 0; j < kMaxNF; ++j) P.delta_f[j] = s_ctl.delta_f[j];
-            P.radius = s_ctl.radius;
-            P.ee_fast_min = s_ctl.ee_fast_min;
-            P.first = 0;
-            P.next = (int)nx;
-            sweep_uniforms<NF>(&P, &U);
-            if (t_begin) {
-                const unsigned long long t_end = globaltimer();
-                atomicAdd(&sh->t_phase[run_init ? 10 : 11], t_end - t_fin);
-                atomicAdd(&sh->t_phase[run_init ? 6 : 9], t_end - t_ctl);
-                atomicAdd(&sh->t_phase[run_init ? 0 : 2], t_end - t_begin); atomicAdd(&sh->t_phase[run_init ? 1 : 3], 1ull);
-            }
+        if (t_begin) {
+            const unsigned long long t_end = globaltimer();
+            atomicAdd(&sh->t_phase[run_init ? 10 : 11], t_end - t_fin);
+            atomicAdd(&sh->t_phase[run_init ? 6 : 9], t_end - t_ctl);
+            atomicAdd(&sh->t_phase[run_init ? 0 : 2], t_end - t_begin); atomicAdd(&sh->t_phase[run_init ? 1 : 3], 1ull);
         }
-        __syncthreads();
         gen++;
         // ---- the depth prefetch assumed "accepted" (or INIT): anything else reloads the first tiles
         const bool spec_ok = run_init || accepted;
