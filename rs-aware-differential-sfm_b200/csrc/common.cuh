@@ -15,7 +15,10 @@
 namespace rsdsfm {
 
 constexpr int kNumSMsB200 = 148;
-constexpr int kThreads = 256;          // threads per CTA for the per-pixel map-reduce kernels
+#ifndef RS_THREADS
+#define RS_THREADS 256
+#endif
+constexpr int kThreads = RS_THREADS;   // threads per CTA for the per-pixel map-reduce kernels (RS_THREADS: experiments only)
 constexpr int kWarps = kThreads / 32;
 
 // A grow-only device buffer owned by the context.

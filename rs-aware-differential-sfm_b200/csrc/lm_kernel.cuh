@@ -18,8 +18,7 @@
 //    shared-memory loads and the rank-1 updates: padded blocks are all-zero records that contribute
 //    nothing by construction, range tests are integer compares on the bit patterns, and everything
 //    rare (LM diagonal clamped at the focus of expansion, non-finite values) is decided by ONE warp
-//    vote at the end of the step, which sends the warp through an out-of-line exact path.  ptxas can
-//    then interleave the latency-bound residual/Jacobian chain with the 70 independent Schur FMAs.
+//    vote per step, which sends the warp through an out-of-line exact path.
 //  * TMA RING.  256-block tiles (12 KB + 2 KB bulk copies, cp.async.bulk + mbarrier complete_tx), 14
 //    stages per SM, full/empty mbarriers; consumers release a stage with one arrival per warp, and the
 //    warps take turns at refilling released stages (see sweep()).
@@ -178,7 +177,7 @@ struct Stage {
     double2 xy[kTile], uu[kTile], aa[kTile];
     double d[kTile];
 };
-static_assert(sizeof(Stage) == 14336 && kTile == kThreads, "stage layout: one residual block per thread and tile");
+static_assert(sizeof(Stage) == 56 * kTile && kTile == kThreads, "stage layout: one residual block per thread and tile");
 
 struct Loaded {
     double2 p, u, a;
@@ -376,8 +375,7 @@ __device__ __noinline__ void pixel_exact(const Loaded *Lp, int index, const Phas
 
 // ------------------------------------------------------------------------------------------
 // The straight-line body.  Uniform quantities of a phase: built once per phase by one thread in shared
-// memory; the sweep keeps the most used ones in registers and re-reads the others every step (broadcast
-// loads), which is what leaves room for the software-pipelined rank-1 updates.
+// memory; every thread copies them into registers before its sweep.
 // ------------------------------------------------------------------------------------------
 struct __align__(16) SweepU {
     double v0, v1, v2, w0, w1, w2, k, c2;          // current point x (FUSED) / evaluation point (INIT)
@@ -417,40 +415,40 @@ __device__ __forceinline__ void sweep_uniforms(const PhaseParams *Pp, SweepU *Up
     *Up = U;
 }
 
-struct SweepR {                                      // the part of SweepU a thread keeps in registers
-    double v0, v1, v2, w0, w1, w2, k, c2, kc, c2c;
-};
-
 __device__ __forceinline__ double mask_double(double v, bool keep)
 {   // v or +0.0, as integer logic: never becomes a branch around the (expensive) producer of v
     return __longlong_as_double(__double_as_longlong(v) & (keep ? -1ll : 0ll));
 }
 
-// One residual block, no branches.  The scalar terms are added to acc / S and the block's two projected
-// Jacobian vectors are returned -- unless the block needs the exact path (a real block whose e^Te left the
-// fast range at x or at the evaluation point): then nothing is added, the vectors are zero and `true` is returned.
+// One residual block, no branches.  Measured on B200: the sweep is bound by instruction issue / operand
+// delivery (about 1.9 cycles per warp instruction of ANY kind with two warps per sub-partition), not by
+// latency, so the body is written for the fewest instructions: no per-pixel finiteness flags (a non-finite
+// residual, Jacobian or depth step makes sum r^2, sum d^2 or sum |step|^2 non-finite -- all terms are
+// squares -- and the controller tests those), one mask per reciprocal, shared products for the two
+// projected Jacobian vectors.  The scalar terms are added to acc / S and the block's two projected
+// vectors are returned -- unless the block needs the exact path (a real block whose e^Te left the fast
+// range at x or at the evaluation point): then nothing is added, the vectors are zero and `true` is returned.
 template <int NF, bool INIT>
-__device__ __forceinline__ bool pixel_fast(const Loaded &L, bool inb, int index, const SweepR &R, const SweepU &U, bool e_role,
+__device__ __forceinline__ bool pixel_fast(const Loaded &L, bool inb, int index, const SweepU &U, bool e_role,
                                            double *__restrict__ d_cand, double (&acc)[TAcc<NF>::NS], SweepScalars &S,
                                            double (&kv)[NF > 0 ? NF : 1], double (&sv)[NF > 0 ? NF : 1], double &ks, double &ss)
 {
     const double x = L.p.x, y = L.p.y, d = L.d;
     const double xy = x * y, xx1 = fma(x, x, 1.0), yy1 = fma(y, y, 1.0);
-    double a0 = fma(-x, R.v2, R.v0), a1 = fma(-y, R.v2, R.v1);
-    double b0 = fma(-xy, R.w0, fma(xx1, R.w1, -(y * R.w2)));
-    double b1 = fma(-yy1, R.w0, fma(xy, R.w1, x * R.w2));
+    double a0 = fma(-x, U.v2, U.v0), a1 = fma(-y, U.v2, U.v1);
+    double b0 = fma(-xy, U.w0, fma(xx1, U.w1, -(y * U.w2)));
+    double b1 = fma(-yy1, U.w0, fma(xy, U.w1, x * U.w2));
     double dc = d, mcc = 0.0, stp = 0.0;
-    bool fast_x = true;
-    unsigned flags = 0u;
+    bool fast = true;
     if (!INIT) {
         // ---- candidate step at x: delta_d = -q e^T (r + F delta_f)
-        const double ak = fma(R.k, L.a.y, L.a.x), beta = R.c2 * ak;
+        const double ak = fma(U.k, L.a.y, L.a.x), beta = U.c2 * ak;
         const double p0 = fma(d, a0, b0), p1 = fma(d, a1, b1);
         const double r0 = fma(-beta, p0, L.u.x), r1 = fma(-beta, p1, L.u.y);
         const double e0 = -(beta * a0), e1 = -(beta * a1);
         const double ee = fma(e0, e0, e1 * e1);
-        fast_x = bits_in_range(ee, U.lo_x, U.hi_x);
-        const double q = mask_double(fast_rcp(ee) * U.rfac, fast_x);
+        fast = bits_in_range(ee, U.lo_x, U.hi_x);
+        const double q = mask_double(fast_rcp(ee) * U.rfac, fast);
         double m0 = 0.0, m1 = 0.0;
         if (NF >= 6) {
             // F delta_f = -beta (d A dv + B dw) - dbeta p dk; the increments of A v and B w are reused for the candidate
@@ -473,43 +471,41 @@ __device__ __forceinline__ bool pixel_fast(const Loaded &L, bool inb, int index,
         if (inb) d_cand[index] = dc;
         mcc = fma(j0, fma(0.5, j0, r0), j1 * fma(0.5, j1, r1));
         stp = dd * dd;
-        if (not_finite(delta_e)) flags = 4u;
     }
     // ---- evaluation at the candidate (INIT: at the start point)
-    const double akc = fma(R.kc, L.a.y, L.a.x), bc = R.c2c * akc;
+    const double akc = fma(U.kc, L.a.y, L.a.x), bc = U.c2c * akc;
     const double p0 = fma(dc, a0, b0), p1 = fma(dc, a1, b1);
     const double r0 = fma(-bc, p0, L.u.x), r1 = fma(-bc, p1, L.u.y);
     const double e0 = -(bc * a0), e1 = -(bc * a1);
     const double ee = fma(e0, e0, e1 * e1);
-    const bool fast = fast_x && bits_in_range(ee, U.lo_c, U.hi_c);
+    fast = fast && bits_in_range(ee, U.lo_c, U.hi_c);
     const bool slow = inb && !fast;
-    if (not_finite(r0 + r1)) flags |= 3u;
-    if (not_finite(ee)) flags |= 2u;
-    // scalar terms: masked out for a block that takes the exact path (padded records contribute zeros anyway)
-    acc[0] += mask_double(fma(r0, r0, r1 * r1), !slow);
-    acc[1] += mask_double(dc * dc, !slow);
-    if (!INIT) { acc[2] += mask_double(mcc, !slow); acc[3] += mask_double(stp, !slow); }
-    S.gmax = umax64(S.gmax, slow ? 0ull : dbits(fabs(fma(e0, r0, e1 * r1))));     // |e^T r|
-    S.eemax = umax64(S.eemax, slow ? 0ull : dbits(ee));
-    S.flags |= slow ? 0u : flags;
+    // scalar terms (a padded record contributes zeros; a block on the exact path adds them there)
+    if (!slow) {
+        acc[0] = fma(r0, r0, fma(r1, r1, acc[0]));
+        acc[1] = fma(dc, dc, acc[1]);
+        if (!INIT) { acc[2] += mcc; acc[3] += stp; }
+        S.gmax = umax64(S.gmax, dbits(fma(e0, r0, e1 * r1)) & 0x7fffffffffffffffull);     // |e^T r|
+        S.eemax = umax64(S.eemax, dbits(ee));
+    }
     if (NF > 0) {
         const double mu = mask_double(fast_rsqrt(ee), fast);          // 1/|e|
         const double c = mu * e0, s = mu * e1;                        // unit depth-column direction
         const double mc = e_role ? c : -s, ms = e_role ? s : c;       // the direction this lane keeps: e or n = (-s, c)
         // F^T (mc, ms) and F^T (-ms, mc) share their products (F = -beta [d A | B | (dbeta/beta) p])
         const double P0 = bc * mc, P1 = bc * ms;
-        const double dP0 = dc * P0, dP1 = dc * P1;
+        const double nd = -dc;
         const double t1 = fma(x, P0, y * P1), t2 = fma(y, P0, -(x * P1));
-        kv[0] = -dP0;            sv[0] = dP1;
-        kv[1] = -dP1;            sv[1] = -dP0;
+        kv[0] = nd * P0;         sv[0] = dc * P1;
+        kv[1] = nd * P1;         sv[1] = kv[0];
         kv[2] = dc * t1;         sv[2] = dc * t2;
         kv[3] = fma(y, t1, P1);  sv[3] = fma(y, t2, P0);
-        kv[4] = -fma(x, t1, P0); sv[4] = fma(-x, t2, P1);
+        kv[4] = fma(-x, t1, -P0); sv[4] = fma(-x, t2, P1);
         kv[5] = t2;              sv[5] = -t1;
         if (NF == 7) {
-            const double dbc = fma(-akc, U.K4, R.c2c * L.a.y);        // dbeta/dk at the evaluation point
-            kv[6] = -(dbc * fma(p0, mc, p1 * ms));
-            sv[6] = -(dbc * fma(p1, mc, -(p0 * ms)));
+            const double ndbc = fma(akc, U.K4, -(U.c2c * L.a.y));     // -(dbeta/dk) at the evaluation point
+            kv[6] = ndbc * fma(p0, mc, p1 * ms);
+            sv[6] = ndbc * fma(p1, mc, -(p0 * ms));
         }
         ks = fma(mc, r0, ms * r1);
         ss = fma(mc, r1, -(ms * r0));
@@ -797,7 +793,19 @@ __device__ __noinline__ int controller_warp(LmController &c, PhaseParams &P, Swe
     using RW = Row<NF>;
     constexpr int NS = T::NS;
     const int lane = threadIdx.x & 31;
-    const unsigned int flags = (unsigned int)dbits(fin[RW::oFLAGS]);
+    // flags of the exact path, plus what the sums themselves say: the sweep keeps no per-pixel finiteness flags,
+    // a non-finite residual / depth step / Jacobian entry shows up as a non-finite sum (1: residual, 2: evaluation, 4: step)
+    unsigned int flags = 0u;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int j = lane + 32 * q;
+        if (j < 2 * NS && not_finite(fin[j < 2 * NS ? j : 0])) {
+            const int jj = j >= NS ? j - NS : j;
+            flags |= (jj == 0) ? 3u : (jj == 1) ? 6u : (jj == 2) ? 0u : (jj == 3) ? 4u : 2u;
+        }
+    }
+    flags = __reduce_or_sync(0xffffffffu, flags) | (unsigned int)dbits(fin[RW::oFLAGS]);
+    if (lane == 0) s_flag[7] = (int)flags;
     int nx = (int)LM_RUN_A;
     if (!run_init) {
         if (lane == 0) {
@@ -950,20 +958,20 @@ struct RingPos {
 
 // ------------------------------------------------------------------------------------------
 // One sweep over this CTA's tiles: one residual block per thread and step.
-//  * Software-pipelined: the 70 rank-1 FMAs of the PREVIOUS step's block (vectors held in registers,
-//    independent of everything else) are issued together with the latency-bound residual / Jacobian
-//    chain of this step's block.
 //  * Ring refill by rotation: at step k the leader of warp k % 8 refills the stage that held tile
 //    k - kRefillLag (waiting, if it must, until every warp has released it) with tile k - kRefillLag + kStages.
 //    Every tile is queued by a warp that is known in advance: no producer state, and the cost of queueing
 //    (two bulk copies per tile) is spread over all warps instead of making warp 0 the straggler.
 //  * The full barrier of the NEXT tile is tested at the top of a step; the blocking wait is only entered
 //    when that early test failed.
+//  (Variants that were measured and dropped: rank-1 updates software-pipelined one step behind the chain,
+//   with and without artificial dependences that spread them over the chain's latencies -- both slower than
+//   this plain order, the sweep is issue-bound; two residual blocks per step; a producer warp.)
 // ------------------------------------------------------------------------------------------
 constexpr int kRefillLag = 5;
 
 template <int NF, bool INIT>
-__device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P, const SweepU &U, Stage *stages, uint64_t *full,
+__device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P, const SweepU &Us, Stage *stages, uint64_t *full,
                                       uint64_t *empty, int n_my, RingPos &cons, unsigned int &consumed, const double *dx,
                                       double *dcand, int elist, double (&acc)[TAcc<NF>::NS], SweepScalars &S)
 {
@@ -975,14 +983,8 @@ __device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P,
     unsigned int *n_exc = &A_.sh->n_exc[elist];
     ExcEntry *elist_p = A_.exc + (size_t)elist * A_.exc_cap;
 
-    SweepR R;
-    R.v0 = U.v0; R.v1 = U.v1; R.v2 = U.v2; R.w0 = U.w0; R.w1 = U.w1; R.w2 = U.w2; R.k = U.k; R.c2 = U.c2; R.kc = U.kc; R.c2c = U.c2c;
+    const SweepU U = Us;                   // registers
     RingPos rc = cons;                     // consumer position (registers)
-    RingPos rd = cons;                     // position of the tile kRefillLag steps back
-
-    double hk[NFa], hp[NFa], hks = 0.0, hps = 0.0;     // held: vectors of the previous step's block
-#pragma unroll
-    for (int j = 0; j < NFa; ++j) { hk[j] = 0.0; hp[j] = 0.0; }
 #ifdef LM_DBG_WAITCLK
     long long dbg_wait = 0; const long long dbg_t0 = clock64();
 #endif
@@ -994,7 +996,11 @@ __device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P,
 #ifdef LM_DBG_WAITCLK
         const long long w0_ = clock64();
 #endif
+#ifdef LM_DBG_NOLOAD
+        if (consumed + (unsigned)k < (unsigned)kStages) mbar_wait(&full[rc.s], rc.par);
+#else
         if (!ready) mbar_wait(&full[rc.s], rc.par);
+#endif
 #ifdef LM_DBG_WAITCLK
         dbg_wait += clock64() - w0_;
 #endif
@@ -1004,29 +1010,26 @@ __device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P,
             L.p = st.xy[tid]; L.u = st.uu[tid]; L.a = st.aa[tid]; L.d = st.d[tid];
         }
         const int s_now = rc.s;
+        const unsigned par_now = rc.par;
         rc.advance();
+#ifndef LM_DBG_NOLOAD
         ready = mbar_test(&full[rc.s], rc.par);        // next tile: result needed only at the top of the next step
-        // ---- rank-1 updates of the previous block + this block's chain: one straight-line stretch
+#endif
+        // ---- the residual block: straight-line
+        double kv[NFa], sv[NFa], pv[NFa], ks, ss, ps = 0.0;
 #ifdef LM_DBG_NOCOMPUTE
         acc[0] += L.p.x + L.p.y + L.u.x + L.u.y + L.a.x + L.a.y + L.d;
         if (!INIT && inb) dcand[idx] = L.d;
-        double sv[NFa], ss = 0.0;
+        ks = 0.0; ss = 0.0;
 #pragma unroll
-        for (int j = 0; j < NFa; ++j) sv[j] = 0.0;
+        for (int j = 0; j < NFa; ++j) { kv[j] = 0.0; sv[j] = 0.0; }
         const bool slow = false;
 #else
-        if (NF > 0) rank1_update<NF>(hk, hp, hks, hps, acc);
-        double sv[NFa], ss;
-        const bool slow = pixel_fast<NF, INIT>(L, inb, idx, R, U, e_role, dcand, acc, S, hk, sv, hks, ss);
+        const bool slow = pixel_fast<NF, INIT>(L, inb, idx, U, e_role, dcand, acc, S, kv, sv, ks, ss);
 #endif
-        if (NF > 0) {
-#pragma unroll
-            for (int j = 0; j < NF; ++j) hp[j] = __shfl_xor_sync(0xffffffffu, sv[j], 1);
-            hps = __shfl_xor_sync(0xffffffffu, ss, 1);
-        }
         if (__any_sync(0xffffffffu, slow)) {
             // rare: some block of this warp needs the exact treatment (it added nothing above, its vectors are zero):
-            // its lane replaces the held vectors and the partners exchange again
+            // its lane replaces them before the partners exchange
             if (slow) {
                 const Loaded Lc = L;
                 PixOut<NF> X;
@@ -1035,29 +1038,37 @@ __device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P,
                 if (!INIT) { acc[2] += X.mcc; acc[3] += X.stp; }
                 S.gmax = umax64(S.gmax, X.gb); S.eemax = umax64(S.eemax, X.eb); S.flags |= X.flags;
 #pragma unroll
-                for (int j = 0; j < NFa; ++j) { hk[j] = X.kv[j]; sv[j] = X.sv[j]; }
-                hks = X.ks; ss = X.ss;
-            }
-            if (NF > 0) {
-#pragma unroll
-                for (int j = 0; j < NF; ++j) hp[j] = __shfl_xor_sync(0xffffffffu, sv[j], 1);
-                hps = __shfl_xor_sync(0xffffffffu, ss, 1);
+                for (int j = 0; j < NFa; ++j) { kv[j] = X.kv[j]; sv[j] = X.sv[j]; }
+                ks = X.ks; ss = X.ss;
             }
         }
-        // ---- this warp is done with the stage: release it (one arrival per warp)
-        __syncwarp();
+        if (NF > 0) {
+#pragma unroll
+            for (int j = 0; j < NF; ++j) pv[j] = __shfl_xor_sync(0xffffffffu, sv[j], 1);
+            ps = __shfl_xor_sync(0xffffffffu, ss, 1);
+            rank1_update<NF>(kv, pv, ks, ps, acc);
+        }
+        // ---- this warp is done with the stage: release it (one arrival per warp; the warp is converged here and
+        // every lane's loads of the tile have long been consumed)
+#ifndef LM_DBG_NOLOAD
         if (lane == 0) mbar_arrive(&empty[s_now]);
-        // ---- refill duty of this step
-        if (k >= kRefillLag) {
-            const int j = k - kRefillLag;              // tile (of this sweep) whose stage is refilled, with tile j + kStages
-            if ((k & (kWarps - 1)) == warp && lane == 0 && j + kStages < n_my) {
-                mbar_wait(&empty[rd.s], rd.par);       // every warp has released tile j
-                issue_tile(D, dx, (int)blockIdx.x + (j + kStages) * G, &stages[rd.s], &full[rd.s]);
+#endif
+        // ---- refill duty of this step (warp-uniform test): the stage that held tile k - kRefillLag gets tile k - kRefillLag + kStages
+        const int kd = k - kRefillLag;
+#ifdef LM_DBG_NOLOAD
+        if (false) {
+#else
+        if (((k & (kWarps - 1)) == warp) & (kd >= 0) & (kd + kStages < n_my)) {
+#endif
+            if (lane == 0) {
+                int sd = s_now - kRefillLag;                       // ring position of tile kd, from this step's
+                unsigned pd = par_now;
+                if (sd < 0) { sd += kStages; pd ^= 1u; }
+                mbar_wait(&empty[sd], pd);                         // every warp has released tile kd
+                issue_tile(D, dx, (int)blockIdx.x + (kd + kStages) * G, &stages[sd], &full[sd]);
             }
-            rd.advance();
         }
     }
-    if (NF > 0) rank1_update<NF>(hk, hp, hks, hps, acc);
 #ifdef LM_DBG_WAITCLK
     if (!INIT && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77) && consumed > 20u * (unsigned)n_my && consumed < 21u * (unsigned)n_my + 20u)
         printf("cta %d warp %d: sweep %lld cycles, waiting for tiles %lld cycles, %d steps\n", (int)blockIdx.x, tid >> 5, clock64() - dbg_t0, dbg_wait, n_my);
@@ -1072,6 +1083,9 @@ __device__ __noinline__ void queue_phase_head(const RefineData D, const double *
                                               RingPos at, unsigned int first_use, int pre)
 {
     const int G = gridDim.x;
+#ifdef LM_DBG_NOLOAD
+    if (first_use != 0u) return;
+#endif
     fence_proxy_async();          // the ring may have served as scratch (sort keys) since its last tile
     for (int i = 0; i < pre; ++i) {
         if (first_use + (unsigned)i >= (unsigned)kStages) mbar_wait(&empty[at.s], at.par ^ 1u);   // the stage's previous use was released
@@ -1085,6 +1099,9 @@ __device__ __noinline__ void queue_phase_head(const RefineData D, const double *
 __device__ __noinline__ void drain_prefetch(uint64_t *full, uint64_t *empty, RingPos *cons, unsigned int *consumed, int pre, bool release)
 {
     const int lane = threadIdx.x & 31;
+#ifdef LM_DBG_NOLOAD
+    return;
+#endif
     for (int u = 0; u < pre; ++u) {
         mbar_wait(&full[cons->s], cons->par);
         if (release) {
@@ -1112,7 +1129,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
     __shared__ double part[kWarps][kRowLd];
     __shared__ ExcSums s_exc;
     __shared__ double s_L[7][8];
-    __shared__ int s_flag[8];     // [1] next, [2] n_exc of the current list, [3] accepted, [4] current slot, [5] error
+    __shared__ int s_flag[8];     // [1] next, [2] n_exc of the current list, [3] accepted, [4] current slot, [5] error, [6] listed pixels: CTA-wide path, [7] flags
     __shared__ unsigned int s_ne[kExcSlots];
 
     const RefineData D = A_.D;
@@ -1261,7 +1278,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
             __syncthreads();
         }
         const unsigned long long t_fin = t_begin ? globaltimer() : 0ull;
-        const unsigned int fin_flags = (unsigned int)dbits(fin[RW::oFLAGS]);
         // ---- the controller step: one warp, one contiguous piece of code (controller_warp)
         if (warp == 0)
             controller_warp<NF>(s_ctl, P, U, fin, s_flag, s_ne, slot_cur, slot_spec, run_init, exc_cap, s_L);
@@ -1289,7 +1305,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
                 } else if (tid == 64) {
                     s_ctl.ev.cost = 0.5 * (fin[0] + fin[NS]); s_ctl.ev.sumsq_d = fin[1] + fin[NS + 1];
                     s_ctl.ev.gmax_e = fin[RW::oGMAX];
-                    s_ctl.ev.bad = (fin_flags & 2u) ? 1.0 : 0.0; s_ctl.ev.ee_max = fin[RW::oEEMAX];
+                    s_ctl.ev.bad = ((unsigned int)s_flag[7] & 2u) ? 1.0 : 0.0; s_ctl.ev.ee_max = fin[RW::oEEMAX];
                 }
             }
             __syncthreads();

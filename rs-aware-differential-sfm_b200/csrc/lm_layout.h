@@ -11,7 +11,10 @@
 
 namespace rsdsfm {
 
-constexpr int kTile = 256;                      // residual blocks per tile (one per thread of the solver CTA)
+#ifndef RS_THREADS
+#define RS_THREADS 256
+#endif
+constexpr int kTile = RS_THREADS;               // residual blocks per tile (one per thread of the solver CTA)
 
 #ifdef __CUDACC__
 __host__ __device__
