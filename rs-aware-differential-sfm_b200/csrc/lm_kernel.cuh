@@ -149,6 +149,49 @@ __device__ __forceinline__ void fence_proxy_async()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---- the same, on 32-bit shared-window addresses that the sweep computes once (a generic pointer to shared
+// memory makes the compiler rebuild the window base -- S2R SR_CgaCtaId, LEA, ... -- at every use)
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ bool mbar_test_s(uint32_t bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_s(uint32_t dst, const void *src, unsigned bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 // non-negative doubles order like their bit patterns; a NaN or a negative value fails both tests
 __device__ __forceinline__ bool bits_in_range(double v, unsigned long long lo, unsigned long long hi)
 {
@@ -438,7 +481,7 @@ __device__ __forceinline__ bool pixel_fast(const Loaded &L, bool inb, int index,
     double a0 = fma(-x, U.v2, U.v0), a1 = fma(-y, U.v2, U.v1);
     double b0 = fma(-xy, U.w0, fma(xx1, U.w1, -(y * U.w2)));
     double b1 = fma(-yy1, U.w0, fma(xy, U.w1, x * U.w2));
-    double dc = d, mcc = 0.0, stp = 0.0;
+    double dc = d, mj0 = 0.0, mt0 = 0.0, mj1 = 0.0, mt1 = 0.0, stp = 0.0;
     bool fast = true;
     if (!INIT) {
         // ---- candidate step at x: delta_d = -q e^T (r + F delta_f)
@@ -467,10 +510,9 @@ __device__ __forceinline__ bool pixel_fast(const Loaded &L, bool inb, int index,
         const double delta_e = -(q * fma(e0, r0 + m0, e1 * (r1 + m1)));
         const double j0 = fma(e0, delta_e, m0), j1 = fma(e1, delta_e, m1);                    // J delta
         dc = d + delta_e;
-        const double dd = d - dc;
         if (inb) d_cand[index] = dc;
-        mcc = fma(j0, fma(0.5, j0, r0), j1 * fma(0.5, j1, r1));
-        stp = dd * dd;
+        mj0 = j0; mt0 = fma(0.5, j0, r0); mj1 = j1; mt1 = fma(0.5, j1, r1);    // model cost term (J delta)^T (r + J delta / 2)
+        stp = delta_e;                                                       // |step|^2 term of this depth
     }
     // ---- evaluation at the candidate (INIT: at the start point)
     const double akc = fma(U.kc, L.a.y, L.a.x), bc = U.c2c * akc;
@@ -484,7 +526,7 @@ __device__ __forceinline__ bool pixel_fast(const Loaded &L, bool inb, int index,
     if (!slow) {
         acc[0] = fma(r0, r0, fma(r1, r1, acc[0]));
         acc[1] = fma(dc, dc, acc[1]);
-        if (!INIT) { acc[2] += mcc; acc[3] += stp; }
+        if (!INIT) { acc[2] = fma(mj0, mt0, fma(mj1, mt1, acc[2])); acc[3] = fma(stp, stp, acc[3]); }
         S.gmax = umax64(S.gmax, dbits(fma(e0, r0, e1 * r1)) & 0x7fffffffffffffffull);     // |e^T r|
         S.eemax = umax64(S.eemax, dbits(ee));
     }
@@ -971,8 +1013,7 @@ struct RingPos {
 constexpr int kRefillLag = 5;
 
 template <int NF, bool INIT>
-__device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P, const SweepU &Us, Stage *stages, uint64_t *full,
-                                      uint64_t *empty, int n_my, RingPos &cons, unsigned int &consumed, const double *dx,
+__device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P, const SweepU &Us, const uint32_t *A_s, int n_my, RingPos &cons, unsigned int &consumed, const double *dx,
                                       double *dcand, int elist, double (&acc)[TAcc<NF>::NS], SweepScalars &S)
 {
     constexpr int NFa = NF > 0 ? NF : 1;
@@ -985,6 +1026,10 @@ __device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P,
 
     const SweepU U = Us;                   // registers
     RingPos rc = cons;                     // consumer position (registers)
+    // shared-window addresses, computed once: ring, this thread's record inside a stage, the barriers
+    // (read back from shared memory: values the compiler can recompute from %cluster_ctarank it DOES recompute, every step)
+    const uint32_t ring_s = ((const volatile uint32_t *)A_s)[0], full_s = ((const volatile uint32_t *)A_s)[1], empty_s = ((const volatile uint32_t *)A_s)[2];
+    const uint32_t rec16 = (uint32_t)tid * 16u, rec8 = (uint32_t)(3 * kTile * 16) + (uint32_t)tid * 8u;
 #ifdef LM_DBG_WAITCLK
     long long dbg_wait = 0; const long long dbg_t0 = clock64();
 #endif
@@ -997,23 +1042,24 @@ __device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P,
         const long long w0_ = clock64();
 #endif
 #ifdef LM_DBG_NOLOAD
-        if (consumed + (unsigned)k < (unsigned)kStages) mbar_wait(&full[rc.s], rc.par);
+        if (consumed + (unsigned)k < (unsigned)kStages) mbar_wait_s(full_s + 8u * (uint32_t)rc.s, rc.par);
 #else
-        if (!ready) mbar_wait(&full[rc.s], rc.par);
+        if (!ready) mbar_wait_s(full_s + 8u * (uint32_t)rc.s, rc.par);
 #endif
 #ifdef LM_DBG_WAITCLK
         dbg_wait += clock64() - w0_;
 #endif
         Loaded L;
         {
-            const Stage &st = stages[rc.s];
-            L.p = st.xy[tid]; L.u = st.uu[tid]; L.a = st.aa[tid]; L.d = st.d[tid];
+            const uint32_t st = ring_s + (uint32_t)rc.s * (uint32_t)sizeof(Stage);
+            L.p = lds_f64x2(st + rec16); L.u = lds_f64x2(st + (uint32_t)(kTile * 16) + rec16);
+            L.a = lds_f64x2(st + (uint32_t)(2 * kTile * 16) + rec16); L.d = lds_f64(st + rec8);
         }
         const int s_now = rc.s;
         const unsigned par_now = rc.par;
         rc.advance();
 #ifndef LM_DBG_NOLOAD
-        ready = mbar_test(&full[rc.s], rc.par);        // next tile: result needed only at the top of the next step
+        ready = mbar_test_s(full_s + 8u * (uint32_t)rc.s, rc.par);        // next tile: result needed only at the top of the next step
 #endif
         // ---- the residual block: straight-line
         double kv[NFa], sv[NFa], pv[NFa], ks, ss, ps = 0.0;
@@ -1051,7 +1097,7 @@ __device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P,
         // ---- this warp is done with the stage: release it (one arrival per warp; the warp is converged here and
         // every lane's loads of the tile have long been consumed)
 #ifndef LM_DBG_NOLOAD
-        if (lane == 0) mbar_arrive(&empty[s_now]);
+        if (lane == 0) mbar_arrive_s(empty_s + 8u * (uint32_t)s_now);
 #endif
         // ---- refill duty of this step (warp-uniform test): the stage that held tile k - kRefillLag gets tile k - kRefillLag + kStages
         const int kd = k - kRefillLag;
@@ -1064,8 +1110,12 @@ __device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P,
                 int sd = s_now - kRefillLag;                       // ring position of tile kd, from this step's
                 unsigned pd = par_now;
                 if (sd < 0) { sd += kStages; pd ^= 1u; }
-                mbar_wait(&empty[sd], pd);                         // every warp has released tile kd
-                issue_tile(D, dx, (int)blockIdx.x + (kd + kStages) * G, &stages[sd], &full[sd]);
+                mbar_wait_s(empty_s + 8u * (uint32_t)sd, pd);     // every warp has released tile kd
+                const int tile = (int)blockIdx.x + (kd + kStages) * G;
+                const uint32_t st = ring_s + (uint32_t)sd * (uint32_t)sizeof(Stage), fb = full_s + 8u * (uint32_t)sd;
+                mbar_expect_tx_s(fb, (unsigned)sizeof(Stage));
+                bulk_g2s_s(st, D.blk + (size_t)tile * (3 * kTile), (unsigned)(3 * kTile * sizeof(double2)), fb);
+                bulk_g2s_s(st + (uint32_t)(3 * kTile * 16), dx + (size_t)tile * kTile, (unsigned)(kTile * sizeof(double)), fb);
             }
         }
     }
@@ -1131,6 +1181,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
     __shared__ double s_L[7][8];
     __shared__ int s_flag[8];     // [1] next, [2] n_exc of the current list, [3] accepted, [4] current slot, [5] error, [6] listed pixels: CTA-wide path, [7] flags
     __shared__ unsigned int s_ne[kExcSlots];
+    __shared__ uint32_t s_addr[4];  // shared-window addresses of the ring and of the full / empty barriers
 
     const RefineData D = A_.D;
     double *const d0 = A_.d0, *const d1 = A_.d1;
@@ -1151,6 +1202,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
     int slot_cur = 0, slot_spec = 1, slot_zero = 2;
 
     if (tid == 0) {
+        s_addr[0] = smem_u32(stages); s_addr[1] = smem_u32(full); s_addr[2] = smem_u32(empty);
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1191,8 +1243,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
         for (int j = 0; j < NS; ++j) acc[j] = 0.0;
         SweepScalars S;
         S.gmax = 0ull; S.eemax = 0ull; S.flags = 0u;
-        if (run_init) sweep<NF, true>(A_, P, U, stages, full, empty, n_my, cons, consumed, dx, dcand, slot_cur, acc, S);
-        else          sweep<NF, false>(A_, P, U, stages, full, empty, n_my, cons, consumed, dx, dcand, slot_spec, acc, S);
+        if (run_init) sweep<NF, true>(A_, P, U, s_addr, n_my, cons, consumed, dx, dcand, slot_cur, acc, S);
+        else          sweep<NF, false>(A_, P, U, s_addr, n_my, cons, consumed, dx, dcand, slot_spec, acc, S);
         // the candidate depths written above are read by TMA in the next phase: order them for the async proxy
         asm volatile("fence.proxy.async;" ::: "memory");
         __syncthreads();
