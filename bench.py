@@ -7,11 +7,12 @@
 
 A "step" = one pass of the hot path over one 1920x1080 frame pair: nonLinearRefinement ->
 sign fix -> depth raster -> setPose -> backProject -> interpolateCrackyImage (main.cc:457-523).
+The run processes ONE sequence of N x K distinct frame pairs, block-sharded by pair over the N
+ranks (BASELINE config 5 scaled to the run; weak scaling: K pairs per rank), with no data-path
+collective and one final NCCL all-gather of the per-pair records inside the timed region.
 `value` = pairs/s with every input already resident in HBM (CUDA events, max over ranks);
-`e2e`   = pairs/s through the same C-ABI call with HOST (pinned) buffers, host<->device copies
+`e2e`   = pairs/s through the compact C-ABI call with HOST (pinned) buffers, host<->device copies
           inside the timed region.
-Multi-GPU: frame pairs are independent, so ranks shard them with no data-path collective
-(weak scaling: every rank processes `steps` pairs); one final max-reduce of the elapsed time.
 """
 import argparse
 import importlib
@@ -35,7 +36,8 @@ WORKLOAD = ("synthetic analytic RS flow 1920x1080 (galaxy_stabil K, gamma 0.95),
             "RANSAC winner (H=16 hypotheses, tol 0.05), then per-scanline GS rectification + crack fill")
 ALGO_BYTES_PASS_A = 24.0   # read flow 16 B + inverse depth 8 B per residual block
 ALGO_BYTES_PASS_B = 32.0   # read flow 16 B + inverse depth 8 B, write candidate inverse depth 8 B
-N_PAIRS = 3                # distinct pairs cycled through: >= 3 x ~170 MB of inputs, larger than the 126 MB L2
+FP64_INSTR_PER_BLOCK = 188.0   # SASS count of the fused sweep's executed path (tools/sass_loops.py): DFMA + DMUL + DADD
+OTHER_INSTR_PER_BLOCK = 130.0  # ... and every other instruction of that path (integer, shuffles, loads, control)
 CONST_ACC = True           # headline workload: constant-acceleration trajectory (k estimated); --const-vel: k = 0 fixed
 
 
@@ -48,55 +50,63 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while a timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of one GPU, sampled through NVML every ~5 ms by a thread while the
+    timed regions run (nvidia-smi's 200 ms polling sees nothing of a 100 ms measurement)."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("hw_power_brake", 0x80),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.index = str(index)
-        self.proc = None
-        self.lines = []
+        self.index = index
+        self.samples, self.bits, self.max_mhz = [], 0, None
+        self.stop_flag = threading.Event()
+        self.t = None
+
+    def _handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            p = torch.cuda.get_device_properties(self.index)
+            return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)).encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-i", self.index, "-lms", "200"], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            nv, h = self._handle()
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            return
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        def loop():
+            while not self.stop_flag.is_set():
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    pass
+                time.sleep(0.005)
+
+        self.t = threading.Thread(target=loop, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"]}
+        self.stop_flag.set()
+        self.t.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_min_mhz": float(min(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": [n for n, b in self.REASONS if self.bits & b], "samples": len(self.samples)}
+
+
+def pair_params(p):
+    """Motion of frame pair p of the synthetic sequence (a slowly varying hand-held trajectory) and its seed."""
+    s = 0.1 * np.sin(0.37 * p)
+    c = 0.1 * np.cos(0.23 * p)
+    return dict(v=(0.30 * (1 + s), 0.05 * (1 - c), 0.02 * (1 + c)), w=(0.002 * (1 + c), -0.004 * (1 + s), 0.0087 * (1 - s)),
+                k=(0.5 * (1 + 0.5 * s)) if CONST_ACC else 0.0, seed=1000 + p)
 
 
 def gen_pair(synth, seed):
@@ -104,37 +114,45 @@ def gen_pair(synth, seed):
                            k=0.5 if CONST_ACC else 0.0, seed=seed, noise_sigma_px=0.3, outlier_frac=0.05)
 
 
-def prepare_pair_gpu(ctx, synth, torch, seed, H=16, tol=0.05):
-    """Upstream stages (flatten, alpha, RANSAC, consensus gather) on the GPU, outside any timed
-    region; returns device-resident inputs of the refine+rectify step and pinned host copies."""
-    P = gen_pair(synth, seed)
+def prepare_pair_gpu(ctx, synth, torch, p, H=16, tol=0.05, host=True):
+    """Frame pair p of the sequence: synthesis and the upstream stages (flatten, alpha, RANSAC, consensus
+    gather) on the GPU, outside any timed region.  Returns the device-resident inputs of the refine+rectify
+    step (expanded arrays, as nonLinearRefinement takes them) and, with host=True, pinned host copies of the
+    COMPACT inputs (flow field + RANSAC's outputs) and of the outputs."""
+    q = pair_params(p)
     dev = torch.device("cuda", torch.cuda.current_device())
-    flow_img = torch.from_numpy(P["flow_img"]).to(dev)
+    P = synth.make_pair_device(torch, dev, ROWS, COLS, "galaxy_stabil", gamma=0.95, v=q["v"], w=q["w"], k=q["k"], seed=q["seed"],
+                               noise_sigma_px=0.3, outlier_frac=0.05)
+    flow_img, image = P["flow_img"], P["image"]
     n, coord, flow, cpx, fpx, pidx = ctx.flatten(flow_img, P["K4"], P["gamma"])
     coord, flow, cpx, fpx = coord[:2 * n], flow[:2 * n], cpx[:2 * n], fpx[:2 * n]
     alpha, alpha_k = ctx.alpha(fpx, cpx, n, ROWS, P["gamma"])
-    samples = synth.sample_list(n, H, seed=seed + 100)
+    samples = synth.sample_list(n, H, seed=q["seed"] + 100)
     R = ctx.ransac(coord, flow, alpha, alpha_k, n, CONST_ACC, samples, tol)
     inl, a_in, ak_in, ix, m = ctx.gather_inliers(coord, alpha, alpha_k, n, R["mask"], R["inv_depth"])
-    image = torch.from_numpy(P["image"]).to(dev)
     d = dict(flow=flow.contiguous(), inliers3=inl.contiguous(), alpha=a_in.contiguous(), alpha_k=ak_in.contiguous(),
-             image=image, m=m, n=n, v=R["v"], w=R["w"], k=R["k"], K4=P["K4"], gamma=P["gamma"])
+             image=image, m=m, n=n, v=R["v"], w=R["w"], k=R["k"], K4=P["K4"], gamma=P["gamma"], pair=p)
     d["out"] = (torch.empty(m, dtype=torch.float64, device=dev), torch.empty(ROWS * COLS, dtype=torch.float64, device=dev),
                 torch.empty_like(image))
-    keep = []
+    if host:
+        keep = []
 
-    def pin(t):
-        t = t.cpu().pin_memory()
-        keep.append(t)
-        return t.numpy()
+        def pin(t):
+            t = t.cpu().pin_memory()
+            keep.append(t)
+            return t.numpy()
 
-    # (write-combined pinned inputs -- capi.HostBuffer(write_combined=True) -- were measured: no difference)
-    h = dict(flow=pin(d["flow"][:2 * m]), inliers3=pin(d["inliers3"]), alpha=pin(d["alpha"]), alpha_k=pin(d["alpha_k"]),
-             image=pin(image))
-    h["out"] = (pin(d["out"][0]), pin(d["out"][1]), pin(d["out"][2]))
-    h["_keep"] = keep
-    d["host"] = h
+        z = torch.empty(m, dtype=torch.float64).pin_memory(); rect = torch.empty(image.shape, dtype=torch.uint8).pin_memory()
+        keep += [z, rect]
+        d["compact"] = dict(flow_img=pin(flow_img), image=pin(image), mask=pin(R["mask"]), inv_depth=pin(R["inv_depth"]), n=n, m=m,
+                            v=R["v"], w=R["w"], k=R["k"], out=(z.numpy(), None, rect.numpy()), _keep=keep)
     return d
+
+
+def expanded_host(p):
+    """Host copies of the expanded arrays of a prepared pair (for the CPU baseline)."""
+    return dict(flow=p["flow"][:2 * p["m"]].cpu().numpy(), inliers3=p["inliers3"].cpu().numpy(), alpha=p["alpha"].cpu().numpy(),
+                alpha_k=p["alpha_k"].cpu().numpy(), image=p["image"].cpu().numpy())
 
 
 def prepare_pair_cpu(O, synth, seed, H=16, tol=0.05):
@@ -154,12 +172,6 @@ def prepare_pair_cpu(O, synth, seed, H=16, tol=0.05):
 def step_device(ctx, capi, p):
     return ctx.refine_rectify(p["flow"], p["inliers3"], p["alpha"], p["alpha_k"], p["m"], p["v"], p["w"], p["k"], CONST_ACC, False,
                               p["image"], p["K4"], p["gamma"], layout=capi.DEPTH_ROWMAJOR, out=p["out"])
-
-
-def step_host(ctx, capi, p):
-    h = p["host"]
-    return ctx.refine_rectify(h["flow"], h["inliers3"], h["alpha"], h["alpha_k"], p["m"], p["v"], p["w"], p["k"], CONST_ACC, False,
-                              h["image"], p["K4"], p["gamma"], layout=capi.DEPTH_ROWMAJOR, out=h["out"])
 
 
 def bind_to_gpu_numa_node(index):
@@ -185,7 +197,24 @@ def bind_to_gpu_numa_node(index):
         print("bench: CPU affinity not set (%s)" % e, file=sys.stderr)
 
 
+def fp64_pipe_cycles():
+    """Measured FP64 issue cost on this GPU (tools/fp64_operands.cu, committed output under profiles/): cycles per
+    warp-wide DFMA per SM sub-partition with operands served by the reuse cache, and with three distinct registers."""
+    p = os.path.join(ROOT, "profiles", "r02_fp64_operands.txt")
+    best, three = 2.0, 3.0
+    try:
+        for ln in open(p):
+            if "warps/SM= 8" in ln and "1 varying" in ln:
+                best = float(ln.split(":")[1].split()[0])
+            if "warps/SM= 8" in ln and "3 distinct" in ln:
+                three = float(ln.split(":")[1].split()[0])
+    except OSError:
+        pass
+    return best, three
+
+
 def run_ours(args):
+    import hashlib
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -203,97 +232,104 @@ def run_ours(args):
         dist.barrier()
     capi = importlib.import_module(PKG + ".capi")
     synth = importlib.import_module(PKG + ".synth")
+    seqm = importlib.import_module(PKG + ".sequence")
     stream = torch.cuda.current_stream()
     ctx = capi.Context(local, stream=stream.cuda_stream)
+    dev = torch.device("cuda", local)
+    K, W = args.steps, args.warmup
 
-    # weak scaling: every rank gets the SAME three pairs (same seeds), so that the per-GPU work -- in
-    # particular the data-dependent number of LM iterations -- does not change with the rank count
-    pairs = [prepare_pair_gpu(ctx, synth, torch, 1000 + i) for i in range(N_PAIRS)]
+    # BASELINE config 5, scaled to the run: ONE sequence of world * K distinct frame pairs, block-sharded over the
+    # ranks (rank r owns pairs [r K, (r + 1) K): weak scaling, the sequence grows with the rank count), plus W
+    # warm-up pairs per rank taken from behind the end of the sequence.
+    total = world * K
+    lo, hi = seqm.shard_range(total, rank, world)
+    mine = {p: prepare_pair_gpu(ctx, synth, torch, p) for p in range(lo, hi)}
+    warm = [prepare_pair_gpu(ctx, synth, torch, total + rank * W + i) for i in range(W)]
     torch.cuda.synchronize()
+    K4, gamma = warm[0]["K4"], warm[0]["gamma"]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
-        for i in range(warmup):
-            fn(ctx, capi, pairs[i % N_PAIRS])
-        barrier()
-        l0 = ctx.launch_count()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        its = 0
-        e0.record(stream)
-        for i in range(steps):
-            r = fn(ctx, capi, pairs[(warmup + i) % N_PAIRS])
-            its += r["summary"]["iterations"]
-        e1.record(stream)
-        barrier()
+    def elapsed_max(e0, e1):
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, ctx.launch_count() - l0, its
+        return ms
 
-    def seq_entries(i0, count, host):
-        out = []
-        for i in range(count):
-            p = pairs[(i0 + i) % N_PAIRS]
-            src = p["host"] if host else p
-            out.append(dict(flow=src["flow"], inliers3=src["inliers3"], alpha=src["alpha"], alpha_k=src["alpha_k"], image=src["image"],
-                            m=p["m"], v=p["v"], w=p["w"], k=p["k"], out=src["out"]))
-        return out
-
-    def timed_sequence(host, steps, warmup):
-        """K steps = one rsdsfm_refine_rectify_sequence call over K frame pairs (upload i+1 | compute i |
-        download i-1 on three streams; with device buffers only the result collection is deferred)."""
-        p0 = pairs[0]
-        run = lambda ent: ctx.refine_rectify_sequence(ent, CONST_ACC, False, p0["K4"], p0["gamma"], layout=capi.DEPTH_ROWMAJOR)
-        run(seq_entries(0, warmup, host))
-        ent = seq_entries(warmup, steps, host)
-        barrier()
-        l0 = ctx.launch_count()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        res = run(ent)
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, ctx.launch_count() - l0, sum(r["summary"]["iterations"] for r in res)
+    def dev_entry(p):
+        return dict(flow=p["flow"], inliers3=p["inliers3"], alpha=p["alpha"], alpha_k=p["alpha_k"], image=p["image"], m=p["m"],
+                    v=p["v"], w=p["w"], k=p["k"], out=p["out"])
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms, launches, its = timed_sequence(False, args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
-    lm_ms = 0.0
-    for i in range(min(args.steps, N_PAIRS)):          # ms per LM iteration: the solve's own CUDA-event time
-        r = step_device(ctx, capi, pairs[i])
-        lm_ms += r["summary"]["device_ms"] / max(r["summary"]["iterations"], 1)
-    lm_ms /= min(args.steps, N_PAIRS)
-    ms_e2e, _, _ = timed_sequence(True, args.steps, max(3, min(args.warmup, 3)))
-    # the same step through one synchronous rsdsfm_refine_rectify call per pair (no overlap between pairs)
-    # ... which is also where the dominant kernel is timed ALONE on the whole GPU for the roofline (in a
-    # sequence two solves share the SMs, so a kernel's own duration says little about the machine)
+
+    # ---- value: the rank's shard through rsdsfm_refine_rectify_sequence (device buffers, two compute lanes), then the
+    # final gather of the per-pair records over NCCL -- all inside the timed region
+    ctx.refine_rectify_sequence([dev_entry(p) for p in warm], CONST_ACC, False, K4, gamma, layout=capi.DEPTH_ROWMAJOR)
+    barrier()
+    l0 = ctx.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    _, rec, res = seqm.run_shard_sequence(ctx, lambda p: dev_entry(mine[p]), total, rank, world, CONST_ACC, False, K4, gamma,
+                                          batch=max(K, 1), layout=capi.DEPTH_ROWMAJOR)
+    records = seqm.gather_records(rec, total, dist if world > 1 else None, device=dev)
+    e1.record(stream)
+    barrier()
+    ms = elapsed_max(e0, e1)
+    launches = ctx.launch_count() - l0
+    its = float(records[:, 7].sum()) / max(world, 1)
+    # identical records for a pair whatever the rank count: the digest of the first shard is comparable across N
+    digest = hashlib.sha256(np.ascontiguousarray(records[:K]).tobytes()).hexdigest()[:16]
+
+    # ---- e2e: the same shard through the compact host interface (pinned host buffers: flow field + RANSAC outputs in,
+    # depths + rectified frame out; copies inside the timed region, overlapped with the compute of the neighbours)
+    run_c = lambda ps: ctx.refine_rectify_compact_sequence([p["compact"] for p in ps], CONST_ACC, False, K4, gamma,
+                                                           layout=capi.DEPTH_ROWMAJOR, want_depth_map=False)
+    run_c(warm[:max(3, min(W, 3))])
+    shard = [mine[p] for p in range(lo, hi)]
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    res_c = run_c(shard)
+    e1.record(stream)
+    barrier()
+    ms_e2e = elapsed_max(e0, e1)
+    e2e_ok = all(r["status"] == 0 for r in res_c) and all(
+        rc["summary"]["iterations"] == rd["summary"]["iterations"] for rc, rd in zip(res_c, res))
+    c0 = shard[0]["compact"]
+    h2d = sum(c0[k].nbytes for k in ("flow_img", "image", "mask", "inv_depth"))
+    d2h = c0["out"][0].nbytes + c0["out"][2].nbytes
+
+    # ---- one synchronous rsdsfm_refine_rectify call per pair (no overlap between pairs): where the dominant kernel
+    # runs ALONE on the whole GPU and is timed for the roofline (in a sequence two solves share the SMs)
+    for p in warm[:3]:
+        step_device(ctx, capi, p)
     ctx.profile_enable(True)
-    ms_single, _, _ = timed(step_device, args.steps, 3)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    lm_ms = 0.0
+    for p in shard:
+        r = step_device(ctx, capi, p)
+        lm_ms += r["summary"]["device_ms"] / max(r["summary"]["iterations"], 1)
+    e1.record(stream)
+    barrier()
+    ms_single = elapsed_max(e0, e1)
+    lm_ms /= max(len(shard), 1)
     prof = ctx.profile_read()
     ctx.profile_enable(False)
-    ms_single_host, _, _ = timed(step_host, args.steps, 3)
+    clocks = sampler.stop() if rank == 0 else None
 
-    p0 = pairs[0]
-    h2d = sum(p0["host"][k].nbytes for k in ("flow", "inliers3", "alpha", "alpha_k", "image"))
-    d2h = sum(a.nbytes for a in p0["host"]["out"])
     peak, peak_src = load_peaks()
-    # Dominant kernel = k_lm_persistent (one launch = one whole LM solve).  Algorithmic bytes per
-    # launch (SURVEY.md 8d): 24 B per residual block for the initial evaluation phase + 56 B per
-    # LM iteration (candidate step 32 B + evaluation 24 B; here fused into one sweep);
-    # duration = CUDA events around the launch on the launching stream, measured live.
+    # Dominant kernel = k_lm_solve (one launch = one whole LM solve).  Algorithmic bytes per launch:
+    # 24 B per residual block for the initial evaluation phase + 56 B per LM iteration (candidate step 32 B +
+    # evaluation 24 B; here fused into one sweep); duration = CUDA events around the launch on the launching stream.
     n_launch = max(prof["kernel_launches"], 1)
     algo_bytes = (ALGO_BYTES_PASS_A * prof["pass_a_blocks"] + (ALGO_BYTES_PASS_A + ALGO_BYTES_PASS_B) * prof["pass_b_blocks"]) / n_launch
     k_t = prof["kernel_ms"] / n_launch * 1e-3
@@ -301,29 +337,36 @@ def run_ours(args):
     f_t = prof["pass_b_ms"] / max(prof["pass_b_launches"], 1) * 1e-3
     f_blocks = prof["pass_b_blocks"] / max(prof["pass_b_launches"], 1)
     f_loop = prof["b_loop_ms"] / max(prof["pass_b_launches"], 1) * 1e-3
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "lm_kernel_traffic.json")     # dram bytes per launch from the committed ncu capture
     if os.path.exists(tp) and CONST_ACC:
         with open(tp) as f:
             tj = json.load(f)
-        # the captured launch ran `lm_iterations_in_captured_launch` iterations; scale to this run's average
         it_cap = float(tj.get("lm_iterations_in_captured_launch", 0)) or None
         it_now = prof["pass_b_launches"] / n_launch
         traffic = tj.get("dram_bytes_per_launch")
         if traffic is not None and it_cap:
             traffic = traffic * (it_now + 0.45) / (it_cap + 0.45)   # initial evaluation streams 24/56 of an iteration
-    # FP64 side of the roofline: ~218 double-precision instructions per residual block per fused
-    # iteration (SASS count), 64 FP64 lanes/SM -> 148 * 64 * 2 * 1.965 GHz = 37.2 TFLOP/s
-    fp64_instr = 218.0
+            traffic_src = ("NOT measured in this run: dram__bytes_read+write of the committed ncu capture (%s), "
+                           "rescaled from %d to %.1f LM iterations per launch" % (tj.get("source", "profiles/"), int(it_cap), it_now))
+    fp64_instr = FP64_INSTR_PER_BLOCK
+    cyc2, cyc3 = fp64_pipe_cycles()
+    sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
     line = None
     if rank == 0:
+        m_avg = int(np.mean([p["m"] for p in shard]))
         line = {
-            "metric": "frame-pairs/sec (refine+rectify, 1080p)", "value": world * args.steps / (ms * 1e-3), "unit": "pairs/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "metric": "frame-pairs/sec (refine+rectify, 1080p)", "value": total / (ms * 1e-3), "unit": "pairs/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / max(K, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rows": ROWS, "cols": COLS, "inliers_per_pair": int(np.mean([p["m"] for p in pairs])),
-                       "lm_iterations_per_pair": its / args.steps, "sharding": "independent frame pairs per rank, no collective",
-                       "l2": "inputs larger than L2: %d distinct pairs cycled (~%.0f MB device inputs each)" % (N_PAIRS, h2d / 1e6)},
+            "config": {"workload": WORKLOAD, "rows": ROWS, "cols": COLS, "inliers_per_pair": m_avg,
+                       "lm_iterations_per_pair": its / max(K, 1),
+                       "sequence": "one sequence of n_gpus x steps DISTINCT frame pairs (pair p: seed 1000+p, slowly varying motion), "
+                                   "block-sharded by pair over the ranks; no data-path collective, one final NCCL all-gather of the "
+                                   "per-pair records inside the timed region",
+                       "records_sha256_first_shard": digest,
+                       "l2": "inputs larger than L2: every step is a different pair (~%.0f MB of device inputs each)" % (
+                           sum(shard[0][k].numel() * shard[0][k].element_size() for k in ("flow", "inliers3", "alpha", "alpha_k", "image")) / 1e6)},
             "ms_per_lm_iteration": lm_ms,
             "lm_phase_breakdown_us": {
                 "initial_evaluation": {k[2:-3] + "_us": 1e3 * prof[k] / max(prof["pass_a_launches"], 1)
@@ -332,18 +375,21 @@ def run_ours(args):
                                  for k in ("b_loop_ms", "b_reduce_ms", "b_ctl_ms", "b_logic_ms")},
                 "kernel_ms_per_solve": prof["kernel_ms"] / max(prof["kernel_launches"], 1)},
             "clocks": clocks,
-            "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
-                    "api": "rsdsfm_refine_rectify_sequence, pinned host buffers: upload of pair i+1 and download of pair i-1 "
-                           "overlap the compute of pair i (PCIe-bound: one compute lane)",
-                    "single_call_ms_per_step": ms_single_host / args.steps},
-            "api": "rsdsfm_refine_rectify_sequence over `steps` pairs, device buffers (two solves share the SMs: even / odd pairs)",
-            "single_call_ms_per_step": ms_single / args.steps,
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / max(K, 1), "results_match_device_path": bool(e2e_ok),
+                    "api": "rsdsfm_refine_rectify_compact_sequence, pinned host buffers: the float64 flow field, the frame and "
+                           "RANSAC's outputs (consensus mask, winner inverse depths) go up, coordinates / alpha factors / pairing "
+                           "are rebuilt on the device; depths and the rectified frame come back (the depth raster stays on the "
+                           "device); the upload of pair i+1 and the download of pair i-1 overlap the compute of pair i"},
+            "api": "rsdsfm_refine_rectify_sequence over the rank's shard, device buffers (two solves share the SMs: even / odd pairs), "
+                   "+ sequence.gather_records",
+            "single_call_ms_per_step": ms_single / max(K, 1),
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm",
-                         "kernel": "k_lm_persistent<%d> (persistent LM solve: fused candidate-step + residual/Jacobian/Schur "
-                                   "evaluation sweep per iteration, FP64 grid reduction, on-device controller)" % (7 if CONST_ACC else 6),
+                         "kernel": "k_lm_solve<%d> (persistent LM solve: fused candidate-step + residual/Jacobian/Schur "
+                                   "evaluation sweep per iteration, FP64 grid reduction, replicated on-device controller)" % (7 if CONST_ACC else 6),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                          "algorithmic_bytes_per_block": {"initial_evaluation": ALGO_BYTES_PASS_A,
                                                          "lm_iteration": ALGO_BYTES_PASS_A + ALGO_BYTES_PASS_B},
@@ -352,11 +398,19 @@ def run_ours(args):
                                                 "achieved_GBps": ((ALGO_BYTES_PASS_A + ALGO_BYTES_PASS_B) * f_blocks / f_t / 1e9) if f_t > 0 else 0.0,
                                                 "streamed_bytes_per_block": 64,
                                                 "streamed_GBps_in_loop": (64.0 * f_blocks / f_loop / 1e9) if f_loop > 0 else 0.0},
-                         "fp64": {"instr_per_block_per_iteration": fp64_instr, "peak_tflops_nominal": 37.2,
+                         "fp64": {"note": "the sweep is FP64-issue bound, not HBM bound: an FP64 instruction holds its sub-partition's "
+                                          "issue port for >= 2 cycles (3 with three distinct register operands) and nothing else "
+                                          "issues meanwhile (tools/fp64_operands.cu, tools/fp64_mix.cu; outputs under profiles/)",
+                                  "instr_per_block_per_iteration": fp64_instr, "other_instr_per_block_per_iteration": OTHER_INSTR_PER_BLOCK,
+                                  "measured_cycles_per_fp64_instr": [cyc2, cyc3],
+                                  "issue_bound_us_per_iteration": (fp64_instr * 2.3 + OTHER_INSTR_PER_BLOCK) * f_blocks / 32.0
+                                                                  / (4 * 148) / (sm_hz * 1e6) * 1e6,
+                                  "peak_tflops_measured": 148 * 4 * 32 * 2 / cyc2 * sm_hz * 1e6 / 1e12,
                                   "achieved_tflops_in_loop": (2.0 * fp64_instr * f_blocks / f_loop / 1e12) if f_loop > 0 else 0.0}},
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(pairs[0], threads=1, budget_s=args.cpu_budget)
+            pb = dict(shard[0]); pb["host"] = expanded_host(shard[0])
+            line["cpu_baseline"] = cpu_baseline(pb, threads=1, budget_s=args.cpu_budget)
         emit(line)
     ctx.close()
     if world > 1:

@@ -166,3 +166,72 @@ def sample_list(n, H, seed=3):
     for h in range(H):
         out[h] = rng.choice(n, size=9, replace=False)
     return out
+
+
+def make_pair_device(torch, device, rows=1080, cols=1920, intrinsics="galaxy_stabil", gamma=0.95, v=(0.30, 0.05, 0.02),
+                     w=(0.002, -0.004, 0.0087), k=0.0, seed=1, noise_sigma_px=0.0, outlier_frac=0.0, ncells=64,
+                     z_range=(2.0, 30.0)):
+    """make_pair with the per-pixel work done by torch on `device` (milliseconds instead of seconds at 1080p),
+    for benchmarks that need many DISTINCT pairs.  Same scene model and the same exact solution of the RS
+    differential equations; the random streams differ from make_pair's (torch generators), so a pair is
+    reproducible from its seed on a given device type but is not the numpy pair of the same seed.
+    Returns dict(flow_img (rows, cols, 2) float64 tensor, image (rows, cols, 3) uint8 tensor, K4, gamma, v, w, k)."""
+    K4 = INTRINSICS[intrinsics] if isinstance(intrinsics, str) else tuple(intrinsics)
+    fx, fy, cx, cy = K4
+    rng = np.random.default_rng(seed)
+    sx = rng.uniform(0, cols, ncells); sy = rng.uniform(0, rows, ncells)
+    dmin, dmax = 1.0 / z_range[1], 1.0 / z_range[0]
+    c0 = rng.uniform(dmin * 1.5, dmax * 0.8, ncells)
+    a = rng.uniform(-0.15, 0.15, ncells) * c0
+    b = rng.uniform(-0.15, 0.15, ncells) * c0
+    f64 = dict(dtype=torch.float64, device=device)
+    T = lambda arr: torch.as_tensor(np.asarray(arr, dtype=np.float64), **f64)
+    jj, ii = torch.meshgrid(torch.arange(rows, **f64), torch.arange(cols, **f64), indexing="ij")
+    # nearest Voronoi site, in chunks of sites (rows x cols x 8 doubles at a time)
+    best = torch.full((rows, cols), float("inf"), **f64)
+    cell = torch.zeros((rows, cols), dtype=torch.int64, device=device)
+    sxt, syt = T(sx), T(sy)
+    for c in range(0, ncells, 8):
+        dist = (ii[..., None] - sxt[c:c + 8]) ** 2 + (jj[..., None] - syt[c:c + 8]) ** 2
+        dm, am = dist.min(dim=2)
+        upd = dm < best
+        best = torch.where(upd, dm, best); cell = torch.where(upd, am + c, cell)
+    x = (ii - cx) / fx; y = (jj - cy) / fy
+    xs, ys = (sxt - cx) / fx, (syt - cy) / fy
+    d = (T(a)[cell] * (x - xs[cell]) + T(b)[cell] * (y - ys[cell]) + T(c0)[cell]).clamp(dmin, dmax)
+    v = np.asarray(v, dtype=np.float64); w = np.asarray(w, dtype=np.float64)
+    gx = (v[0] - x * v[2]) * d + (-x * y * w[0] + (1 + x * x) * w[1] - y * w[2])
+    gy = (v[1] - y * v[2]) * d + (-(1 + y * y) * w[0] + x * y * w[1] + x * w[2])
+    h = float(rows)
+    if k == 0.0:
+        uy = gy / (1.0 - gy * fy / h)
+        beta = 1.0 + uy * fy / h
+    else:
+        uy = gy.clone()
+        for _ in range(60):
+            dy = uy * fy / gamma
+            alpha = 1.0 + gamma * dy / h
+            p1 = gamma * jj / h
+            p2 = 1.0 + gamma * (jj + dy) / h
+            beta = (2.0 / (2.0 + k)) * (alpha + k * 0.5 * (p2 * p2 - p1 * p1))
+            uy = beta * gy
+    flow = torch.stack((beta * gx * fx / gamma, uy * fy / gamma), dim=2)
+    g = torch.Generator(device=device); g.manual_seed(int(seed) + 1)
+    if noise_sigma_px > 0:
+        flow = flow + noise_sigma_px * torch.randn(flow.shape, generator=g, **f64)
+    if outlier_frac > 0:
+        mask = torch.rand((rows, cols), generator=g, device=device) < outlier_frac
+        rnd = torch.rand((rows, cols, 2), generator=g, **f64) * 40.0 - 20.0
+        flow = torch.where(mask[..., None], rnd, flow)
+    i32 = dict(dtype=torch.int32, device=device)
+    ji, iic = torch.meshgrid(torch.arange(rows, **i32), torch.arange(cols, **i32), indexing="ij")
+    img = torch.stack(((96 + 80 * torch.sin(iic * 0.031) * torch.cos(ji * 0.017)).to(torch.int32),
+                       (128 + 90 * torch.sin((iic + ji) * 0.011)).to(torch.int32),
+                       ((iic * 3 + ji * 5) % 200 + 30)), dim=2)
+    img = (img + torch.randint(-8, 9, img.shape, generator=g, **i32)).clamp(16, 255).to(torch.uint8)
+    nd = int(0.01 * rows * cols); nv = int(0.0005 * rows * cols)
+    pick = lambda n: (torch.randint(0, rows, (n,), generator=g, device=device), torch.randint(0, cols, (n,), generator=g, device=device))
+    r_, c_ = pick(nd); img[r_, c_] = torch.randint(0, 12, (nd, 3), generator=g, device=device).to(torch.uint8)
+    r_, c_ = pick(nv); img[r_, c_] = 1
+    return dict(flow_img=flow.contiguous(), image=img.contiguous(), K4=np.array(K4), gamma=float(gamma), v=v, w=w, k=float(k),
+                rows=rows, cols=cols)
