@@ -119,6 +119,26 @@ RSDSFM_API int rsdsfm_profile_detail(rsdsfm_ctx *ctx, double *out8);
 RSDSFM_API int rsdsfm_host_alloc(size_t bytes, int write_combined, void **out);
 RSDSFM_API int rsdsfm_host_free(void *p);
 
+/* ---- row split of ONE solve over several GPUs (BASELINE.json config 4; the reference is single-threaded, main.cc
+ * has nothing to replace here) ---------------------------------------------------------------------------------
+ * A group of contexts (one per GPU; one process per GPU, or several contexts of one process) solves one
+ * nonLinearRefinement problem together: every member passes ITS share of the residual blocks (any contiguous split of
+ * the consensus set) to rsdsfm_refine / rsdsfm_estimate_inverse_depths, which become collective calls -- every member
+ * must make the same sequence of calls.  Each member receives the complete refined motion, the same termination
+ * report, and the depths of its share.  Per LM iteration one row of 84 sums crosses the GPUs, through peer memory
+ * (NVLink), from inside the persistent kernels; there is no NCCL call and no host round trip.
+ *   1. every member: rsdsfm_peer_export -> a 64-byte CUDA IPC handle of its mailbox;
+ *   2. the caller exchanges the handles (e.g. torch.distributed.all_gather) and every member calls
+ *      rsdsfm_peer_connect with all of them, in group order;
+ *   3. a barrier of the caller's choice (the mailboxes are cleared by connect), then the collective solves.
+ * rsdsfm_peer_connect_local does 1-2 for contexts of ONE process.  rsdsfm_peer_disconnect returns a context to
+ * single-GPU operation.  At most 8 members. */
+#define RSDSFM_PEER_HANDLE_BYTES 64
+RSDSFM_API int rsdsfm_peer_export(rsdsfm_ctx *ctx, void *handle_out);
+RSDSFM_API int rsdsfm_peer_connect(rsdsfm_ctx *ctx, int n_members, int my_index, const void *handles);
+RSDSFM_API int rsdsfm_peer_connect_local(rsdsfm_ctx **members, int n_members);
+RSDSFM_API int rsdsfm_peer_disconnect(rsdsfm_ctx *ctx);
+
 /* ---- a2: flatten + normalise glue (main.cc:398-432, errorMeasure.cpp:66-97) --------------- */
 /* flow_img: rows*cols*2.  Outputs (each 2*rows*cols doubles) are pre-filled like the reference
  * (coord = 1, flow = 0) and the kept pixels (|flow|^2 > flow_threshold) are compacted in

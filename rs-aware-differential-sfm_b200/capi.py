@@ -477,6 +477,29 @@ class Context:
         self._ck(rc)
         return res
 
+    # ---- row split of one solve over several GPUs
+    def peer_export(self):
+        """rsdsfm_peer_export: the 64-byte CUDA IPC handle of this context's mailbox (bytes)."""
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.rsdsfm_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_connect(self, handles, my_index):
+        """rsdsfm_peer_connect: `handles` = the members' exported handles in group order (list of 64-byte strings)."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * len(handles)
+        self._ck(self.lib.rsdsfm_peer_connect(self.h, len(handles), int(my_index), blob))
+
+    def peer_disconnect(self):
+        self._ck(self.lib.rsdsfm_peer_disconnect(self.h))
+
+    @staticmethod
+    def peer_connect_local(contexts):
+        """rsdsfm_peer_connect_local: contexts of THIS process (one per GPU) form a group, in list order."""
+        arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+        rc = contexts[0].lib.rsdsfm_peer_connect_local(arr, len(contexts))
+        contexts[0]._ck(rc)
+
     # ---- SURVEY 8(f)-1
     def reprojection_error(self, coords3d, unproj, R_gt, t_gt, depth_est, K4, max_norm=1.0, layout=DEPTH_COLMAJOR,
                            want_image=False, want_gt_depth=False):

@@ -89,6 +89,8 @@ void rsdsfm_destroy(rsdsfm_ctx *ctx)
         if (ctx->pe0[j]) cudaEventDestroy(ctx->pe0[j]);
         if (ctx->pe1[j]) cudaEventDestroy(ctx->pe1[j]);
     }
+    rsdsfm_peer_disconnect(ctx);
+    if (ctx->mailbox) cudaFree(ctx->mailbox);
     if (ctx->pinned_io) cudaFreeHost(ctx->pinned_io);
     DevBuf *all[] = {&ctx->partials, &ctx->sums, &ctx->pix, &ctx->dA, &ctx->dB, &ctx->rdepth, &ctx->misc, &ctx->winner,
                      &ctx->poses, &ctx->hyp, &ctx->rpart, &ctx->scan,
@@ -99,6 +101,91 @@ void rsdsfm_destroy(rsdsfm_ctx *ctx)
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+// ---- row split of one solve over several GPUs: mailboxes in peer memory (lm_kernel.cuh: peer_allreduce)
+static int peer_mailbox(rsdsfm_ctx *ctx)
+{
+    RS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->mailbox) {
+        cudaError_t e = cudaMalloc(&ctx->mailbox, lm_mailbox_bytes());      // its own allocation: exported through CUDA IPC
+        if (e != cudaSuccess) return fail(ctx, RSDSFM_ERR_NOMEM, "cudaMalloc (mailbox)", e);
+    }
+    RS_CUDA(ctx, cudaMemsetAsync(ctx->mailbox, 0, lm_mailbox_bytes(), ctx->stream));
+    RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RSDSFM_OK;
+}
+
+int rsdsfm_peer_disconnect(rsdsfm_ctx *ctx)
+{
+    if (!ctx) return RSDSFM_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int g = 0; g < 8; ++g) {
+        if (ctx->peer_ipc[g] && ctx->peer_mail[g]) cudaIpcCloseMemHandle(ctx->peer_mail[g]);
+        ctx->peer_mail[g] = nullptr; ctx->peer_ipc[g] = false;
+    }
+    ctx->n_peers = 1; ctx->my_peer = 0; ctx->peer_epoch = 0;
+    return RSDSFM_OK;
+}
+
+int rsdsfm_peer_export(rsdsfm_ctx *ctx, void *handle_out)
+{
+    RS_ENTER(ctx);
+    if (!handle_out) return fail(ctx, RSDSFM_ERR_ARG, "rsdsfm_peer_export: null handle");
+    static_assert(sizeof(cudaIpcMemHandle_t) == RSDSFM_PEER_HANDLE_BYTES, "IPC handle size");
+    RS_TRY(peer_mailbox(ctx));
+    cudaIpcMemHandle_t h;
+    RS_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->mailbox));
+    memcpy(handle_out, &h, sizeof h);
+    return RSDSFM_OK;
+}
+
+int rsdsfm_peer_connect(rsdsfm_ctx *ctx, int n_members, int my_index, const void *handles)
+{
+    RS_ENTER(ctx);
+    if (n_members < 1 || n_members > 8 || my_index < 0 || my_index >= n_members || !handles)
+        return fail(ctx, RSDSFM_ERR_ARG, "rsdsfm_peer_connect: 1..8 members, my_index inside the group");
+    rsdsfm_peer_disconnect(ctx);
+    if (!ctx->mailbox) RS_TRY(peer_mailbox(ctx));
+    for (int g = 0; g < n_members; ++g) {
+        if (g == my_index) { ctx->peer_mail[g] = ctx->mailbox; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + (size_t)g * RSDSFM_PEER_HANDLE_BYTES, sizeof h);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { rsdsfm_peer_disconnect(ctx); return fail(ctx, RSDSFM_ERR_CUDA, "cudaIpcOpenMemHandle (peer mailbox)", e); }
+        ctx->peer_mail[g] = p; ctx->peer_ipc[g] = true;
+    }
+    ctx->n_peers = n_members; ctx->my_peer = my_index; ctx->peer_epoch = 0;
+    return RSDSFM_OK;
+}
+
+int rsdsfm_peer_connect_local(rsdsfm_ctx **members, int n_members)
+{
+    if (!members || n_members < 1 || n_members > 8) return RSDSFM_ERR_ARG;
+    for (int g = 0; g < n_members; ++g) {
+        if (!members[g]) return RSDSFM_ERR_ARG;
+        rsdsfm_peer_disconnect(members[g]);
+        RS_TRY(peer_mailbox(members[g]));
+    }
+    for (int g = 0; g < n_members; ++g) {
+        rsdsfm_ctx *c = members[g];
+        RS_CUDA(c, cudaSetDevice(c->device));
+        for (int o = 0; o < n_members; ++o) {
+            if (o != g && members[o]->device != c->device) {
+                int can = 0;
+                RS_CUDA(c, cudaDeviceCanAccessPeer(&can, c->device, members[o]->device));
+                if (!can) return fail(c, RSDSFM_ERR_CUDA, "rsdsfm_peer_connect_local: no peer access between the devices");
+                cudaError_t e = cudaDeviceEnablePeerAccess(members[o]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(c, RSDSFM_ERR_CUDA, "cudaDeviceEnablePeerAccess", e);
+                cudaGetLastError();
+            }
+            c->peer_mail[o] = members[o]->mailbox;
+        }
+        c->n_peers = n_members; c->my_peer = g; c->peer_epoch = 0;
+    }
+    return RSDSFM_OK;
 }
 
 const char *rsdsfm_last_error(rsdsfm_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }

@@ -42,6 +42,13 @@ struct rsdsfm_ctx {
     rsdsfm::DevBuf hyp, rpart, scan, lm_shared, exc;
     rsdsfm::DevBuf pipe[16];  // intermediates of the fused a2-a15 driver (pipeline.cu)
     int exc_cap = 0;          // capacity (entries) of the clamped-pixel exception list
+    // Row split of one solve over several GPUs (refine.cu / lm_kernel.cuh): this GPU's mailbox (its own allocation, so
+    // that it can be exported through CUDA IPC) and the mailboxes of the group, peer_mail[my_peer] == mailbox.
+    void *mailbox = nullptr;
+    void *peer_mail[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool peer_ipc[8] = {false, false, false, false, false, false, false, false};   // opened with cudaIpcOpenMemHandle
+    int n_peers = 1, my_peer = 0;
+    unsigned int peer_epoch = 0;   // split solves since the group was formed (identical on every GPU of the group)
     void *pinned = nullptr;   // small pinned host buffer for reduced sums / scalars
     size_t pinned_cap = 0;
     // Pipelined sequences (pipeline.cu): while pair i computes on `stream`, pair i+1 uploads on

@@ -202,6 +202,40 @@ __device__ __forceinline__ bool not_finite(double x) { return (__double2hiint(x)
 __device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 __device__ __forceinline__ unsigned long long dbits(double v) { return (unsigned long long)__double_as_longlong(v); }
 
+// ------------------------------------------------------------------------------------------
+// Row split of ONE solve over several GPUs (BASELINE config 4).  Every GPU sweeps its own share of the
+// residual blocks with this same kernel; what crosses the GPUs is one row of sums per phase (and the sums
+// of the listed pixels, when there are any).  The exchange goes through peer memory (NVLink), without NCCL
+// and without leaving the persistent kernel: every value travels with the tag of its exchange in ONE 16-byte
+// store -- a reader that sees the tag it waits for also sees the value -- so there is neither a fence nor a
+// flag.  CTA 0 of every GPU writes its GPU's totals into the mailbox of every GPU; every CTA then waits
+// for the rows of all GPUs in its local mailbox and combines them in GPU order: all CTAs of all GPUs hold
+// bit-identical sums and their replicated controllers take identical decisions.
+// ------------------------------------------------------------------------------------------
+struct __align__(16) Tagged {
+    double v;
+    unsigned long long tag;
+};
+constexpr int kMaxPeers = 8;
+constexpr int kMailSlots = 16;          // exchanges in flight before a slot is reused (at most ~8 per phase)
+constexpr int kMailLd = 96;             // values per row
+struct PeerInfo {
+    Tagged *mail[kMaxPeers];            // mail[g]: mailbox of GPU g, [kMailSlots][kMaxPeers][kMailLd]; mail[me] is local memory
+    int n, me;
+    unsigned int epoch;                 // solve number (the same on every GPU): tags are (epoch << 32) | exchange number
+};
+__device__ __forceinline__ void st_tagged(Tagged *p, double v, unsigned long long tag)
+{
+    asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(tag) : "memory");
+}
+__device__ __forceinline__ Tagged ld_tagged(const Tagged *p)
+{
+    long long v; unsigned long long t;
+    asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(v), "=l"(t) : "l"(p) : "memory");
+    Tagged r; r.v = __longlong_as_double(v); r.tag = t;
+    return r;
+}
+
 struct PhaseParams {           // shared-memory copy of the phase parameters (+ options, start point)
     int next, which_x, first, cur_list;
     Motion mot, cand;
@@ -248,7 +282,7 @@ struct Row {
 };
 constexpr int kExcVals = kTri + kMaxNF;          // exception sums: S triangle + rhs
 constexpr int kRowLd = 96;                       // >= Row<7>::NV (81): three 32-lane column chunks
-static_assert(Row<7>::NV <= kRowLd && kExcVals <= kRowLd, "row scratch");
+static_assert(Row<7>::NV + 3 <= kRowLd && kExcVals <= kRowLd, "row scratch");
 
 struct SweepScalars {                           // per-thread non-FP64 accumulators of a sweep
     unsigned long long gmax, eemax;             // bit patterns of max |e^T r|, max e^Te
@@ -828,8 +862,8 @@ __device__ __forceinline__ void publish_phase(const LmController &c, PhaseParams
 // has listed (clamped) pixels: their sums need the whole CTA, and the caller finishes the step.
 template <int NF>
 __device__ __noinline__ int controller_warp(LmController &c, PhaseParams &P, SweepU &U, const double *fin, int *s_flag,
-                                            const unsigned int *s_ne, int slot_cur, int slot_spec, bool run_init,
-                                            unsigned int exc_cap, double (*Lm)[8])
+                                            const unsigned int *s_ne, const unsigned int *s_ne_all, int slot_cur, int slot_spec,
+                                            bool run_init, unsigned int exc_cap, double (*Lm)[8])
 {
     using T = TAcc<NF>;
     using RW = Row<NF>;
@@ -860,9 +894,9 @@ __device__ __noinline__ int controller_warp(LmController &c, PhaseParams &P, Swe
     }
     const bool accepted = (nx == (int)LM_RUN_A);
     const int cur = run_init ? slot_cur : (accepted ? slot_spec : slot_cur);
-    unsigned int ne = s_ne[cur];
+    unsigned int ne = s_ne[cur];                                 // this GPU's list
     if (ne > exc_cap) ne = exc_cap;
-    const int need_cta = (NF > 0 && ne > 0u) ? 1 : 0;
+    const int need_cta = (NF > 0 && s_ne_all[cur] > 0u) ? 1 : 0;   // listed pixels on ANY GPU of a row split
     if (lane == 0) { s_flag[1] = nx; s_flag[3] = accepted ? 1 : 0; s_flag[4] = cur; s_flag[2] = (int)ne; s_flag[6] = need_cta; }
     if (need_cta) return 1;
     if (accepted) {
@@ -976,6 +1010,40 @@ __device__ __noinline__ void exc_sums(int mode, const ExcEntry *cur_exc, int ne,
     cta_reduce_sums<kExcVals>(a, part, out);
 }
 
+// All-reduce of vals[0..n) over the GPUs of a row split (whole CTA; vals in shared memory, identical in all CTAs of
+// a GPU).  Columns [0, n_sum) and [tail, n) are added in GPU order, column i_or is or-ed, the others (bit patterns of
+// non-negative doubles) are max-ed.  seq: number of this exchange within the solve (the same on every GPU).  false: watchdog.
+__device__ __noinline__ bool peer_allreduce(const PeerInfo &pi, double *vals, int n, int n_sum, int i_or, int tail, unsigned int seq,
+                                            const int *abort_flag)
+{
+    const int tid = threadIdx.x;
+    const unsigned long long tag = ((unsigned long long)pi.epoch << 32) | (unsigned long long)(seq + 1u);
+    const size_t slot = (size_t)(seq % (unsigned)kMailSlots) * kMaxPeers * kMailLd;
+    if (blockIdx.x == 0 && tid < n)
+        for (int g = 0; g < pi.n; ++g) st_tagged(pi.mail[g] + slot + (size_t)pi.me * kMailLd + tid, vals[tid], tag);
+    int err = 0;
+    if (tid < n) {
+        const Tagged *box = pi.mail[pi.me] + slot + tid;
+        double x = 0.0;
+        unsigned long long xb = 0ull;
+        const unsigned long long t0 = globaltimer();
+        for (int g = 0; g < pi.n; ++g) {
+            Tagged t = ld_tagged(box + (size_t)g * kMailLd);
+            while (t.tag != tag) {
+                __nanosleep(40);
+                t = ld_tagged(box + (size_t)g * kMailLd);
+                if (t.tag != tag && (globaltimer() - t0 > 4000000000ull || __ldcg(abort_flag))) { err = 1; break; }
+            }
+            if (err) break;
+            if (tid < n_sum || tid >= tail) x += t.v;
+            else if (tid == i_or) xb |= (unsigned long long)__double_as_longlong(t.v);
+            else { const unsigned long long b = (unsigned long long)__double_as_longlong(t.v); xb = b > xb ? b : xb; }
+        }
+        vals[tid] = (tid < n_sum || tid >= tail) ? x : __longlong_as_double((long long)xb);
+    }
+    return __syncthreads_or(err) == 0;
+}
+
 struct SolveArgs {
     RefineData D;
     double *d0, *d1;
@@ -988,6 +1056,7 @@ struct SolveArgs {
     double *out;
     int invert_out;
     double *zstats;
+    PeerInfo peers;              // n = 1: a solve on one GPU
 };
 
 // Ring bookkeeping: tile "uses" are numbered from kernel start; use u lives in stage u % kStages and completes
@@ -1180,7 +1249,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
     __shared__ ExcSums s_exc;
     __shared__ double s_L[7][8];
     __shared__ int s_flag[8];     // [1] next, [2] n_exc of the current list, [3] accepted, [4] current slot, [5] error, [6] listed pixels: CTA-wide path, [7] flags
-    __shared__ unsigned int s_ne[kExcSlots];
+    __shared__ unsigned int s_ne[kExcSlots], s_ne_all[kExcSlots];   // listed pixels: on this GPU / on all GPUs of a row split
     __shared__ uint32_t s_addr[4];  // shared-window addresses of the ring and of the full / empty barriers
 
     const RefineData D = A_.D;
@@ -1195,6 +1264,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
     const int n_my = ((int)blockIdx.x < NT) ? (NT - 1 - (int)blockIdx.x) / G + 1 : 0;
     const int pre = n_my < kStages ? n_my : kStages;              // tiles queued ahead of a phase
     unsigned int gen = 0;
+    unsigned int xseq = 0;                                        // exchanges with the other GPUs of a row split so far
     unsigned int consumed = 0;                                    // tile uses consumed by this CTA since kernel start
     RingPos cons{0, 0u};                                          // every use before this position has been consumed; a phase's first `pre` tiles are queued ahead of it
     // exception lists: cur = list of the current point, spec = list the FUSED evaluation appends to,
@@ -1329,10 +1399,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
             }
             __syncthreads();
         }
+        if (tid < kExcSlots) s_ne_all[tid] = s_ne[tid];
+        if (A_.peers.n > 1) {
+            // row split: the totals (and the numbers of listed pixels) of all GPUs, combined in GPU order
+            if (tid < kExcSlots) fin[RW::NV + tid] = (double)s_ne[tid];
+            __syncthreads();
+            const bool ok = peer_allreduce(A_.peers, fin, RW::NV + kExcSlots, 2 * NS, RW::oFLAGS, RW::NV, xseq++, &sh->error);
+            if (tid < kExcSlots) s_ne_all[tid] = (unsigned int)fin[RW::NV + tid];
+            if (!ok) {
+                if (tid == 0) { sh->error = 1; P.error = 1; }
+                drain_prefetch(full, empty, &cons, &consumed, pre, false);
+                __syncthreads();
+                break;
+            }
+        }
+        __syncthreads();
         const unsigned long long t_fin = t_begin ? globaltimer() : 0ull;
         // ---- the controller step: one warp, one contiguous piece of code (controller_warp)
         if (warp == 0)
-            controller_warp<NF>(s_ctl, P, U, fin, s_flag, s_ne, slot_cur, slot_spec, run_init, exc_cap, s_L);
+            controller_warp<NF>(s_ctl, P, U, fin, s_flag, s_ne, s_ne_all, slot_cur, slot_spec, run_init, exc_cap, s_L);
         __syncthreads();
         const bool accepted = s_flag[3] != 0;
         if (!run_init) {
@@ -1368,6 +1453,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
             const bool xsorted = sort_exceptions(exc + (size_t)s_flag[4] * exc_cap, s_flag[2], xkeys, 16384);
             if (accepted) {
                 exc_sums<NF>(0, exc + (size_t)s_flag[4] * exc_cap, s_flag[2], xkeys, xsorted, 0.0, 0.0, 0.0, part, fin);
+                if (A_.peers.n > 1) peer_allreduce(A_.peers, fin, kExcVals, kExcVals, -1, kExcVals, xseq++, &sh->error);
                 if (tid < T::TRI) s_ctl.ev.G1[tid] += fin[tid];
                 if (tid < NF) s_ctl.ev.h1[tid] += fin[kTri + tid];
                 __syncthreads();
@@ -1381,6 +1467,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
             while (s_flag[1] == (int)LM_SOLVE) {
                 exc_sums<NF>(1, exc + (size_t)s_flag[4] * exc_cap, s_flag[2], xkeys, xsorted, s_ctl.radius, s_ctl.opt.min_lm_diagonal,
                              s_ctl.opt.max_lm_diagonal, part, fin);
+                if (A_.peers.n > 1) peer_allreduce(A_.peers, fin, kExcVals, kExcVals, -1, kExcVals, xseq++, &sh->error);
                 if (tid < kTri) s_exc.S[tid] = fin[tid];
                 if (tid < kMaxNF) s_exc.rhs[tid] = fin[kTri + tid];
                 __syncthreads();

@@ -77,7 +77,14 @@ static int launch_persistent(rsdsfm_ctx *ctx, RefineData D, double *d0, double *
     const size_t smem = sizeof(Stage) * (size_t)kStages;
     if (ctx->profile) cudaEventRecord(ctx->pe0[ctx->io_slot], ctx->stream);
     RS_CUDA(ctx, cudaFuncSetAttribute(k_lm_solve<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SolveArgs a{D, d0, d1, sh, partials, exc, exc_cap, z_in, z_stride, out, invert_out, zstats};
+    SolveArgs a{};
+    a.D = D; a.d0 = d0; a.d1 = d1; a.sh = sh; a.partials = partials; a.exc = exc; a.exc_cap = exc_cap;
+    a.z_in = z_in; a.z_stride = z_stride; a.out = out; a.invert_out = invert_out; a.zstats = zstats;
+    a.peers.n = 1; a.peers.me = 0; a.peers.epoch = 0;
+    if (ctx->n_peers > 1) {            // row split: every GPU of the group launches the same solve (collective call)
+        a.peers.n = ctx->n_peers; a.peers.me = ctx->my_peer; a.peers.epoch = ++ctx->peer_epoch;
+        for (int g = 0; g < ctx->n_peers; ++g) a.peers.mail[g] = (Tagged *)ctx->peer_mail[g];
+    }
     void *args[] = {&a};
     RS_CUDA(ctx, cudaLaunchCooperativeKernel((void *)k_lm_solve<NF>, dim3(grid), dim3(kThreads), args, smem, ctx->stream));
     if (ctx->profile) cudaEventRecord(ctx->pe1[ctx->io_slot], ctx->stream);
@@ -139,6 +146,8 @@ static int lm_solve_async(rsdsfm_ctx *ctx, const RefineData &D, double *d0, doub
     const int nv = (nf == 0) ? Row<0>::NV : (nf == 6 ? Row<6>::NV : Row<7>::NV);
     RS_TRY(ensure(ctx, ctx->partials, sizeof(double) * 2 * (size_t)grid * nv));   // rows of even / odd phases
     if (ctx->exc_cap < min_exc_cap()) ctx->exc_cap = min_exc_cap();
+    // (row split: a member cannot repeat its solve alone when its list overflows, so the lists start larger)
+    if (ctx->n_peers > 1 && ctx->exc_cap < D.m / 16 + 4096) ctx->exc_cap = D.m / 16 + 4096;
     RS_TRY(ensure(ctx, ctx->exc, sizeof(ExcEntry) * kExcSlots * (size_t)ctx->exc_cap));   // current + speculative + being cleared
     static_assert(sizeof(LmShared) <= 8192 - 256, "pinned slot layout (common.cuh)");
 
@@ -311,6 +320,8 @@ int refine_device(rsdsfm_ctx *ctx, const double *flow, const double *inliers3, c
         mot.k = *k;
         bool overflow = false;
         RS_TRY(lm_collect(ctx, const_acc ? 7 : 6, m, &mot, summary, &overflow));
+        if (overflow && ctx->n_peers > 1)
+            return fail(ctx, RSDSFM_ERR_INTERNAL, "refine (row split): clamped-pixel list overflow on this member");
         if (overflow) continue;                         // exception list enlarged: run again
         for (int j = 0; j < 3; ++j) { v[j] = mot.v[j]; w[j] = mot.w[j]; }
         *k = mot.k;
@@ -344,5 +355,9 @@ int estimate_inverse_depths_device(rsdsfm_ctx *ctx, const double *coord, const d
     bool overflow = false;
     return lm_collect(ctx, 0, n, nullptr, summary, &overflow);
 }
+
+// ---- row split over GPUs: the mailbox of this context and the mailboxes of its peers
+size_t lm_mailbox_bytes() { return sizeof(Tagged) * (size_t)kMailSlots * kMaxPeers * kMailLd; }
+static_assert(kMailLd >= kRowLd, "a mailbox row holds a row of sums");
 
 }  // namespace rsdsfm

@@ -45,6 +45,7 @@ int refine_prepared_async(rsdsfm_ctx *, int m, const double *v, const double *w,
 int compact_build_device(rsdsfm_ctx *, const void *flow_img, int flow_f32, int rows, int cols, const double *K4, double gamma,
                          double thr, const uint8_t *mask, const double *inv_depth, int n, int m, void *blk, double *d0,
                          double *z_in, double *xy, int *input_flag);
+size_t lm_mailbox_bytes();                              // mailbox of a row split over GPUs (lm_kernel.cuh)
 int lm_grid_size(const rsdsfm_ctx *);                   // CTAs of the LM kernel = rows of its z statistics
 int lm_reserve(rsdsfm_ctx *, int m);                     // pre-sizes the solver's buffers for up to m residual blocks
 int lm_collect_enqueue(rsdsfm_ctx *, const double *stats_dev8);   // zero-copy read-back into the I/O slot's pinned area
