@@ -22,6 +22,7 @@ EXPORTS = [
     "rsdsfm_refine", "rsdsfm_depth_glue", "rsdsfm_set_relative_pose", "rsdsfm_backproject", "rsdsfm_fill_cracks",
     "rsdsfm_refine_rectify", "rsdsfm_refine_rectify_sequence", "rsdsfm_refine_rectify_compact_sequence", "rsdsfm_pipeline_pair", "rsdsfm_pipeline_sequence",
     "rsdsfm_relocate_pose", "rsdsfm_reprojection_error", "rsdsfm_true_flow", "rsdsfm_host_alloc", "rsdsfm_host_free",
+    "rsdsfm_peer_export", "rsdsfm_peer_connect", "rsdsfm_peer_connect_local", "rsdsfm_peer_disconnect",
 ]
 
 
