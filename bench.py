@@ -32,7 +32,7 @@ PKG = "rs-aware-differential-sfm_b200"
 ROWS, COLS = 1080, 1920
 WORKLOAD = ("synthetic analytic RS flow 1920x1080 (galaxy_stabil K, gamma 0.95), piecewise-planar depth "
             "(64 Voronoi planes, Z in [2,30]), constant-acceleration trajectory k=0.5, sigma 0.3 px noise + 5% "
-            "outliers, refine (const-acc, 7 motion parameters + one inverse depth per inlier) started from the "
+            "outliers, flow rounded to float32 as DeepFlow delivers it, refine (const-acc, 7 motion parameters + one inverse depth per inlier) started from the "
             "RANSAC winner (H=16 hypotheses, tol 0.05), then per-scanline GS rectification + crack fill")
 ALGO_BYTES_PASS_A = 24.0   # read flow 16 B + inverse depth 8 B per residual block
 ALGO_BYTES_PASS_B = 32.0   # read flow 16 B + inverse depth 8 B, write candidate inverse depth 8 B
@@ -123,7 +123,8 @@ def prepare_pair_gpu(ctx, synth, torch, p, H=16, tol=0.05, host=True):
     dev = torch.device("cuda", torch.cuda.current_device())
     P = synth.make_pair_device(torch, dev, ROWS, COLS, "galaxy_stabil", gamma=0.95, v=q["v"], w=q["w"], k=q["k"], seed=q["seed"],
                                noise_sigma_px=0.3, outlier_frac=0.05)
-    flow_img, image = P["flow_img"], P["image"]
+    flow32 = P["flow_img"].float()                      # optical flow arrives as float32 (DeepFlow, camera.cc:262-274) ...
+    flow_img, image = flow32.double(), P["image"]        # ... and is widened to double by the caller (main.cc:398-432)
     n, coord, flow, cpx, fpx, pidx = ctx.flatten(flow_img, P["K4"], P["gamma"])
     coord, flow, cpx, fpx = coord[:2 * n], flow[:2 * n], cpx[:2 * n], fpx[:2 * n]
     alpha, alpha_k = ctx.alpha(fpx, cpx, n, ROWS, P["gamma"])
@@ -144,7 +145,7 @@ def prepare_pair_gpu(ctx, synth, torch, p, H=16, tol=0.05, host=True):
 
         z = torch.empty(m, dtype=torch.float64).pin_memory(); rect = torch.empty(image.shape, dtype=torch.uint8).pin_memory()
         keep += [z, rect]
-        d["compact"] = dict(flow_img=pin(flow_img), image=pin(image), mask=pin(R["mask"]), inv_depth=pin(R["inv_depth"]), n=n, m=m,
+        d["compact"] = dict(flow_img=pin(flow32), image=pin(image), mask=pin(R["mask"]), inv_depth=pin(R["inv_depth"]), n=n, m=m,
                             v=R["v"], w=R["w"], k=R["k"], out=(z.numpy(), None, rect.numpy()), _keep=keep)
     return d
 
@@ -377,7 +378,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / max(K, 1), "results_match_device_path": bool(e2e_ok),
-                    "api": "rsdsfm_refine_rectify_compact_sequence, pinned host buffers: the float64 flow field, the frame and "
+                    "api": "rsdsfm_refine_rectify_compact_sequence, pinned host buffers: the float32 flow field, the frame and "
                            "RANSAC's outputs (consensus mask, winner inverse depths) go up, coordinates / alpha factors / pairing "
                            "are rebuilt on the device; depths and the rectified frame come back (the depth raster stays on the "
                            "device); the upload of pair i+1 and the download of pair i-1 overlap the compute of pair i"},

@@ -211,6 +211,7 @@ static int sequence_core(rsdsfm_ctx *ctx, int mem, std::vector<SeqPair> &pairs, 
     // context of its own; with both lanes busy each LM solve takes half of the SMs.
     // Host buffers, expanded interface: the sequence is PCIe-bound and a lane holds its staging slot for the whole
     // (twice as long) half-GPU compute, which would starve the upload stream -- one lane, full-GPU solves.
+    // (compact interface, host buffers, two lanes: measured 631 vs 761 pairs/s with one lane -- same reason)
     const bool two_lanes = !host && n_ok >= 2 && ctx->num_sms >= 2 && !getenv("RSDSFM_SINGLE_LANE");
     if (two_lanes && !ctx->lane1) {
         if (rsdsfm_create(ctx->device, nullptr, &ctx->lane1) != RSDSFM_OK)
