@@ -13,8 +13,8 @@
 // decisions, which are functions of a few global sums.  Per (point, hypothesis) only the inverse
 // depth is kept between passes, in two ping-pong planes (current point / candidate); a pass
 // evaluates the current point, takes the candidate step, writes the candidate depth and reduces
-// the sums the controller needs; the host runs the Ceres logic per hypothesis and flips the planes
-// of the hypotheses whose step was accepted.  The kernel is bound by FP64 issue (IEEE divisions and
+// the sums the controller needs; a one-block-per-hypothesis kernel (k_ransac_ctl) runs the Ceres logic and
+// flips the planes of the hypotheses whose step was accepted -- no host round trip per pass.  The kernel is bound by FP64 issue (IEEE divisions and
 // square roots that bit-exactness forbids replacing): algorithmic traffic is 48 B per point per
 // hypothesis (L2-resident: the point arrays are 100 MB) plus 16 B of depth planes per pass.
 #include "common.cuh"
@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(kThreads, OCC) k_ransac_pass(const double2 *__
     // so the point arrays are fetched from DRAM once per pass and served from L2 to the other hypotheses
     const int h0 = blockIdx.x * HG, chunk = blockIdx.y, nchunks = gridDim.y;
     load_hyps<HG>(sh, hyps, h0, H);
+    if (HG == 1 && !sh[0].active) return;          // finished (or never started): its row of partials is not read
     double s[HG * RS_NS], mx[HG * RM_NM];
 #pragma unroll
     for (int j = 0; j < HG * RS_NS; ++j) s[j] = 0.0;
@@ -196,8 +197,11 @@ __global__ void __launch_bounds__(kThreads, OCC) k_ransac_score(const double2 *_
     const int h0 = blockIdx.x * HG, chunk = blockIdx.y, nchunks = gridDim.y;
     load_hyps<HG>(sh, hyps, h0, H);
     double s[HG * 2], mx[1] = {0.0};
+    int cnt[HG];
 #pragma unroll
     for (int j = 0; j < HG * 2; ++j) s[j] = 0.0;
+#pragma unroll
+    for (int g = 0; g < HG; ++g) cnt[g] = 0;
     for (int i = chunk * blockDim.x + threadIdx.x; i < n; i += nchunks * blockDim.x) {
         const double2 qq = q[i], uu = u[i];
         const double al = alpha[i], alk = alpha_k[i];
@@ -207,9 +211,14 @@ __global__ void __launch_bounds__(kThreads, OCC) k_ransac_score(const double2 *_
             const HypDev &h = sh[g];
             const double d = final_depth(h, depth, h0 + g, n, i);
             const double err = ransac_error(qq.x, qq.y, uu.x, uu.y, al, alk, h, d);
-            if (err < tol) { s[g * 2] += 1.0; s[g * 2 + 1] += err; }
+            const bool inl = err < tol;
+            cnt[g] += __popc(__ballot_sync(__activemask(), inl));        // every lane keeps the warp's count
+            if (inl) s[g * 2 + 1] += err;
         }
     }
+    // lane 0 of every warp carries the warp's ballot count into the block sum (exact: integers below 2^53)
+#pragma unroll
+    for (int g = 0; g < HG; ++g) s[g * 2] = ((threadIdx.x & 31) == 0) ? (double)cnt[g] : 0.0;
     block_reduce_store<HG * 2, 0>(s, mx, partials + (size_t)blockIdx.x * nchunks * (HG * 2), chunk);
 }
 
@@ -252,6 +261,115 @@ __global__ void __launch_bounds__(kThreads) k_ransac_reduce(const double *__rest
     }
 }
 
+// ---- the Ceres logic of every hypothesis' depth-only problem, on the device -------------------------------
+// Per batch: HypDev (what the pass kernels read), the LmController of each hypothesis and its pending request.
+struct HypCtl {
+    LmController ctl;
+    int pend;                   // LmNext the next sums answer (LM_RUN_A: evaluation at a new point, LM_RUN_B: candidate)
+};
+
+__global__ void k_ransac_init(const double *__restrict__ hyps7, int Hb, int n, rsdsfm_lm_options opt, HypDev *hd, HypCtl *hc,
+                              int *n_active)
+{
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= Hb) return;
+    const double *p = hyps7 + 7 * h;
+    HypDev d;
+    memset(&d, 0, sizeof d);
+    bool finite = true;
+    for (int j = 0; j < 7; ++j) finite = finite && isfinite(p[j]);
+    for (int j = 0; j < 3; ++j) { d.w[j] = p[j]; d.v[j] = p[3 + j]; }
+    d.k = p[6];
+    d.c2 = 2.0 / (2.0 + p[6]);
+    hc[h].ctl.init(opt, 0, nullptr);
+    hc[h].pend = (int)LM_RUN_A;
+    d.radius = hc[h].ctl.radius;
+    // solver.cc: non-finite parameter values => FAILURE, depths stay at 1.0.  n == 0: nothing to do.
+    d.active = (finite && n > 0) ? 1 : 0;
+    d.failed = finite ? 0 : 1;
+    hd[h] = d;
+    if (d.active) atomicAdd(n_active, 1);
+}
+
+// One block per hypothesis: the sums of its pass (same order as k_ransac_reduce: one warp per column, lane l
+// combines rows l, l+32, ... in ascending order, then a fixed shuffle tree), then the controller step on thread 0.
+__global__ void __launch_bounds__(kThreads) k_ransac_ctl(const double *__restrict__ partials, int gx, HypDev *hd, HypCtl *hc, int *n_active)
+{
+    constexpr int width = RS_NS + RM_NM;
+    __shared__ double row[width];
+    const int h = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (!hd[h].active) return;
+    for (int j = warp; j < width; j += kWarps) {
+        const double *p = partials + (size_t)h * gx * width + j;
+        const bool is_sum = j < RS_NS;
+        double v = 0.0;                                       // maxima are all >= 0
+        for (int b = lane; b < gx; b += 32) { const double x = p[(size_t)b * width]; v = is_sum ? v + x : fmax(v, x); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double x = __shfl_xor_sync(0xffffffffu, v, o);
+            v = is_sum ? v + x : fmax(v, x);
+        }
+        if (lane == 0) row[j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const double *ss = row, *mm = row + RS_NS;
+    LmController &c = hc[h].ctl;
+    EvalSums e;
+    memset(&e, 0, sizeof e);
+    e.cost = ss[RS_COST]; e.sumsq_d = ss[RS_SUMSQ_D]; e.gmax_e = mm[RM_GMAX_E]; e.bad = mm[RM_BAD];
+    CandSums cs;
+    cs.mcc = ss[RS_MCC]; cs.step_sq = ss[RS_STEP_SQ]; cs.cand_cost = ss[RS_CAND_COST];
+    cs.bad_step = mm[RM_BAD_STEP]; cs.bad_cand = mm[RM_BAD_CAND];
+    LmNext next = (LmNext)hc[h].pend;
+    if (next == LM_RUN_A) next = c.on_eval(e);               // evaluation at a new point
+    while (next == LM_SOLVE) next = c.solve_step(nullptr);   // no f-blocks: nothing to solve
+    if (next == LM_RUN_B) next = c.on_candidate(cs);
+    hc[h].pend = (int)next;
+    if (next == LM_DONE) {
+        // the candidate of the terminating iteration is not taken (Ceres tests the tolerances first)
+        hd[h].active = 0;
+        hd[h].failed = (c.termination == RSDSFM_FAILURE) ? 1 : 0;
+        atomicSub(n_active, 1);
+    } else {
+        if (c.accepted_last) { hd[h].cur ^= 1; hd[h].n_acc++; }   // the candidate plane becomes the current point
+        hd[h].radius = c.radius;
+    }
+}
+
+// Exact tie-break (minimal.cc:255-278 adds the errors of the inliers in index order): per-point errors of one
+// hypothesis (0 for outliers) ...
+__global__ void __launch_bounds__(kThreads) k_ransac_errors(const double2 *__restrict__ q, const double2 *__restrict__ u,
+                                                            const double *__restrict__ alpha, const double *__restrict__ alpha_k, int n,
+                                                            const HypDev *__restrict__ hyps, int which, double tol,
+                                                            const double *__restrict__ depth, double *err_out)
+{
+    const HypDev h = hyps[which];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double2 qq = q[i], uu = u[i];
+        const double err = ransac_error(qq.x, qq.y, uu.x, uu.y, alpha[i], alpha_k[i], h, final_depth(h, depth, which, n, i));
+        err_out[i] = (err < tol) ? err : 0.0;
+    }
+}
+// ... and their sum in ascending index order, by one thread
+__global__ void __launch_bounds__(kThreads) k_sequential_sum(const double *__restrict__ x, int n, double *out)
+{
+    __shared__ double buf[2][2048];
+    double s = 0.0;
+    for (int t = threadIdx.x; t < 2048 && t < n; t += kThreads) buf[0][t] = x[t];
+    __syncthreads();
+    for (int base = 0, b = 0; base < n; base += 2048, b ^= 1) {
+        const int cnt = n - base < 2048 ? n - base : 2048;
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < cnt; ++i) s += buf[b][i];                 // index order: the reference's loop
+        } else {
+            for (int t = threadIdx.x - 1; t < 2048 && base + 2048 + t < n; t += kThreads - 1) buf[b ^ 1][t] = x[base + 2048 + t];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = s;
+}
+
 __global__ void k_gather_samples(const double2 *__restrict__ q, const double2 *__restrict__ u,
                                  const double *__restrict__ alpha, const double *__restrict__ alpha_k,
                                  const int32_t *__restrict__ samples, int count, int n, double *out6)
@@ -265,99 +383,84 @@ __global__ void k_gather_samples(const double2 *__restrict__ q, const double2 *_
     out6[6 * t + 4] = alpha[idx]; out6[6 * t + 5] = alpha_k[idx];
 }
 
-// Scores one batch of Hb <= kHChunk hypotheses (host array hyps7) on device-resident points.
+// Scores one batch of Hb <= kHChunk hypotheses (host array hyps7) on device-resident points.  The depth-only LM of
+// every hypothesis runs without host round trips: [pass, controller] pairs are queued blind -- a finished hypothesis
+// makes its CTAs return at once -- followed by the scoring pass; ONE synchronisation then tells whether every solve
+// had terminated (almost always: 3-4 passes) or more passes are needed.
 static int score_batch(rsdsfm_ctx *ctx, const double *q, const double *u, const double *alpha, const double *alpha_k, int n,
                        const double *hyps7, int Hb, double tol, int *counts, double *sumerr, HypDev **hd_out)
 {
     rsdsfm_lm_options opt;
     rsdsfm_lm_default_options(&opt);
-    constexpr int hg = kHG;
-    const int gy = (Hb + hg - 1) / hg;
+    static_assert(kHG == 1, "one hypothesis per CTA row");
+    const int gy = Hb;
     const int gx = grid_for(ctx, n, 2);
-    const int widthP = hg * (RS_NS + RM_NM), widthS = hg * 2;
+    constexpr int widthP = RS_NS + RM_NM, widthS = 2;
     RS_TRY(ensure(ctx, ctx->partials, sizeof(double) * (size_t)gx * gy * widthP));
-    RS_TRY(ensure(ctx, ctx->sums, sizeof(double) * (size_t)gy * widthP));
-    RS_TRY(ensure(ctx, ctx->hyp, sizeof(HypDev) * (size_t)gy * hg));
-    RS_TRY(ensure(ctx, ctx->rdepth, sizeof(double) * 2 * (size_t)gy * hg * (size_t)(n > 0 ? n : 1)));
-    RS_TRY(ensure_pinned(ctx, sizeof(HypDev) * (size_t)gy * hg + sizeof(double) * (size_t)gy * widthP + 64));
-    HypDev *hh = (HypDev *)ctx->pinned;
-    double *hs = (double *)((char *)ctx->pinned + sizeof(HypDev) * (size_t)gy * hg);
+    RS_TRY(ensure(ctx, ctx->sums, sizeof(double) * ((size_t)gy * widthS + 8)));
+    RS_TRY(ensure(ctx, ctx->hyp, sizeof(HypDev) * (size_t)kHChunk + sizeof(HypCtl) * (size_t)kHChunk + sizeof(double) * 7 * (size_t)kHChunk + 64));
+    RS_TRY(ensure(ctx, ctx->rdepth, sizeof(double) * 2 * (size_t)gy * (size_t)(n > 0 ? n : 1)));
+    RS_TRY(ensure_pinned(ctx, sizeof(double) * ((size_t)gy * widthS + 8) + sizeof(double) * 7 * (size_t)kHChunk + 64));
+    double *hs = (double *)ctx->pinned;                                   // [gy * 2] counts / error sums, then the active count
+    double *h7 = hs + (size_t)gy * widthS + 8;                            // staging of the hypotheses
     HypDev *hd = (HypDev *)ctx->hyp.p;
+    HypCtl *hc = (HypCtl *)(hd + kHChunk);
+    double *d7 = (double *)(hc + kHChunk);
+    int *n_active = (int *)(d7 + 7 * kHChunk);
     double *partials = (double *)ctx->partials.p, *sums = (double *)ctx->sums.p, *depth = (double *)ctx->rdepth.p;
+    int *sums_active = (int *)(sums + (size_t)gy * widthS);
     *hd_out = hd;
 
-    std::vector<LmController> ctl((size_t)Hb);
-    std::vector<LmNext> pend((size_t)Hb, LM_RUN_A);
-    memset(hh, 0, sizeof(HypDev) * (size_t)gy * hg);
-    int n_active = 0;
-    for (int h = 0; h < Hb; ++h) {
-        const double *p = hyps7 + 7 * h;
-        for (int j = 0; j < 3; ++j) { hh[h].w[j] = p[j]; hh[h].v[j] = p[3 + j]; }
-        hh[h].k = p[6];
-        hh[h].c2 = 2.0 / (2.0 + p[6]);
-        ctl[h].init(opt, 0, nullptr);
-        hh[h].radius = ctl[h].radius;
-        bool finite = true;
-        for (int j = 0; j < 7; ++j) finite = finite && isfinite(p[j]);
-        // solver.cc: non-finite parameter values => FAILURE, depths stay at 1.0.  n == 0: nothing to do.
-        hh[h].active = (finite && n > 0) ? 1 : 0;
-        hh[h].failed = finite ? 0 : 1;
-        n_active += hh[h].active;
-    }
+    memcpy(h7, hyps7, sizeof(double) * 7 * (size_t)Hb);
+    RS_CUDA(ctx, cudaMemcpyAsync(d7, h7, sizeof(double) * 7 * (size_t)Hb, cudaMemcpyHostToDevice, ctx->stream));
+    RS_CUDA(ctx, cudaMemsetAsync(n_active, 0, sizeof(int), ctx->stream));
+    k_ransac_init<<<1, kHChunk, 0, ctx->stream>>>(d7, Hb, n, opt, hd, hc, n_active);
+    ctx->launches++;
     const dim3 grid(gy, gx);          // x = hypothesis row (fastest), y = point chunk
-    while (n_active > 0) {
-        RS_CUDA(ctx, cudaMemcpyAsync(hd, hh, sizeof(HypDev) * (size_t)gy * hg, cudaMemcpyHostToDevice, ctx->stream));
-        k_ransac_pass<kHG, kPassOcc><<<grid, kThreads, 0, ctx->stream>>>((const double2 *)q, (const double2 *)u, alpha, alpha_k, n, hd, Hb,
-                                                                          opt.min_lm_diagonal, opt.max_lm_diagonal, depth, partials);
-        k_ransac_reduce<<<gy, kThreads, 0, ctx->stream>>>(partials, gx, widthP, hg * RS_NS, sums);
-        ctx->launches += 2;
-        RS_CUDA(ctx, cudaMemcpyAsync(hs, sums, sizeof(double) * (size_t)gy * widthP, cudaMemcpyDeviceToHost, ctx->stream));
-        RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        n_active = 0;
-        for (int h = 0; h < Hb; ++h) {
-            if (!hh[h].active) continue;
-            const double *row = hs + (size_t)(h / hg) * widthP;
-            const double *ss = row + (h % hg) * RS_NS, *mm = row + hg * RS_NS + (h % hg) * RM_NM;
-            EvalSums e;
-            memset(&e, 0, sizeof e);
-            e.cost = ss[RS_COST]; e.sumsq_d = ss[RS_SUMSQ_D]; e.gmax_e = mm[RM_GMAX_E]; e.bad = mm[RM_BAD];
-            CandSums c;
-            c.mcc = ss[RS_MCC]; c.step_sq = ss[RS_STEP_SQ]; c.cand_cost = ss[RS_CAND_COST];
-            c.bad_step = mm[RM_BAD_STEP]; c.bad_cand = mm[RM_BAD_CAND];
-            LmNext next = pend[h];
-            if (next == LM_RUN_A) next = ctl[h].on_eval(e);               // evaluation at a new point
-            while (next == LM_SOLVE) next = ctl[h].solve_step(nullptr);   // no f-blocks: nothing to solve
-            if (next == LM_RUN_B) next = ctl[h].on_candidate(c);
-            pend[h] = next;
-            if (next == LM_DONE) {
-                // the candidate of the terminating iteration is not taken (Ceres tests the tolerances first)
-                hh[h].active = 0;
-                hh[h].failed = (ctl[h].termination == RSDSFM_FAILURE) ? 1 : 0;
-            } else {
-                if (ctl[h].accepted_last) { hh[h].cur ^= 1; hh[h].n_acc++; }   // the candidate plane becomes the current point
-                hh[h].radius = ctl[h].radius;
-                n_active++;
+    int passes = 4;                   // a depth-only solve takes 3-4 passes
+    for (int round = 0; round < 64; ++round) {
+        if (n > 0) {
+            for (int p = 0; p < passes; ++p) {
+                k_ransac_pass<kHG, kPassOcc><<<grid, kThreads, 0, ctx->stream>>>((const double2 *)q, (const double2 *)u, alpha, alpha_k, n, hd,
+                                                                                  Hb, opt.min_lm_diagonal, opt.max_lm_diagonal, depth, partials);
+                k_ransac_ctl<<<gy, kThreads, 0, ctx->stream>>>(partials, gx, hd, hc, n_active);
             }
+            k_ransac_score<kHG, kScoreOcc><<<grid, kThreads, 0, ctx->stream>>>((const double2 *)q, (const double2 *)u, alpha, alpha_k, n, hd, Hb,
+                                                                                tol, depth, partials);
+            k_ransac_reduce<<<gy, kThreads, 0, ctx->stream>>>(partials, gx, widthS, widthS, sums);
+            ctx->launches += 2 * passes + 2;
+        } else {
+            RS_CUDA(ctx, cudaMemsetAsync(sums, 0, sizeof(double) * (size_t)gy * widthS, ctx->stream));
         }
-    }
-    // scoring
-    RS_CUDA(ctx, cudaMemcpyAsync(hd, hh, sizeof(HypDev) * (size_t)gy * hg, cudaMemcpyHostToDevice, ctx->stream));
-    if (n > 0) {
-        k_ransac_score<kHG, kScoreOcc><<<grid, kThreads, 0, ctx->stream>>>((const double2 *)q, (const double2 *)u, alpha, alpha_k, n, hd, Hb,
-                                                                            tol, depth, partials);
-        k_ransac_reduce<<<gy, kThreads, 0, ctx->stream>>>(partials, gx, widthS, widthS, sums);
-        ctx->launches += 2;
-        RS_CUDA(ctx, cudaMemcpyAsync(hs, sums, sizeof(double) * (size_t)gy * widthS, cudaMemcpyDeviceToHost, ctx->stream));
+        RS_CUDA(ctx, cudaMemcpyAsync(sums_active, n_active, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+        RS_CUDA(ctx, cudaMemcpyAsync(hs, sums, sizeof(double) * ((size_t)gy * widthS + 1), cudaMemcpyDeviceToHost, ctx->stream));
         RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    } else {
-        RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        for (int j = 0; j < gy * widthS; ++j) hs[j] = 0.0;
+        if (*(const int *)(hs + (size_t)gy * widthS) <= 0) break;        // every solve had terminated before the scoring pass
+        passes = 2;
     }
     for (int h = 0; h < Hb; ++h) {
-        const double *row = hs + (size_t)(h / hg) * widthS + (h % hg) * 2;
-        counts[h] = (int)row[0];
-        sumerr[h] = row[1];
+        counts[h] = (int)hs[(size_t)h * widthS];
+        sumerr[h] = hs[(size_t)h * widthS + 1];
     }
+    return RSDSFM_OK;
+}
+
+// minimal.cc:278 decides a tie in the inlier count by `<` on the error sums, which the reference accumulates in index
+// order; the parallel sums agree with those to rounding only.  For a tie the sums of both contenders are therefore
+// recomputed in that order (rare: per-point errors in parallel, then one thread adds them up).
+static int exact_error_sum(rsdsfm_ctx *ctx, const double *q, const double *u, const double *alpha, const double *alpha_k, int n,
+                           const HypDev *hd, int which, double tol, double *out)
+{
+    RS_TRY(ensure(ctx, ctx->misc, sizeof(double) * ((size_t)n + 8)));
+    double *err = (double *)ctx->misc.p;
+    k_ransac_errors<<<grid_for(ctx, n, 4), kThreads, 0, ctx->stream>>>((const double2 *)q, (const double2 *)u, alpha, alpha_k, n, hd, which, tol,
+                                                                       (const double *)ctx->rdepth.p, err);
+    k_sequential_sum<<<1, kThreads, 0, ctx->stream>>>(err, n, err + n);
+    ctx->launches += 2;
+    RS_TRY(ensure_pinned(ctx, 64));
+    RS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, err + n, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    RS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = *(const double *)ctx->pinned;
     return RSDSFM_OK;
 }
 
@@ -376,13 +479,41 @@ int ransac_score_device(rsdsfm_ctx *ctx, const double *q, const double *u, const
         const int Hb = (H - b0 < kHChunk) ? (H - b0) : kHChunk;
         HypDev *hd = nullptr;
         RS_TRY(score_batch(ctx, q, u, alpha, alpha_k, n, hyps7 + 7 * (size_t)b0, Hb, tol, cnt.data(), err.data(), &hd));
-        int batch_best = -1;
+        // minimal.cc:278 scans the hypotheses in order and replaces the leader on a larger count, or on an equal count
+        // and a smaller error sum: the winner is, among the hypotheses with the largest count, the first one with the
+        // smallest sum.  Only ties AT the largest count need the index-order sums.
+        int batch_max = -1, n_max = 0;
         for (int h = 0; h < Hb; ++h) {
             if (counts) counts[b0 + h] = cnt[(size_t)h];
             if (sumerr) sumerr[b0 + h] = err[(size_t)h];
-            if (cnt[(size_t)h] > best_count || (cnt[(size_t)h] == best_count && err[(size_t)h] < best_err)) {   // minimal.cc:278
-                best_count = cnt[(size_t)h]; best_err = err[(size_t)h]; best = b0 + h; batch_best = h;
+            if (cnt[(size_t)h] > batch_max) { batch_max = cnt[(size_t)h]; n_max = 1; }
+            else if (cnt[(size_t)h] == batch_max) ++n_max;
+        }
+        // The parallel sums agree with the index-order sums to n * 2^-53 relative at worst (n < 2^23: 1e-9), so only
+        // contenders whose parallel sums lie within that of the smallest one can change places: those are re-summed
+        // in index order (rare: duplicated or scaled copies of one hypothesis), everybody else is decided already.
+        double min_par = 0.0;
+        bool have = false;
+        for (int h = 0; h < Hb; ++h)
+            if (cnt[(size_t)h] == batch_max && (!have || err[(size_t)h] < min_par)) { min_par = err[(size_t)h]; have = true; }
+        const double band = min_par + 1e-9 * fabs(min_par);
+        int n_close = 0;
+        for (int h = 0; h < Hb; ++h) if (cnt[(size_t)h] == batch_max && err[(size_t)h] <= band) ++n_close;
+        int batch_best = -1;
+        double batch_err = 0.0;
+        for (int h = 0; h < Hb; ++h) {
+            if (cnt[(size_t)h] != batch_max || !(err[(size_t)h] <= band)) continue;
+            if (n_close > 1 && batch_max > 0 && n > 0) {
+                RS_TRY(exact_error_sum(ctx, q, u, alpha, alpha_k, n, hd, h, tol, &err[(size_t)h]));
+                if (sumerr) sumerr[b0 + h] = err[(size_t)h];             // report the index-order sums where they were formed
             }
+            if (batch_best < 0 || err[(size_t)h] < batch_err) { batch_best = h; batch_err = err[(size_t)h]; }
+        }
+        // against the leader of the earlier batches (its depths are gone: a tie across batches is decided on the sums as they are)
+        if (batch_best >= 0 && (batch_max > best_count || (batch_max == best_count && batch_err < best_err))) {
+            best_count = batch_max; best_err = batch_err; best = b0 + batch_best;
+        } else {
+            batch_best = -1;
         }
         // the depth planes only live until the next batch: extract the leader's consensus set now
         if (batch_best >= 0 && n > 0 && (mask_best || inv_depth_best)) {

@@ -85,6 +85,27 @@ def test_ransac_from_samples_and_gather(ctx, oracle, case_cv):
         assert np.array_equal(inl, c["inliers3"]) and np.array_equal(a, c["alpha_in"]) and np.array_equal(ak, c["alpha_k_in"])
 
 
+def test_ransac_tie_in_inlier_count_is_decided_like_the_reference(ctx, oracle, case_cv):
+    """minimal.cc:278: equal inlier counts are decided by `<` on the error sums, which the reference accumulates in
+    index order.  Copies of one hypothesis with the translation scaled by 1 +- a few ulps have the same consensus set
+    (the depth-only LM absorbs the scale) and error sums that differ in the last bits: the winner must be the one the
+    sequential sums pick -- the GPU recomputes the contenders' sums in index order for exactly this case."""
+    c = case_cv
+    base = c["ransac"]["hyps"][c["ransac"]["best_idx"]].copy()
+    hyps = np.stack([base.copy() for _ in range(6)])
+    for j, s in enumerate([1.0, 1.0 + 2.3e-16, 1.0 - 1.2e-16, 1.0 + 4.5e-16, 1.0, 1.0 - 3.4e-16]):
+        hyps[j, 3:6] = base[3:6] * s
+    ref = oracle.ransac(c["coord"], c["flow"], c["alpha"], c["alpha_k"], c["n"], False, c["tol"], hyps=hyps)
+    got = ctx.ransac_score(c["coord"], c["flow"], c["alpha"], c["alpha_k"], c["n"], hyps, c["tol"])
+    assert np.array_equal(got["counts"], ref["counts"])
+    assert len(set(int(x) for x in ref["counts"])) < len(ref["counts"]), "the case must contain ties"
+    assert got["best_idx"] == ref["best_idx"]
+    assert np.array_equal(got["mask"], ref["mask"])
+    # the reported sum of the winner, when it won a tie, is the index-order sum: bit-equal to the reference's
+    if list(ref["counts"]).count(ref["counts"][ref["best_idx"]]) > 1 and ref["best_idx"] > 0:
+        assert got["sumerr"][got["best_idx"]] == ref["sumerr"][ref["best_idx"]]
+
+
 def test_ransac_degenerate_hypotheses(ctx, oracle, case_cv):
     c = case_cv
     hyps = c["ransac"]["hyps"].copy()
