@@ -418,6 +418,54 @@ public:
         setUnprojectionMaps(m[0], m[1], m[2]);
         return true;
     }
+    // rsframe.cc:222-378: N_gs_unproject_{x,y,z}.csv -- the world points seen by the global-shutter frame
+    bool setUnprojectionMapGs(const std::string csv_unprojection_x, const std::string csv_unprojection_y,
+                              const std::string csv_unprojection_z)
+    {
+        std::vector<double> v[3];
+        const std::string *paths[3] = {&csv_unprojection_x, &csv_unprojection_y, &csv_unprojection_z};
+        for (int a = 0; a < 3; ++a)
+            if (!rsdsfm_host::readCsv(*paths[a], rows_, cols_, v[a], "GS unprojection map")) {
+                std::cout << "Unprojection maps for GS image not set" << std::endl;
+                return false;
+            }
+        Eigen::MatrixXd *dst[3] = {&gs_unprojection_map_x_, &gs_unprojection_map_y_, &gs_unprojection_map_z_};
+        for (int a = 0; a < 3; ++a) {
+            *dst[a] = Eigen::MatrixXd::Zero(rows_, cols_);
+            for (int y = 0; y < rows_; ++y) for (int x = 0; x < cols_; ++x) (*dst[a])(y, x) = v[a][(size_t)y * cols_ + x];
+        }
+        return true;
+    }
+    // rsframe.cc:565-586 / :589-614: depth of every pixel's world point in the camera frame -- of scanline 0 for the GS
+    // frame, of the pixel's own scanline for the RS frame; pixels without a world point (all-zero entry) get depth 0.
+    void setSyntheticDepthMapGs()
+    {
+        gs_depth_map_ = Eigen::MatrixXd::Zero(rows_, cols_);
+        for (int y = 0; y < (int)scanlines_.size(); ++y)
+            for (int x = 0; x < cols_; ++x) {
+                const Eigen::Vector3d Pw(gs_unprojection_map_x_(y, x), gs_unprojection_map_y_(y, x), gs_unprojection_map_z_(y, x));
+                gs_depth_map_(y, x) = (Pw.norm() > 0) ? worldToCameraFrame(Pw, 0).z() : 0.0;
+            }
+    }
+    void setSyntheticDepthMapRs()
+    {
+        depth_map_ = Eigen::MatrixXd::Zero(rows_, cols_);
+        double z_sum = 0;
+        long z_count = 0;
+        for (int y = 0; y < (int)scanlines_.size(); ++y)
+            for (int x = 0; x < cols_; ++x) {
+                const Eigen::Vector3d Pw(unprojection_map_x_(y, x), unprojection_map_y_(y, x), unprojection_map_z_(y, x));
+                if (Pw.norm() > 0) { const double z = worldToCameraFrame(Pw, y).z(); depth_map_(y, x) = z; z_sum += z; ++z_count; }
+            }
+        std::cout << "z mean: " << z_sum * 1.0 / z_count << std::endl;
+    }
+    Eigen::MatrixXd getGsDepthMap() { return gs_depth_map_; }
+    // rsframe.cc:617-625
+    Eigen::Vector3d getUnprojectedWorldCoordinates(const Eigen::Vector2d &point)
+    {
+        const int r = (int)point.y(), c = (int)point.x();
+        return Eigen::Vector3d(unprojection_map_x_(r, c), unprojection_map_y_(r, c), unprojection_map_z_(r, c));
+    }
     bool hasUnprojectionMaps() const { return unprojection_map_x_.rows() == rows_ && unprojection_map_x_.cols() == cols_ && rows_ > 0; }
     // camera.cc:209-249 seen from frame 1: flow towards `frame2` (its relative scanline poses, rsframe.h:239)
     cv::Mat_<cv::Point_<double>> trueFlowTo(const RsFrame &frame2)
@@ -512,6 +560,7 @@ private:
     cv::Mat image_, gs_image_, coordinates_3d_;
     Eigen::MatrixXd depth_map_;
     Eigen::MatrixXd unprojection_map_x_, unprojection_map_y_, unprojection_map_z_;
+    Eigen::MatrixXd gs_unprojection_map_x_, gs_unprojection_map_y_, gs_unprojection_map_z_, gs_depth_map_;
     std::vector<Scanline> scanlines_;
 };
 
@@ -586,6 +635,76 @@ public:
                 << (unsigned)colour[0] << '\n';
         ply.close();
         std::cout << "Point cloud file " << fileName << " created." << std::endl;
+    }
+    // camera.cc:280-308: the flow field as colours -- hue = direction (degrees), value = magnitude / largest magnitude,
+    // full saturation -- returned as a float BGR image in [0, 1] (main.cc:390-392 scales it by 255 and stores it).
+    // The reference goes through cv::cartToPolar / cv::cvtColor; this is the same colour model in plain arithmetic
+    // (OpenCV's fast arctangent is accurate to 0.3 degrees, so the last grey level may differ).
+    cv::Mat getImageOpticalFlow(cv::Mat_<cv::Point_<double>> flow)
+    {
+        const int rows = flow.rows, cols = flow.cols;
+        cv::Mat bgr(rows, cols, CV_32FC3);
+        float mag_max = 0.f;
+        for (int y = 0; y < rows; ++y)
+            for (int x = 0; x < cols; ++x) {
+                const float fx = (float)flow(y, x).x, fy = (float)flow(y, x).y;
+                mag_max = std::max(mag_max, std::sqrt(fx * fx + fy * fy));
+            }
+        for (int y = 0; y < rows; ++y)
+            for (int x = 0; x < cols; ++x) {
+                const float fx = (float)flow(y, x).x, fy = (float)flow(y, x).y;
+                float hue = std::atan2(fy, fx) * 57.29577951308232f;
+                if (hue < 0.f) hue += 360.f;
+                const float val = mag_max > 0.f ? std::sqrt(fx * fx + fy * fy) / mag_max : 0.f;
+                // HSV -> BGR with S = 1 (cv::COLOR_HSV2BGR on float images: H in [0, 360), S and V in [0, 1])
+                const float h6 = hue / 60.f;
+                const int sector = ((int)std::floor(h6)) % 6;
+                const float f = h6 - std::floor(h6), p = 0.f, q = val * (1.f - f), t = val * f;
+                float r, g, b;
+                switch (sector) {
+                    case 0: r = val; g = t; b = p; break;
+                    case 1: r = q; g = val; b = p; break;
+                    case 2: r = p; g = val; b = t; break;
+                    case 3: r = p; g = q; b = val; break;
+                    case 4: r = t; g = p; b = val; break;
+                    default: r = val; g = p; b = q; break;
+                }
+                bgr.at<cv::Vec3f>(y, x) = cv::Vec3f(b, g, r);
+            }
+        return bgr;
+    }
+    // camera.cc:311-332: every delta-th pixel with a non-zero flow gets a red arrow from the pixel to where the flow
+    // (truncated to whole pixels) takes it.  Drawn with a plain integer line and a two-stroke head; the reference
+    // draws with cv::arrowedLine (anti-aliased), so pixel values along the strokes differ, their geometry does not.
+    cv::Mat flowArrows(const cv::Mat image, const cv::Mat_<cv::Point_<double>> flow, const int delta_x, const int delta_y)
+    {
+        cv::Mat out = image;
+        auto put = [&](int x, int y) { if (x >= 0 && y >= 0 && x < out.cols && y < out.rows) out.at<cv::Vec3b>(y, x) = cv::Vec3b(0, 0, 255); };
+        auto line = [&](int x0, int y0, int x1, int y1) {
+            const int dx = std::abs(x1 - x0), dy = -std::abs(y1 - y0), sx = x0 < x1 ? 1 : -1, sy = y0 < y1 ? 1 : -1;
+            for (int e = dx + dy;;) {
+                put(x0, y0);
+                if (x0 == x1 && y0 == y1) break;
+                const int e2 = 2 * e;
+                if (e2 >= dy) { e += dy; x0 += sx; }
+                if (e2 <= dx) { e += dx; y0 += sy; }
+            }
+        };
+        for (int y = 0; y < image.rows; y += delta_y)
+            for (int x = 0; x < image.cols; x += delta_x) {
+                const double dx = flow(y, x).x, dy = flow(y, x).y;
+                const double l = std::sqrt(dx * dx + dy * dy);
+                if (!(l > 0)) continue;
+                const int x2 = x + (int)dx, y2 = y + (int)dy;
+                line(x, y, x2, y2);
+                // head: two strokes of a tenth of the arrow's length at +-45 degrees from the reversed direction (cv::arrowedLine, tipLength 0.1)
+                const double tip = 0.1 * std::sqrt((double)((x2 - x) * (x2 - x) + (y2 - y) * (y2 - y)));
+                const double ang = std::atan2((double)(y - y2), (double)(x - x2));
+                for (int sgn = -1; sgn <= 1; sgn += 2)
+                    line(x2, y2, (int)std::lround(x2 + tip * std::cos(ang + sgn * 0.7853981633974483)),
+                         (int)std::lround(y2 + tip * std::sin(ang + sgn * 0.7853981633974483)));
+            }
+        return out;
     }
     // camera.cc:99-176: A.csv, the 3 x 3 intrinsic matrix
     bool loadIntrinsicsFromFile(const std::string csv_intrinsic_matrix, bool show_messages)
