@@ -210,6 +210,96 @@ __global__ void __launch_bounds__(kThreads) k_splat_vote(const uint8_t *__restri
     }
 }
 
+// ---- the same vote with everything that does not depend on the pixel taken out of the per-pixel path:
+//   k_splat_tables  per scanline the inverse pose [R^T | -R^T t] (12 doubles) and ny = (y - cy) * 1.0 / fy,
+//                   per column nx = (x - cx) * 1.0 / fx -- the very operations k_splat_vote performs per pixel, once;
+//   k_splat_vote4   one row per CTA row, four consecutive pixels per thread: the frame arrives as three 32-bit
+//                   words, the depths and nx as two 16-byte loads each; two IEEE divisions per pixel are left.
+// Table layout: inv[rows][12] | ny[rows] | (pad to an even count) | nx[cols].
+__global__ void k_splat_tables(const double *__restrict__ R, const double *__restrict__ t, SplatParams P, double *tab)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double *inv = tab, *ny = tab + 12 * (size_t)P.rows, *nx = tab + ((13 * (size_t)P.rows + 1) & ~(size_t)1);
+    if (i < P.rows) {
+        const double *Rs = R + 9 * (size_t)i, *ts = t + 3 * (size_t)i;
+        double Rt[9];
+        for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) Rt[a * 3 + c] = Rs[c * 3 + a];
+        for (int a = 0; a < 9; ++a) inv[12 * (size_t)i + a] = Rt[a];
+        for (int a = 0; a < 3; ++a)
+            inv[12 * (size_t)i + 9 + a] = (-Rt[a * 3 + 0]) * ts[0] + (-Rt[a * 3 + 1]) * ts[1] + (-Rt[a * 3 + 2]) * ts[2];
+        ny[i] = ((double)i - P.cy) * 1.0 / P.fy;
+    }
+    if (i < P.cols) nx[i] = ((double)i - P.cx) * 1.0 / P.fx;
+}
+
+__global__ void __launch_bounds__(kThreads) k_splat_vote4(const uint8_t *__restrict__ image, const double *__restrict__ depth,
+                                                          const double *__restrict__ R, const double *__restrict__ t,
+                                                          const double *__restrict__ tab, SplatParams P, unsigned int *winner,
+                                                          float *coords3d)
+{
+    const int y = blockIdx.y;
+    const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (x0 >= P.cols) return;                                        // (cols is a multiple of 4: whole quads only)
+    const double *inv = tab + 12 * (size_t)(P.gs_mode ? 0 : y);
+    const double ny = tab[12 * (size_t)P.rows + y];
+    const double *nxt = tab + ((13 * (size_t)P.rows + 1) & ~(size_t)1) + x0;
+    double Rt[9], ti[3], R0[9], t0[3];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) { Rt[a] = __ldg(inv + a); R0[a] = __ldg(R + a); }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { ti[a] = __ldg(inv + 9 + a); t0[a] = __ldg(t + a); }
+    const size_t p0 = (size_t)y * P.cols + x0;
+    const uint3 w = *reinterpret_cast<const uint3 *>(image + 3 * p0);                 // 12 bytes = 4 BGR pixels
+    const unsigned int bgr[4] = {w.x & 0xffffffu, (w.x >> 24) | ((w.y & 0xffffu) << 8), (w.y >> 16) | ((w.z & 0xffu) << 16), w.z >> 8};
+    const double2 za = *reinterpret_cast<const double2 *>(depth + p0), zb = *reinterpret_cast<const double2 *>(depth + p0 + 2);
+    const double2 na = *reinterpret_cast<const double2 *>(nxt), nb = *reinterpret_cast<const double2 *>(nxt + 2);
+    const double zs[4] = {za.x, za.y, zb.x, zb.y}, nxs[4] = {na.x, na.y, nb.x, nb.y};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const size_t p = p0 + j;
+        if (coords3d) { coords3d[3 * p] = 0.f; coords3d[3 * p + 1] = 0.f; coords3d[3 * p + 2] = 0.f; }
+        if (bgr[j] == 0x010101u) continue;                                           // rsframe.cc:815
+        const double z = zs[j];
+        const double Pc[3] = {z * nxs[j], z * ny, z * 1.0};
+        double Pw[3], Pg[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            Pw[a] = Rt[a * 3 + 0] * Pc[0] + Rt[a * 3 + 1] * Pc[1] + Rt[a * 3 + 2] * Pc[2] + ti[a] * 1.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)                                                  // scanline 0 pose (:821)
+            Pg[a] = R0[a * 3 + 0] * Pw[0] + R0[a * 3 + 1] * Pw[1] + R0[a * 3 + 2] * Pw[2] + t0[a] * 1.0;
+        const double u = Pg[0] / Pg[2] * P.fx + P.cx;                                // spaceToPlane (:629-642)
+        const double v = Pg[1] / Pg[2] * P.fx + P.cy;                                // y uses f_x too (Q12)
+        if (coords3d) { coords3d[3 * p] = (float)Pw[0]; coords3d[3 * p + 1] = (float)Pw[1]; coords3d[3 * p + 2] = (float)Pw[2]; }
+        int tx, ty;
+        if (!to_int_trunc(u + 0.5, tx) || !to_int_trunc(v + 0.5, ty)) continue;
+        if (tx >= 0 && tx < P.cols && ty >= 0 && ty < P.rows)
+            atomicMax(&winner[(size_t)ty * P.cols + tx], (unsigned int)(p + 1));
+    }
+}
+
+// queues the vote: the quad kernel when the frame allows it (row-major depth, cols % 4 == 0, aligned pointers)
+static int launch_vote(rsdsfm_ctx *ctx, const uint8_t *image, const double *depth, const double *R, const double *t, const SplatParams &P,
+                       unsigned int *winner, float *coords3d)
+{
+    const long long total = (long long)P.rows * P.cols;
+    const bool quads = P.layout != RSDSFM_DEPTH_COLMAJOR && P.cols % 4 == 0 && (reinterpret_cast<uintptr_t>(image) & 3) == 0 &&
+                       (reinterpret_cast<uintptr_t>(depth) & 15) == 0;
+    if (!quads) {
+        k_splat_vote<<<grid_for(ctx, total, 8), kThreads, 0, ctx->stream>>>(image, depth, R, t, P, winner, coords3d);
+        ctx->launches++;
+        return RSDSFM_OK;
+    }
+    RS_TRY(ensure(ctx, ctx->splat_tab, sizeof(double) * (13 * (size_t)P.rows + (size_t)P.cols + 4)));
+    double *tab = (double *)ctx->splat_tab.p;
+    const int nmax = P.rows > P.cols ? P.rows : P.cols;
+    k_splat_tables<<<(nmax + 127) / 128, 128, 0, ctx->stream>>>(R, t, P, tab);
+    const dim3 grid((unsigned)((P.cols / 4 + kThreads - 1) / kThreads), (unsigned)P.rows);
+    k_splat_vote4<<<grid, kThreads, 0, ctx->stream>>>(image, depth, R, t, tab, P, winner, coords3d);
+    ctx->launches += 2;
+    return RSDSFM_OK;
+}
+
 __global__ void __launch_bounds__(kThreads) k_splat_gather(const uint8_t *__restrict__ image,
                                                            const unsigned int *__restrict__ winner, long long total,
                                                            uint8_t *gs)
@@ -374,8 +464,7 @@ int backproject_device(rsdsfm_ctx *ctx, const uint8_t *image, const double *dept
     RS_CUDA(ctx, cudaMemsetAsync(ctx->winner.p, 0, sizeof(unsigned int) * (size_t)total, ctx->stream));
     SplatParams P{K4[0], K4[1], K4[2], K4[3], rows, cols, layout, gs_mode};
     const int grid = grid_for(ctx, total, 8);
-    k_splat_vote<<<grid, kThreads, 0, ctx->stream>>>(image, depth, R, t, P, (unsigned int *)ctx->winner.p, coords3d);
-    ctx->launches++;
+    RS_TRY(launch_vote(ctx, image, depth, R, t, P, (unsigned int *)ctx->winner.p, coords3d));
     k_splat_gather<<<grid, kThreads, 0, ctx->stream>>>(image, (const unsigned int *)ctx->winner.p, total, gs_out);
     ctx->launches++;
     return RSDSFM_OK;
@@ -389,8 +478,7 @@ int backproject_fill_device(rsdsfm_ctx *ctx, const uint8_t *image, const double 
     RS_TRY(ensure(ctx, ctx->winner, sizeof(unsigned int) * (size_t)total));
     RS_CUDA(ctx, cudaMemsetAsync(ctx->winner.p, 0, sizeof(unsigned int) * (size_t)total, ctx->stream));
     SplatParams P{K4[0], K4[1], K4[2], K4[3], rows, cols, layout, gs_mode};
-    k_splat_vote<<<grid_for(ctx, total, 8), kThreads, 0, ctx->stream>>>(image, depth, R, t, P, (unsigned int *)ctx->winner.p, nullptr);
-    ctx->launches++;
+    RS_TRY(launch_vote(ctx, image, depth, R, t, P, (unsigned int *)ctx->winner.p, nullptr));
     const dim3 grid((unsigned)((cols + kFW - 1) / kFW), (unsigned)((rows + kFH - 1) / kFH));
     k_gather_fill<<<grid, kThreads, 0, ctx->stream>>>(image, (const unsigned int *)ctx->winner.p, rows, cols, rectified);
     ctx->launches++;
