@@ -261,7 +261,9 @@ inline std::vector<int32_t> drawSamples(int n, int iterations)
     std::vector<int32_t> samples;
     samples.reserve((size_t)9 * (iterations > 0 ? iterations : 0));
     SubsetDrawer drawer(n);
-    srand((unsigned)time(NULL));
+    // RSDSFM_RANSAC_SEED (environment): a fixed seed instead of the reference's time(NULL), for reproducible runs and tests
+    const char *fixed = getenv("RSDSFM_RANSAC_SEED");
+    srand(fixed ? (unsigned)strtoul(fixed, nullptr, 10) : (unsigned)time(NULL));
     for (int trial = 0; trial < iterations; ++trial) drawer.draw([] { return rand(); }, samples);
     return samples;
 }

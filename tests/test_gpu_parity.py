@@ -288,7 +288,7 @@ def test_cpp_host_shim_single_run(capi):
            "-L", os.path.dirname(capi.LIB_PATH), "-lrsdsfm", "-Wl,-rpath," + os.path.dirname(capi.LIB_PATH), "-o", exe]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, RSDSFM_RANSAC_SEED="7"))
     assert r.returncode == 0, r.stdout + r.stderr
     assert "rectified image" in r.stdout
 
@@ -307,7 +307,7 @@ def test_cpp_sweep_driver_evaluate_velocities(capi, tmp_path):
            "-L", os.path.dirname(capi.LIB_PATH), "-lrsdsfm", "-Wl,-rpath," + os.path.dirname(capi.LIB_PATH), "-o", exe]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=300, env=dict(os.environ, RSDSFM_RANSAC_SEED="7"))
     assert r.returncode == 0, r.stdout + r.stderr
     errs = open(os.path.join(str(tmp_path), "errors.csv")).read().strip().split(",")
     assert errs[0] == "synthetic_pair" and len(errs) == 4 and all(np.isfinite(float(x)) for x in errs[1:])
