@@ -272,7 +272,10 @@ def run_ours(args):
 
     # ---- value: the rank's shard through rsdsfm_refine_rectify_sequence (device buffers, two compute lanes), then the
     # final gather of the per-pair records over NCCL -- all inside the timed region
-    ctx.refine_rectify_sequence([dev_entry(p) for p in warm], CONST_ACC, False, K4, gamma, layout=capi.DEPTH_ROWMAJOR)
+    # (a sequence call creates its compute lanes and sizes their buffers on first use: the warm-up sequences are at
+    # least as long as the lane count, so that nothing is allocated inside a timed region)
+    warm_seq = [warm[i % len(warm)] for i in range(max(len(warm), 8))]
+    ctx.refine_rectify_sequence([dev_entry(p) for p in warm_seq], CONST_ACC, False, K4, gamma, layout=capi.DEPTH_ROWMAJOR)
     barrier()
     l0 = ctx.launch_count()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -292,7 +295,7 @@ def run_ours(args):
     # depths + rectified frame out; copies inside the timed region, overlapped with the compute of the neighbours)
     run_c = lambda ps: ctx.refine_rectify_compact_sequence([p["compact"] for p in ps], CONST_ACC, False, K4, gamma,
                                                            layout=capi.DEPTH_ROWMAJOR, want_depth_map=False)
-    run_c(warm[:max(3, min(W, 3))])
+    run_c(warm_seq)
     shard = [mine[p] for p in range(lo, hi)]
     barrier()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)

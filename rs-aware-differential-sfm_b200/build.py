@@ -52,7 +52,7 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc] + ARCH + COMMON + extra + os.environ.get("RSDSFM_EXTRA_NVCC", "").split() + (os.environ.get("RSDSFM_EXTRA_NVCC_REFINE", "").split() if src == "refine.cu" else []) + ["-Xptxas", "-v"] * int(verbose) + ["-c", s, "-o", o]
+            cmd = [nvcc] + ARCH + COMMON + extra + os.environ.get("RSDSFM_EXTRA_NVCC", "").split() + (os.environ.get("RSDSFM_EXTRA_NVCC_REFINE", "").split() if src in ("refine.cu", "preproc.cu") else []) + ["-Xptxas", "-v"] * int(verbose) + ["-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if verbose or r.returncode != 0:
                 print(" ".join(cmd))

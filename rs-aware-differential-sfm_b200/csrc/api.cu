@@ -79,7 +79,7 @@ void rsdsfm_destroy(rsdsfm_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->lane1) { rsdsfm_destroy(ctx->lane1); ctx->lane1 = nullptr; }
+    for (auto &l : ctx->lanes) if (l) { rsdsfm_destroy(l); l = nullptr; }
     if (ctx->s_in) { cudaStreamSynchronize(ctx->s_in); cudaStreamDestroy(ctx->s_in); }
     if (ctx->s_out) { cudaStreamSynchronize(ctx->s_out); cudaStreamDestroy(ctx->s_out); }
     for (int j = 0; j < 2; ++j) {

@@ -29,6 +29,8 @@ struct DevBuf {
 
 }  // namespace rsdsfm
 
+constexpr int kMaxLanes = 8;
+
 struct rsdsfm_ctx {
     int device = 0;
     int num_sms = rsdsfm::kNumSMsB200;
@@ -57,11 +59,13 @@ struct rsdsfm_ctx {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cdone[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     int io_slot = 0;
-    // Two-lane sequences: the LM solve leaves every SM idle for a third of each iteration (grid barrier +
-    // serial controller).  rsdsfm_refine_rectify_sequence therefore computes even pairs on this context
-    // and odd pairs on `lane1` (a full second context: own stream and buffers), each solve on HALF of the
-    // SMs (lm_grid CTAs); the two solves fill each other's gaps (measured +20 % pairs/s at 1080p).
-    rsdsfm_ctx *lane1 = nullptr;
+    // Multi-lane sequences: the LM solve leaves every SM idle for a quarter of each iteration (grid exchange +
+    // serial controller), and that part does not shrink with the grid.  rsdsfm_refine_rectify_sequence therefore
+    // runs several pairs at once, each on a `lane` (lane 0 = this context, lanes[k-1] = full extra contexts with
+    // their own streams and buffers), each solve on a FRACTION of the SMs (lm_grid CTAs): per LM iteration
+    // 53.8 us on 148 SMs, 86.0 on 74, 156.6 on 37 -- i.e. 53.8 / 43.0 / 39.1 us of whole-GPU time.  More lanes
+    // exist than solves fit on the GPU: a lane that is uploading, downloading or waiting for the host costs no SM.
+    rsdsfm_ctx *lanes[kMaxLanes - 1] = {};
     int lm_grid = 0;             // CTAs of the persistent LM kernel; 0 = one per SM
     void *pinned_io = nullptr;   // 2 x kPinnedSlotBytes, allocated with the context
     // per-kernel profiling (bench.py's roofline): CUDA events around the LM passes

@@ -67,6 +67,7 @@ struct LmShared {
     // device timing (globaltimer ns): [0] INIT total, [1] phases, [2] FUSED total, [3] phases,
     // [4..6] INIT pixel loop / CTA reduce / controller, [7..9] same for FUSED, [10], [11] controller logic only
     unsigned long long t_phase[12];
+    unsigned long long t_abs[2];   // globaltimer at the kernel's first / last instruction of CTA 0 (RSDSFM_TRACE: overlap of solves)
     // ---- grid synchronisation
     unsigned int arrive, generation;
     unsigned int n_exc[4], exc_overflow, pad1;   // exception lists: current / speculative / being cleared
@@ -1095,11 +1096,22 @@ struct RingPos {
 //   this plain order, the sweep is issue-bound; two residual blocks per step; a producer warp.)
 // ------------------------------------------------------------------------------------------
 constexpr int kRefillLag = 5;
+// The residual blocks are dealt to kStrips strips (tile t belongs to strip t % kStrips), every strip is summed by one CTA
+// in tile order into a row of its own, and the rows are combined in strip order: the sums -- and with them the whole
+// solve -- do not depend on the grid.  A full-GPU solve has one strip per CTA; a solve that shares the GPU with others
+// (rsdsfm_refine_rectify_sequence: grid = a fraction of the SMs) walks through several strips per phase, CTA b taking
+// strips b, b + grid, ...  Bit-identical results either way.
+constexpr int kStrips = kNumSMsB200;
 
 template <int NF, bool INIT>
-__device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P, const SweepU &Us, const uint32_t *A_s, int n_my, RingPos &cons, unsigned int &consumed, const double *dx,
+__device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P, const SweepU &Us, const uint32_t *A_s, const int *vs, int strip, int n_my,
+                                      RingPos &cons, unsigned int &consumed, const double *dx,
                                       double *dcand, int elist, double (&acc)[TAcc<NF>::NS], SweepScalars &S)
 {
+    // strip `strip` of this CTA = strip v of the solve (see kStrips): tile uses vs[strip] .. vs[strip + 1] - 1 of this
+    // CTA's n_my per phase, tiles v, v + kStrips, ...
+    const int k0 = vs[strip], k1 = vs[strip + 1];
+    int idx = ((int)blockIdx.x + strip * (int)gridDim.x) * kTile + (int)threadIdx.x;   // this thread's residual block of the step
     constexpr int NFa = NF > 0 ? NF : 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x;
@@ -1119,14 +1131,13 @@ __device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P,
 #endif
     bool ready = false;                    // the early test of this step's full barrier succeeded
 #pragma unroll 1
-    for (int k = 0; k < n_my; ++k) {
-        const int idx = ((int)blockIdx.x + k * G) * kTile + tid;
+    for (int k = k0; k < k1; ++k, idx += kStrips * kTile) {
         const bool inb = idx < D.m;
 #ifdef LM_DBG_WAITCLK
         const long long w0_ = clock64();
 #endif
 #ifdef LM_DBG_NOLOAD
-        if (consumed + (unsigned)k < (unsigned)kStages) mbar_wait_s(full_s + 8u * (uint32_t)rc.s, rc.par);
+        if (consumed + (unsigned)(k - k0) < (unsigned)kStages) mbar_wait_s(full_s + 8u * (uint32_t)rc.s, rc.par);
 #else
         if (!ready) mbar_wait_s(full_s + 8u * (uint32_t)rc.s, rc.par);
 #endif
@@ -1195,7 +1206,12 @@ __device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P,
                 unsigned pd = par_now;
                 if (sd < 0) { sd += kStages; pd ^= 1u; }
                 mbar_wait_s(empty_s + 8u * (uint32_t)sd, pd);     // every warp has released tile kd
-                const int tile = (int)blockIdx.x + (kd + kStages) * G;
+                int tile = (idx - tid) / kTile + (kStages - kRefillLag) * kStrips;   // tile use kd + kStages, if it is in this strip
+                if (kd + kStages >= k1) {                          // no: a later strip of this CTA
+                    int rs = 0;
+                    while (kd + kStages >= vs[rs + 1]) ++rs;
+                    tile = (int)blockIdx.x + rs * G + (kd + kStages - vs[rs]) * kStrips;
+                }
                 const uint32_t st = ring_s + (uint32_t)sd * (uint32_t)sizeof(Stage), fb = full_s + 8u * (uint32_t)sd;
                 mbar_expect_tx_s(fb, (unsigned)sizeof(Stage));
                 bulk_g2s_s(st, D.blk + (size_t)tile * (3 * kTile), (unsigned)(3 * kTile * sizeof(double2)), fb);
@@ -1207,23 +1223,25 @@ __device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P,
     if (!INIT && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77) && consumed > 20u * (unsigned)n_my && consumed < 21u * (unsigned)n_my + 20u)
         printf("cta %d warp %d: sweep %lld cycles, waiting for tiles %lld cycles, %d steps\n", (int)blockIdx.x, tid >> 5, clock64() - dbg_t0, dbg_wait, n_my);
 #endif
-    consumed += (unsigned)n_my;
+    consumed += (unsigned)(k1 - k0);
     cons = rc;
 }
 
 // elected thread: queue the first `pre` tiles of the phase that starts at ring position `at` (= the consumer's
 // position: everything before it has been consumed) and reads `dsrc`; `first_use` = number of the first tile use
 __device__ __noinline__ void queue_phase_head(const RefineData D, const double *dsrc, Stage *stages, uint64_t *full, uint64_t *empty,
-                                              RingPos at, unsigned int first_use, int pre)
+                                              RingPos at, unsigned int first_use, int pre, const int *vs)
 {
     const int G = gridDim.x;
+    int rs = 0;
 #ifdef LM_DBG_NOLOAD
     if (first_use != 0u) return;
 #endif
     fence_proxy_async();          // the ring may have served as scratch (sort keys) since its last tile
     for (int i = 0; i < pre; ++i) {
         if (first_use + (unsigned)i >= (unsigned)kStages) mbar_wait(&empty[at.s], at.par ^ 1u);   // the stage's previous use was released
-        issue_tile(D, dsrc, (int)blockIdx.x + i * G, &stages[at.s], &full[at.s]);
+        while (i >= vs[rs + 1]) ++rs;
+        issue_tile(D, dsrc, (int)blockIdx.x + rs * G + (i - vs[rs]) * kStrips, &stages[at.s], &full[at.s]);
         at.advance();
     }
 }
@@ -1276,7 +1294,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x;
     const int NT = (D.m + kTile - 1) / kTile;
-    const int n_my = ((int)blockIdx.x < NT) ? (NT - 1 - (int)blockIdx.x) / G + 1 : 0;
+    const int n_rows = NT < kStrips ? NT : kStrips;               // strips that have tiles = rows of the exchange
+    const int n_strips = ((int)blockIdx.x < n_rows) ? (n_rows - 1 - (int)blockIdx.x) / G + 1 : 0;   // strips of this CTA
+    __shared__ int s_vs[kStrips + 2];                             // s_vs[i]: tile uses of this CTA (per phase) before its strip i
+    if (tid == 0) {
+        int at = 0;
+        for (int i = 0; i < n_strips; ++i) { s_vs[i] = at; at += (NT - 1 - ((int)blockIdx.x + i * G)) / kStrips + 1; }
+        s_vs[n_strips] = at;
+        s_vs[n_strips + 1] = 0x7fffffff;                          // (stops the searches for a tile use's strip)
+    }
+    __syncthreads();
+    const int n_my = s_vs[n_strips];
     const int pre = n_my < kStages ? n_my : kStages;              // tiles queued ahead of a phase
     unsigned int gen = 0;
     unsigned int xseq = 0;                                        // exchanges with the other GPUs of a row split so far
@@ -1286,6 +1314,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
     // zero = list that thread 0 of CTA 0 clears during this phase (it becomes `spec` of the next phase)
     int slot_cur = 0, slot_spec = 1, slot_zero = 2;
 
+    if (blockIdx.x == 0 && tid == 0) sh->t_abs[0] = globaltimer();
     if (tid == 0) {
         s_addr[0] = smem_u32(stages); s_addr[1] = smem_u32(full); s_addr[2] = smem_u32(empty);
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); }
@@ -1312,7 +1341,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
     __syncthreads();
     if (tid == 32) sweep_uniforms<NF>(&P, &U);
 
-    if (tid == 0 && P.next != LM_DONE) queue_phase_head(D, P.which_x ? d1 : d0, stages, full, empty, cons, consumed, pre);
+    if (tid == 0 && P.next != LM_DONE) queue_phase_head(D, P.which_x ? d1 : d0, stages, full, empty, cons, consumed, pre, s_vs);
     __syncthreads();
 
     for (;;) {
@@ -1323,26 +1352,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
         const unsigned long long t_begin = (blockIdx.x == 0 && tid == 0) ? globaltimer() : 0ull;
         if (blockIdx.x == 0 && tid == 0 && !run_init) sh->n_exc[slot_zero] = 0u;
 
-        double acc[NS];
+        unsigned long long t_loop = 0ull;
+#pragma unroll 1
+        for (int strip = 0; strip < n_strips; ++strip) {
+            double acc[NS];
 #pragma unroll
-        for (int j = 0; j < NS; ++j) acc[j] = 0.0;
-        SweepScalars S;
-        S.gmax = 0ull; S.eemax = 0ull; S.flags = 0u;
-        if (run_init) sweep<NF, true>(A_, P, U, s_addr, n_my, cons, consumed, dx, dcand, slot_cur, acc, S);
-        else          sweep<NF, false>(A_, P, U, s_addr, n_my, cons, consumed, dx, dcand, slot_spec, acc, S);
-        // the candidate depths written above are read by TMA in the next phase: order them for the async proxy
-        asm volatile("fence.proxy.async;" ::: "memory");
-        __syncthreads();
-        const unsigned long long t_loop = t_begin ? globaltimer() : 0ull;
-        double *row = A_.partials + ((size_t)(gen & 1u) * G + blockIdx.x) * RW::NV;
-        cta_reduce_sweep<NS>(acc, S, part, row);
+            for (int j = 0; j < NS; ++j) acc[j] = 0.0;
+            SweepScalars S;
+            S.gmax = 0ull; S.eemax = 0ull; S.flags = 0u;
+            if (run_init) sweep<NF, true>(A_, P, U, s_addr, s_vs, strip, n_my, cons, consumed, dx, dcand, slot_cur, acc, S);
+            else          sweep<NF, false>(A_, P, U, s_addr, s_vs, strip, n_my, cons, consumed, dx, dcand, slot_spec, acc, S);
+            // the candidate depths written above are read by TMA in the next phase: order them for the async proxy
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __syncthreads();
+            if (t_begin) t_loop = globaltimer();                 // (with several strips: the earlier strips' reductions count as loop time)
+            double *row = A_.partials + ((size_t)(gen & 1u) * kStrips + (size_t)((int)blockIdx.x + strip * G)) * RW::NV;
+            cta_reduce_sweep<NS>(acc, S, part, row);
+        }
         // ---- arrive; meanwhile another warp queues the next phase's first tiles (depth: from the buffer an ACCEPTED step makes current)
-        if (tid == 32) queue_phase_head(D, run_init ? dx : dcand, stages, full, empty, cons, consumed, pre);
+        if (tid == 32) queue_phase_head(D, run_init ? dx : dcand, stages, full, empty, cons, consumed, pre, s_vs);
         if (tid == 0) {
             __threadfence();
             atomicAdd(&sh->arrive, 1u);
             if (t_begin) {
                 const unsigned long long t2 = globaltimer();
+                if (t_loop == 0ull) t_loop = t2;                  // (a CTA without strips)
                 atomicAdd(&sh->t_phase[run_init ? 4 : 7], t_loop - t_begin); atomicAdd(&sh->t_phase[run_init ? 5 : 8], t2 - t_loop);
             }
             const unsigned long long t0 = globaltimer();
@@ -1364,14 +1398,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
         }
         const unsigned long long t_ctl = t_begin ? globaltimer() : 0ull;
 
-        // ---- every CTA: combine the G rows in a fixed order (warp w: rows w, w+8, ...; lanes: columns)
+        // ---- every CTA: combine the strips' rows in a fixed order (warp w: rows w, w+8, ...; lanes: columns)
         {
             constexpr int nv = RW::NV, ns2 = 2 * NS;
-            const double *rows = A_.partials + (size_t)(gen & 1u) * G * RW::NV;
+            const double *rows = A_.partials + (size_t)(gen & 1u) * kStrips * RW::NV;
             if (tid < kExcSlots) s_ne[tid] = __ldcg(&sh->n_exc[tid]);
-            constexpr int kRowsPerWarp = (kNumSMsB200 + kWarps - 1) / kWarps;      // 19
+            constexpr int kRowsPerWarp = (kStrips + kWarps - 1) / kWarps;      // 19
             double v[3] = {0.0, 0.0, 0.0};
-            if (G <= kNumSMsB200) {
+            {
                 double t[kRowsPerWarp][3];
 #pragma unroll
                 for (int u = 0; u < kRowsPerWarp; ++u) {
@@ -1379,7 +1413,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         const int j = lane + 32 * c;
-                        t[u][c] = (b < G && j < nv) ? __ldcg(rows + (size_t)b * nv + j) : 0.0;
+                        t[u][c] = (b < n_rows && j < nv) ? __ldcg(rows + (size_t)b * nv + j) : 0.0;
                     }
                 }
 #pragma unroll
@@ -1390,16 +1424,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
                         if (j < ns2) v[c] += t[u][c];
                         else if (j == RW::oFLAGS) v[c] = __longlong_as_double((long long)(dbits(v[c]) | dbits(t[u][c])));
                         else v[c] = __longlong_as_double((long long)umax64(dbits(v[c]), dbits(t[u][c])));
-                    }
-            } else {
-                for (int b = warp; b < G; b += kWarps)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const int j = lane + 32 * c;
-                        const double x = (j < nv) ? __ldcg(rows + (size_t)b * nv + j) : 0.0;
-                        if (j < ns2) v[c] += x;
-                        else if (j == RW::oFLAGS) v[c] = __longlong_as_double((long long)(dbits(v[c]) | dbits(x)));
-                        else v[c] = __longlong_as_double((long long)umax64(dbits(v[c]), dbits(x)));
                     }
             }
 #pragma unroll
@@ -1507,7 +1531,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
         if (P.next != LM_DONE && (!spec_ok || drained)) {
             if (!drained) drain_prefetch(full, empty, &cons, &consumed, pre, true);
             __syncthreads();
-            if (tid == 0) queue_phase_head(D, P.which_x ? d1 : d0, stages, full, empty, cons, consumed, pre);
+            if (tid == 0) queue_phase_head(D, P.which_x ? d1 : d0, stages, full, empty, cons, consumed, pre, s_vs);
         } else if (P.next == LM_DONE && !drained) {
             drain_prefetch(full, empty, &cons, &consumed, pre, false);   // leave no bulk copy in flight when the CTA exits
         }
@@ -1528,15 +1552,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
     // zstats (nullable): per-CTA rows {sum z, max z, max -z} of what was written, for the sign fix
     // and depth range of main.cc:466-489 -- saves the rectification stage a pass over z
     double zs[1] = {0.0}, zm[2] = {-INFINITY, -INFINITY};
-    for (int i = blockIdx.x * kThreads + tid; i < D.m; i += G * kThreads) {
-        double dv;
-        if (failed) dv = A_.z_in ? 1.0 / A_.z_in[(size_t)i * A_.z_stride] : 1.0;
-        else dv = dfin[i];
-        const double o = A_.invert_out ? 1.0 / dv : dv;
-        A_.out[i] = o;
-        zs[0] += o; zm[0] = fmax(zm[0], o); zm[1] = fmax(zm[1], -o);
+    // (four loads in flight per thread: with one, 8 warps per SM leave this pass latency bound at ~0.4 TB/s;
+    // the per-thread order of the sums is that of the plain strided loop)
+    constexpr int kEpi = 4;
+    const int stride = G * kThreads;
+    for (int i0 = blockIdx.x * kThreads + tid; i0 < D.m; i0 += kEpi * stride) {
+        double dv[kEpi];
+#pragma unroll
+        for (int u = 0; u < kEpi; ++u) {
+            const int i = i0 + u * stride;
+            dv[u] = 1.0;
+            if (i < D.m) {
+                if (failed) { if (A_.z_in) dv[u] = __ldg(&A_.z_in[(size_t)i * A_.z_stride]); }
+                else dv[u] = __ldcg(&dfin[i]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kEpi; ++u) {
+            const int i = i0 + u * stride;
+            if (i < D.m) {
+                if (failed && A_.z_in) dv[u] = 1.0 / dv[u];
+                const double o = A_.invert_out ? 1.0 / dv[u] : dv[u];
+                A_.out[i] = o;
+                zs[0] += o; zm[0] = fmax(zm[0], o); zm[1] = fmax(zm[1], -o);
+            }
+        }
     }
     if (A_.zstats) block_reduce_store<1, 2>(zs, zm, A_.zstats);
+    if (blockIdx.x == 0 && tid == 0) sh->t_abs[1] = globaltimer();
 }
 
 }  // namespace rsdsfm

@@ -5,6 +5,7 @@
 //   rsdsfm_pipeline_pair / _sequence main.cc:398-523 (flatten .. crack fill) without leaving the device
 // Everything here composes the stage functions of stages.h; there is no arithmetic in this file
 // apart from the reference's sample draw (minimal.cc:226-244) on the host.
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -207,124 +208,129 @@ static int sequence_core(rsdsfm_ctx *ctx, int mem, std::vector<SeqPair> &pairs, 
     }
     if (max_m == 0) return first_err;
 
-    // Two compute lanes (see common.cuh): pair j runs on lane j&1 = I/O slot j&1.  Lane 1 is a second
-    // context of its own; with both lanes busy each LM solve takes half of the SMs.
-    // Host buffers, expanded interface: the sequence is PCIe-bound and a lane holds its staging slot for the whole
-    // (twice as long) half-GPU compute, which would starve the upload stream -- one lane, full-GPU solves.
-    // (compact interface, host buffers, two lanes: measured 631 vs 761 pairs/s with one lane -- same reason)
-    const bool two_lanes = !host && n_ok >= 2 && ctx->num_sms >= 2 && !getenv("RSDSFM_SINGLE_LANE");
-    if (two_lanes && !ctx->lane1) {
-        if (rsdsfm_create(ctx->device, nullptr, &ctx->lane1) != RSDSFM_OK)
+    // Compute lanes (see common.cuh): every pair runs on one lane, a context of its own whose LM solve takes
+    // 1/active of the SMs.  A pair goes to whichever lane is free first (the iteration counts of the pairs of a
+    // sequence differ by several times: a fixed rotation would leave lanes waiting behind the slowest pair).
+    //   RSDSFM_ACTIVE_LANES  solves that share the SMs   (default 4; 1 = full-GPU solves, I/O still overlapped)
+    //   RSDSFM_LANES         lanes                       (default: active + 2 with device buffers, 2 x active with
+    //                        host buffers, where a lane spends a third of its time in its copies)
+    auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return (e && atoi(e) > 0) ? atoi(e) : dflt; };
+    int active = env_int("RSDSFM_ACTIVE_LANES", 4);
+    if (getenv("RSDSFM_SINGLE_LANE")) active = 1;
+    if (active > ctx->num_sms) active = ctx->num_sms;
+    int n_lanes = env_int("RSDSFM_LANES", host ? (active > 1 ? 2 * active : 2) : (active > 1 ? active + 2 : 1));
+    if (n_lanes > kMaxLanes) n_lanes = kMaxLanes;
+    if (n_lanes > n_ok) n_lanes = n_ok;
+    if (ctx->n_peers > 1) n_lanes = 1;                      // row split: the peers step through the same solves in lockstep
+    if (active > n_lanes) active = n_lanes;
+    rsdsfm_ctx *lane[kMaxLanes] = {ctx};
+    for (int l = 1; l < n_lanes; ++l) {
+        if (!ctx->lanes[l - 1] && rsdsfm_create(ctx->device, nullptr, &ctx->lanes[l - 1]) != RSDSFM_OK)
             return fail(ctx, RSDSFM_ERR_CUDA, rsdsfm_last_error(nullptr));
+        lane[l] = ctx->lanes[l - 1];
     }
-    rsdsfm_ctx *lane[2] = {ctx, two_lanes ? ctx->lane1 : ctx};
-    auto drain_all = [&]() { drain(ctx); if (ctx->lane1) cudaStreamSynchronize(ctx->lane1->stream); };
-    const long long launches1_before = ctx->lane1 ? ctx->lane1->launches : 0;
-    if (two_lanes) {
-        // lane 1 has a stream of its own: whatever the caller queued on the context's stream before this call
-        // (e.g. the kernels that produced the device inputs) must be ordered before lane 1's work too
-        RS_CUDA(ctx, cudaEventRecord(ctx->ev_in[0], ctx->stream));
-        RS_CUDA(ctx, cudaStreamWaitEvent(ctx->lane1->stream, ctx->ev_in[0], 0));
-        ctx->lm_grid = ctx->num_sms / 2; ctx->lane1->lm_grid = ctx->num_sms - ctx->num_sms / 2;
-        ctx->lane1->profile = ctx->profile;
-        ctx->lane1->exc_cap = ctx->exc_cap > ctx->lane1->exc_cap ? ctx->exc_cap : ctx->lane1->exc_cap;
-    }
-    // staging buffer j of I/O slot s (one lane: both slots live in this context; two lanes: slot = lane)
-    auto stg = [&](int s, int j) -> DevBuf & { return two_lanes ? lane[s]->stage[j] : ctx->stage[8 * s + j]; };
-
+    auto drain_all = [&]() { drain(ctx); for (auto *L : ctx->lanes) if (L) drain(L); };
+    long long launches_before[kMaxLanes] = {0};
+    auto restore = [&]() {                                   // lanes back to what single calls expect
+        for (int l = 0; l < n_lanes; ++l) { lane[l]->lm_grid = 0; lane[l]->io_slot = 0; }
+    };
     // size every buffer once, before anything is in flight
     drain_all();
-    int rc0 = lm_reserve(lane[0], max_m);
-    if (rc0 == RSDSFM_OK && two_lanes) rc0 = lm_reserve(lane[1], max_m);
-    for (int s = 0; s < 2 && rc0 == RSDSFM_OK; ++s) {
+    int rc0 = RSDSFM_OK;
+    for (int l = 0; l < n_lanes && rc0 == RSDSFM_OK; ++l) {
+        rsdsfm_ctx *L = lane[l];
+        launches_before[l] = L->launches;
+        L->lm_grid = active > 1 ? ctx->num_sms / active : 0;
+        L->io_slot = 0;
+        if (l > 0) { L->profile = ctx->profile; if (ctx->exc_cap > L->exc_cap) L->exc_cap = ctx->exc_cap; }
+        rc0 = ensure_io(L);
+        if (rc0 == RSDSFM_OK) rc0 = lm_reserve(L, max_m);
         const size_t sz[8] = {max_in[0], max_in[1], max_in[2], max_in[3], max_in[4], sizeof(double) * (size_t)max_m, sizeof(double) * tot, tot * 3};
         for (int j = (host ? 0 : 6); j < (host ? 8 : 7) && rc0 == RSDSFM_OK; ++j)       // device buffers: only the optional depth scratch
-            if (sz[j]) rc0 = ensure(lane[s], stg(s, j), sz[j]);
+            if (sz[j]) rc0 = ensure(L, L->stage[j], sz[j]);
         if (rc0 == RSDSFM_OK && C.compact) {
-            rc0 = ensure(lane[s], lane[s]->pipe[14], sizeof(double) * (size_t)max_m);
-            if (rc0 == RSDSFM_OK) rc0 = ensure(lane[s], lane[s]->pipe[15], sizeof(double) * 2 * (size_t)max_m);
+            rc0 = ensure(L, L->pipe[14], sizeof(double) * (size_t)max_m);
+            if (rc0 == RSDSFM_OK) rc0 = ensure(L, L->pipe[15], sizeof(double) * 2 * (size_t)max_m);
         }
+        if (rc0 != RSDSFM_OK && L != ctx) ctx->err = L->err;
     }
-    if (rc0 != RSDSFM_OK) {
-        if (two_lanes) { ctx->lm_grid = 0; ctx->lane1->lm_grid = 0; if (lane[1]->err.size()) ctx->err = lane[1]->err; }
-        return rc0;
-    }
+    if (rc0 != RSDSFM_OK) { restore(); return rc0; }
+    // the lanes have streams of their own: whatever the caller queued on the context's stream before this call
+    // (e.g. the kernels that produced the device inputs) must be ordered before their work too
+    RS_CUDA(ctx, cudaEventRecord(ctx->ev_in[1], ctx->stream));
+    for (int l = 1; l < n_lanes; ++l) RS_CUDA(ctx, cudaStreamWaitEvent(lane[l]->stream, ctx->ev_in[1], 0));
+    if (host) RS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_in[1], 0));
 
-    // In flight at any time: upload of pair i (s_in), compute of pairs <= i (one stream per lane, in order
-    // within a lane), download of pairs < i (s_out).  The upload of pair i starts as soon as the compute of
-    // pair i-2 has released the slot's staging buffers (stream-side wait, the host does not block for it);
-    // pair i-2 is finished (results parsed on the host) before the compute of pair i is queued, because that
-    // compute overwrites the slot's read-back area.
-    int submitted[2] = {-1, -1};                 // pair occupying each slot, not yet finished
-    bool retried = false;
-    auto finish = [&](int slot) -> int {
-        const int j = submitted[slot];
+    // A lane's life: upload (ctx->s_in, all uploads in pair order) -> compute (the lane's stream) -> download (the
+    // lane's own s_out, so that a short pair's results do not queue behind a long pair's) -> parsed by the host.
+    // The host only ever waits for "some lane has finished".
+    int occupant[kMaxLanes];                     // pair on each lane, not yet finished
+    for (int l = 0; l < kMaxLanes; ++l) occupant[l] = -1;
+    auto finish = [&](int l) -> int {
+        const int j = occupant[l];
         if (j < 0) return RSDSFM_OK;
-        submitted[slot] = -1;
+        occupant[l] = -1;
         SeqPair &p = pairs[j];
-        rsdsfm_ctx *L = lane[slot];
-        RS_CUDA(ctx, cudaEventSynchronize(ctx->ev_out[slot]));
-        L->io_slot = two_lanes ? 0 : slot;
+        rsdsfm_ctx *L = lane[l];
+        RS_CUDA(ctx, cudaEventSynchronize(L->ev_out[0]));
         bool overflow = false;
         int rc = finish_step(L, nf, p.m, p.v, p.w, p.k, p.summary, &overflow);
         if (rc == RSDSFM_OK && overflow) {
-            // Exception list too small for this pair (it has been enlarged): let everything in
-            // flight complete, keep the other slot's read-backs, and redo this pair synchronously.
+            // Exception list too small for this pair (it has been enlarged): let everything in flight complete
+            // (the other lanes' read-backs stay where they are) and redo this pair synchronously on its lane.
             drain_all();
-            rc = step_sync(L, mem, two_lanes ? 0 : slot, C, p);
-            retried = true;                       // the slot's staging buffers were reused
+            rc = step_sync(L, mem, 0, C, p);
         }
         if (rc != RSDSFM_OK && L != ctx) ctx->err = L->err;
         *p.status = rc;
         return rc;
     };
-    auto upload = [&](const SeqPair &p, int s) -> int {
-        for (int j = 0; j < 5; ++j)
-            if (p.in[j] && p.in_bytes[j])
-                RS_CUDA(ctx, cudaMemcpyAsync(stg(s, j).p, p.in[j], p.in_bytes[j], cudaMemcpyHostToDevice, ctx->s_in));
-        RS_CUDA(ctx, cudaEventRecord(ctx->ev_in[s], ctx->s_in));
-        return RSDSFM_OK;
+    auto free_lane = [&]() -> int {              // a lane without occupant; else the first lane whose pair is complete
+        for (int l = 0; l < n_lanes; ++l) if (occupant[l] < 0) return l;
+        for (unsigned spin = 0;; ++spin) {
+            for (int l = 0; l < n_lanes; ++l) {
+                const cudaError_t q = cudaEventQuery(lane[l]->ev_out[0]);
+                if (q != cudaErrorNotReady) return l;          // complete (or failed: finish() reports it)
+            }
+            if ((spin & 63u) == 63u) std::this_thread::yield();
+        }
     };
 
     for (int i = 0; i < n_pairs; ++i) {
         SeqPair &p = pairs[i];
         if (*p.status != RSDSFM_OK) continue;
-        const int s = i & 1;
-        rsdsfm_ctx *L = lane[s];
+        const int l = free_lane();
+        rsdsfm_ctx *L = lane[l];
         const size_t mm = (size_t)p.m;
+        const int frc = finish(l);                // the lane's previous pair (complete, or about to be)
+        if (frc != RSDSFM_OK && first_err == RSDSFM_OK) first_err = frc;
         int rc = [&]() -> int {
-            if (host) {
-                // the slot's input staging was last read by the compute of its previous occupant
-                if (submitted[s] >= 0) RS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_cdone[s], 0));
-                RS_TRY(upload(p, s));
-            }
-            retried = false;
-            const int frc = finish(s);            // the previous occupant: blocks until its download is complete
-            if (frc != RSDSFM_OK && first_err == RSDSFM_OK) first_err = frc;
             const void *in[5] = {p.in[0], p.in[1], p.in[2], p.in[3], p.in[4]};
             double *z = p.z_out, *dm = p.depth_map;
             uint8_t *rect = p.rectified;
             if (host) {
-                if (retried) RS_TRY(upload(p, s));
-                RS_CUDA(ctx, cudaStreamWaitEvent(L->stream, ctx->ev_in[s], 0));
-                for (int j = 0; j < 5; ++j) in[j] = stg(s, j).p;
-                z = (double *)stg(s, 5).p; dm = (double *)stg(s, 6).p; rect = (uint8_t *)stg(s, 7).p;
+                for (int j = 0; j < 5; ++j)
+                    if (p.in[j] && p.in_bytes[j])
+                        RS_CUDA(ctx, cudaMemcpyAsync(L->stage[j].p, p.in[j], p.in_bytes[j], cudaMemcpyHostToDevice, ctx->s_in));
+                RS_CUDA(ctx, cudaEventRecord(L->ev_in[0], ctx->s_in));
+                RS_CUDA(ctx, cudaStreamWaitEvent(L->stream, L->ev_in[0], 0));
+                for (int j = 0; j < 5; ++j) in[j] = L->stage[j].p;
+                z = (double *)L->stage[5].p; dm = (double *)L->stage[6].p; rect = (uint8_t *)L->stage[7].p;
             } else if (!dm) {
-                dm = (double *)stg(s, 6).p;       // nobody wants the depth map, but the splat reads it
+                dm = (double *)L->stage[6].p;     // nobody wants the depth map, but the splat reads it
             }
             const StepArgs a = step_args(C, p, in, z, dm, rect);
-            L->io_slot = two_lanes ? 0 : s;
             const int qrc = queue_step(L, a, p.v, p.w, *p.k);
             if (qrc != RSDSFM_OK) { if (L != ctx) ctx->err = L->err; return qrc; }
-            RS_CUDA(ctx, cudaEventRecord(ctx->ev_cdone[s], L->stream));
-            RS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_cdone[s], 0));
+            RS_CUDA(ctx, cudaEventRecord(L->ev_cdone[0], L->stream));
+            RS_CUDA(ctx, cudaStreamWaitEvent(L->s_out, L->ev_cdone[0], 0));
             if (host) {
-                RS_CUDA(ctx, cudaMemcpyAsync(p.z_out, a.z, sizeof(double) * mm, cudaMemcpyDeviceToHost, ctx->s_out));
+                RS_CUDA(ctx, cudaMemcpyAsync(p.z_out, a.z, sizeof(double) * mm, cudaMemcpyDeviceToHost, L->s_out));
                 if (p.depth_map)
-                    RS_CUDA(ctx, cudaMemcpyAsync(p.depth_map, a.depth_map, sizeof(double) * tot, cudaMemcpyDeviceToHost, ctx->s_out));
-                RS_CUDA(ctx, cudaMemcpyAsync(p.rectified, a.rectified, tot * 3, cudaMemcpyDeviceToHost, ctx->s_out));
+                    RS_CUDA(ctx, cudaMemcpyAsync(p.depth_map, a.depth_map, sizeof(double) * tot, cudaMemcpyDeviceToHost, L->s_out));
+                RS_CUDA(ctx, cudaMemcpyAsync(p.rectified, a.rectified, tot * 3, cudaMemcpyDeviceToHost, L->s_out));
             }
-            RS_CUDA(ctx, cudaEventRecord(ctx->ev_out[s], ctx->s_out));
+            RS_CUDA(ctx, cudaEventRecord(L->ev_out[0], L->s_out));
             return RSDSFM_OK;
         }();
         if (rc != RSDSFM_OK) {
@@ -333,25 +339,21 @@ static int sequence_core(rsdsfm_ctx *ctx, int mem, std::vector<SeqPair> &pairs, 
             if (first_err == RSDSFM_OK) first_err = rc;
             continue;
         }
-        submitted[s] = i;
+        occupant[l] = i;
     }
-    // finish in submission order (older pair first)
-    int order[2] = {0, 1};
-    if (submitted[0] >= 0 && submitted[1] >= 0 && submitted[1] < submitted[0]) { order[0] = 1; order[1] = 0; }
-    for (int q = 0; q < 2; ++q) {
-        int rc = finish(order[q]);
+    for (int l = 0; l < n_lanes; ++l) {
+        const int rc = finish(l);
         if (rc != RSDSFM_OK && first_err == RSDSFM_OK) first_err = rc;
     }
     drain_all();
-    ctx->io_slot = 0;
-    if (two_lanes) {
-        rsdsfm_ctx *L1 = ctx->lane1;
-        ctx->lm_grid = 0; L1->lm_grid = 0; L1->io_slot = 0;
-        ctx->launches += L1->launches - launches1_before;
-        if (ctx->profile) {                       // lane 1's timers join the caller-visible ones
-            for (int j = 0; j < 8; ++j) { ctx->prof[j] += L1->prof[j]; ctx->prof_detail[j] += L1->prof_detail[j]; L1->prof[j] = 0.0; L1->prof_detail[j] = 0.0; }
+    restore();
+    for (int l = 1; l < n_lanes; ++l) {
+        rsdsfm_ctx *L = lane[l];
+        ctx->launches += L->launches - launches_before[l];
+        if (ctx->profile) {                       // the lanes' timers join the caller-visible ones
+            for (int j = 0; j < 8; ++j) { ctx->prof[j] += L->prof[j]; ctx->prof_detail[j] += L->prof_detail[j]; L->prof[j] = 0.0; L->prof_detail[j] = 0.0; }
         }
-        if (L1->exc_cap > ctx->exc_cap) ctx->exc_cap = L1->exc_cap;
+        if (L->exc_cap > ctx->exc_cap) ctx->exc_cap = L->exc_cap;
     }
     return first_err;
 }

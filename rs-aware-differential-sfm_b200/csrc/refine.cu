@@ -122,7 +122,12 @@ __global__ void __launch_bounds__(256) k_lm_readback(const LmShared *sh, const d
     if (stats8 && threadIdx.x < 8) host_stats8[threadIdx.x] = stats8[threadIdx.x];
 }
 
-int lm_grid_size(const rsdsfm_ctx *ctx) { return (ctx->lm_grid > 0 && ctx->lm_grid < ctx->num_sms) ? ctx->lm_grid : ctx->num_sms; }
+int lm_grid_size(const rsdsfm_ctx *ctx)
+{
+    static const int forced = getenv("RSDSFM_LM_GRID") ? atoi(getenv("RSDSFM_LM_GRID")) : 0;      // experiments (tools/lm_bench.py)
+    const int g = forced > 0 ? forced : ctx->lm_grid;
+    return (g > 0 && g < ctx->num_sms) ? g : ctx->num_sms;
+}
 
 // Initial capacity (entries) of each clamped-pixel list; an overflow is detected by the kernel and the
 // solve is repeated with room for every residual block.  RSDSFM_EXC_CAP overrides the default so that
@@ -144,7 +149,7 @@ static int lm_solve_async(rsdsfm_ctx *ctx, const RefineData &D, double *d0, doub
     LmShared *sh = (LmShared *)ctx->lm_shared.p;
     const int grid = lm_grid_size(ctx);                 // one persistent CTA per SM (half of them in a two-lane sequence)
     const int nv = (nf == 0) ? Row<0>::NV : (nf == 6 ? Row<6>::NV : Row<7>::NV);
-    RS_TRY(ensure(ctx, ctx->partials, sizeof(double) * 2 * (size_t)grid * nv));   // rows of even / odd phases
+    RS_TRY(ensure(ctx, ctx->partials, sizeof(double) * 2 * (size_t)kStrips * nv));   // rows (one per strip) of even / odd phases
     if (ctx->exc_cap < min_exc_cap()) ctx->exc_cap = min_exc_cap();
     // (row split: a member cannot repeat its solve alone when its list overflows, so the lists start larger)
     if (ctx->n_peers > 1 && ctx->exc_cap < D.m / 16 + 4096) ctx->exc_cap = D.m / 16 + 4096;
@@ -200,6 +205,8 @@ int lm_collect_finish(rsdsfm_ctx *ctx, int nf, int m, Motion *mot, rsdsfm_lm_sum
         return fail(ctx, RSDSFM_ERR_ARG, "compact input: n / m do not match the flow field and the consensus mask");
     *overflow = h->exc_overflow != 0;
     if (*overflow) { if (ctx->exc_cap < m + 1024) ctx->exc_cap = m + 1024; return RSDSFM_OK; }
+    if (getenv("RSDSFM_TRACE"))
+        fprintf(stderr, "[rsdsfm trace] ctx %p solve m=%d it=%d t0=%llu t1=%llu (%.1f us)\n", (void *)ctx, m, h->ctl.iteration, h->t_abs[0], h->t_abs[1], (double)(h->t_abs[1] - h->t_abs[0]) * 1e-3);
     float kms = 0.f;
     if (ctx->profile) cudaEventElapsedTime(&kms, ctx->pe0[ctx->io_slot], ctx->pe1[ctx->io_slot]);
     if (summary) {
@@ -251,7 +258,7 @@ static int ensure_lm_buffers(rsdsfm_ctx *ctx, size_t mm)
 int lm_reserve(rsdsfm_ctx *ctx, int m)
 {
     RS_TRY(ensure_lm_buffers(ctx, (size_t)(m > 0 ? m : 1)));
-    RS_TRY(ensure(ctx, ctx->partials, sizeof(double) * 2 * (size_t)ctx->num_sms * Row<7>::NV));
+    RS_TRY(ensure(ctx, ctx->partials, sizeof(double) * 2 * (size_t)kStrips * Row<7>::NV));
     if (ctx->exc_cap < min_exc_cap()) ctx->exc_cap = min_exc_cap();
     return ensure(ctx, ctx->exc, sizeof(ExcEntry) * kExcSlots * (size_t)ctx->exc_cap);
 }

@@ -1,7 +1,7 @@
 """Parity of the CUDA path with the CPU oracle on the configurations bench.py times and DESIGN.md
 quotes: the exact bench pairs (1080p, seeds 1000.., k = 0.5,
 constant-acceleration model, H = 16) through (i) one synchronous rsdsfm_refine_rectify call and
-(ii) the two-lane device sequence; and one 3840x2160 pair (BASELINE config 4).
+(ii) the multi-lane device sequence; and one 3840x2160 pair (BASELINE config 4).
 
 Tolerances are BASELINE.json's: motion 1e-6 relative, depth 1e-4 relative at the median and 1e-3 at
 p99, rectified 8-bit image within 1 grey level on >= 99.9 % of the pixels; LM iteration counts and
@@ -73,8 +73,9 @@ def test_bench_pair_single_call_matches_oracle(ctx, capi, bench_pairs):
 
 
 def test_bench_pairs_two_lane_device_sequence_matches_oracle(ctx, capi, bench_pairs):
-    """The `value` path of bench.py: rsdsfm_refine_rectify_sequence with device buffers (two compute lanes, each LM
-    solve on half of the SMs) over the three bench pairs, twice over -- every pair against the oracle."""
+    """The `value` path of bench.py: rsdsfm_refine_rectify_sequence with device buffers (several compute lanes, each LM
+    solve on a fraction of the SMs) over the three bench pairs, twice over -- every pair against the oracle, and
+    against the single call (the solver's sums do not depend on the grid)."""
     pairs, refs = bench_pairs
     ent = [dict(flow=d["flow"], inliers3=d["inliers3"], alpha=d["alpha"], alpha_k=d["alpha_k"], image=d["image"], m=d["m"],
                 v=d["v"], w=d["w"], k=d["k"]) for d in pairs + pairs]
@@ -83,9 +84,15 @@ def test_bench_pairs_two_lane_device_sequence_matches_oracle(ctx, capi, bench_pa
     for i, r in enumerate(res):
         assert r["status"] == 0
         _check(_host(r), refs[i % 3], "sequence pair %d" % i)
-    # the two occurrences of a pair ran on different lanes (74 / 74 SMs): same arithmetic, same reduction shape
+    # the two occurrences of a pair ran on different lanes
     for i in range(3):
         assert np.array_equal(res[i]["rectified"].cpu().numpy(), res[i + 3]["rectified"].cpu().numpy())
+    d = pairs[0]
+    one = ctx.refine_rectify(d["flow"], d["inliers3"], d["alpha"], d["alpha_k"], d["m"], d["v"], d["w"], d["k"], True, False,
+                             d["image"], d["K4"], d["gamma"])
+    assert np.array_equal(one["v"], res[0]["v"]) and np.array_equal(one["w"], res[0]["w"]) and one["k"] == res[0]["k"]
+    assert np.array_equal(one["z"].cpu().numpy(), res[0]["z"].cpu().numpy())
+    assert np.array_equal(one["rectified"].cpu().numpy(), res[0]["rectified"].cpu().numpy())
 
 
 def test_4k_pair_matches_oracle(ctx, capi, synth, oracle):

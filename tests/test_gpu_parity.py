@@ -346,19 +346,16 @@ def test_refine_rectify_sequence_equals_single_calls(ctx, oracle, synth, mem, co
     seq = ctx.refine_rectify_sequence(pairs, const_acc, False, cases[0]["K4"], cases[0]["gamma"])
     assert len(seq) == len(single)
     host = (lambda a: a.cpu().numpy()) if mem == "device" else (lambda a: a)
-    # the two-lane sequence reduces over half as many CTA rows as a single call: same arithmetic, another
-    # (fixed) summation order, so the results agree to rounding, not to the bit ...
+    # a sequence runs several pairs at once, each LM solve on a fraction of the SMs; the solver's sums are taken
+    # over fixed strips of residual blocks whatever the grid (lm_kernel.cuh kStrips): identical to the bit
     for s, r in zip(seq, single):
         assert s["status"] == 0
-        assert np.abs(s["v"] - r["v"]).max() <= 1e-10 * np.abs(r["v"]).max() and np.abs(s["w"] - r["w"]).max() <= 1e-10 * np.abs(r["w"]).max()
-        assert abs(s["k"] - r["k"]) <= 1e-10 * max(1.0, abs(r["k"]))
+        assert np.array_equal(s["v"], r["v"]) and np.array_equal(s["w"], r["w"]) and s["k"] == r["k"]
         assert s["summary"]["iterations"] == r["summary"]["iterations"]
-        assert abs(s["summary"]["final_cost"] - r["summary"]["final_cost"]) <= 1e-10 * r["summary"]["final_cost"]
-        rel = helpers.rel_err(host(s["z"]), host(r["z"]))
-        assert np.median(rel) < 1e-9 and np.percentile(rel, 99) < 1e-6
-        assert np.array_equal(host(s["depth_map"]) != 0, host(r["depth_map"]) != 0)
-        assert (host(s["rectified"]) != host(r["rectified"])).mean() < 1e-3
-    # ... while the sequence itself is reproducible to the bit, and a one-pair sequence IS the single call
+        assert s["summary"]["final_cost"] == r["summary"]["final_cost"]
+        for key in ("z", "depth_map", "rectified"):
+            assert np.array_equal(host(s[key]), host(r[key])), key
+    # ... the sequence is reproducible, and a one-pair sequence IS the single call
     again = ctx.refine_rectify_sequence(pairs, const_acc, False, cases[0]["K4"], cases[0]["gamma"])
     for s, t in zip(seq, again):
         assert np.array_equal(s["v"], t["v"]) and np.array_equal(s["w"], t["w"]) and s["k"] == t["k"]
@@ -367,6 +364,26 @@ def test_refine_rectify_sequence_equals_single_calls(ctx, oracle, synth, mem, co
     one = ctx.refine_rectify_sequence(pairs[:1], const_acc, False, cases[0]["K4"], cases[0]["gamma"])[0]
     assert np.array_equal(one["v"], single[0]["v"]) and np.array_equal(host(one["z"]), host(single[0]["z"]))
     assert np.array_equal(host(one["rectified"]), host(single[0]["rectified"]))
+
+
+def test_lm_solve_does_not_depend_on_the_grid(capi):
+    """The persistent LM kernel on 148, 74, 37 and 5 CTAs (RSDSFM_LM_GRID, read once per process: one process each):
+    the refined motion, the cost and the depths come out identical to the bit."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for grid in ("148", "74", "37", "5"):
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "lm_bench.py"), "--reps", "1", "--rows", "270", "--cols", "480"],
+                           capture_output=True, text=True, timeout=300, env=dict(os.environ, RSDSFM_LM_GRID=grid))
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    for o in outs[1:]:
+        for key in ("iterations", "termination", "reason", "final_cost", "v", "w", "k", "z_sum"):
+            assert o[key] == outs[0][key], (key, o[key], outs[0][key])
+    assert outs[0]["iterations"] >= 5
 
 
 def test_refine_rectify_sequence_bad_pair_is_reported(ctx, oracle, synth):
@@ -958,17 +975,13 @@ def test_compact_sequence_equals_expanded_calls(ctx, oracle, synth, mem, f32):
         assert np.array_equal(got["v"], ref["v"]) and np.array_equal(got["w"], ref["w"]) and got["k"] == ref["k"]
         assert np.array_equal(host(got["z"]), ref["z"])
         assert np.array_equal(host(got["depth_map"]), ref["depth_map"]) and np.array_equal(host(got["rectified"]), ref["rectified"])
-    # pipelined (host: one lane -> still bit-identical; device: two lanes -> to rounding), depth map not requested
+    # pipelined over the compute lanes (bit-identical whatever the lane's share of the SMs), depth map not requested
     res = ctx.refine_rectify_compact_sequence(pairs, True, False, K4, 0.95, want_depth_map=False)
     for got, ref in zip(res, refs):
         assert got["status"] == 0 and got["depth_map"] is None
         assert got["summary"]["iterations"] == ref["summary"]["iterations"]
-        _motion_close(got["v"], ref["v"], "v"); _motion_close(got["w"], ref["w"], "w")
-        _depth_close(host(got["z"]), ref["z"])
-        diff = np.abs(host(got["rectified"]).astype(np.int32) - ref["rectified"].astype(np.int32)).max(axis=2)
-        assert (diff <= 1).mean() >= 0.999
-        if mem == "host":
-            assert np.array_equal(host(got["rectified"]), ref["rectified"]) and np.array_equal(host(got["z"]), ref["z"])
+        assert np.array_equal(got["v"], ref["v"]) and np.array_equal(got["w"], ref["w"]) and got["k"] == ref["k"]
+        assert np.array_equal(host(got["rectified"]), ref["rectified"]) and np.array_equal(host(got["z"]), ref["z"])
 
 
 def test_compact_sequence_rejects_wrong_counts(capi, ctx, oracle, case_cv):

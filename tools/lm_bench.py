@@ -46,4 +46,6 @@ out = dict(variant=os.environ.get("RSDSFM_LM_VARIANT", "default"), m=m, iteratio
            iter_phase_us=1e3 * prof["pass_b_ms"] / nb, loop_us=1e3 * prof["b_loop_ms"] / nb, reduce_us=1e3 * prof["b_reduce_ms"] / nb,
            ctl_us=1e3 * prof["b_ctl_ms"] / nb, logic_us=1e3 * prof["b_logic_ms"] / nb,
            init_phase_us=1e3 * prof["pass_a_ms"] / max(prof["pass_a_launches"], 1), init_loop_us=1e3 * prof["a_loop_ms"] / max(prof["pass_a_launches"], 1))
+out["phases_per_solve"] = nb / nk
+out["outside_phases_us"] = 1e3 * (prof["kernel_ms"] - prof["pass_b_ms"] - prof["pass_a_ms"]) / nk
 print(json.dumps(out))
