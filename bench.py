@@ -270,11 +270,11 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
 
-    # ---- value: the rank's shard through rsdsfm_refine_rectify_sequence (device buffers, two compute lanes), then the
+    # ---- value: the rank's shard through rsdsfm_refine_rectify_sequence (device buffers; four LM solves share the SMs, see pipeline.cu), then the
     # final gather of the per-pair records over NCCL -- all inside the timed region
     # (a sequence call creates its compute lanes and sizes their buffers on first use: the warm-up sequences are at
-    # least as long as the lane count, so that nothing is allocated inside a timed region)
-    warm_seq = [warm[i % len(warm)] for i in range(max(len(warm), 8))]
+    # least as long as a sequence that gets every lane (>= 12 pairs), so that nothing is allocated inside a timed region)
+    warm_seq = [warm[i % len(warm)] for i in range(max(len(warm), 16))]
     ctx.refine_rectify_sequence([dev_entry(p) for p in warm_seq], CONST_ACC, False, K4, gamma, layout=capi.DEPTH_ROWMAJOR)
     barrier()
     l0 = ctx.launch_count()
@@ -311,7 +311,7 @@ def run_ours(args):
     d2h = c0["out"][0].nbytes + c0["out"][2].nbytes
 
     # ---- one synchronous rsdsfm_refine_rectify call per pair (no overlap between pairs): where the dominant kernel
-    # runs ALONE on the whole GPU and is timed for the roofline (in a sequence two solves share the SMs)
+    # runs ALONE on the whole GPU and is timed for the roofline (in a sequence four solves share the SMs)
     for p in warm[:3]:
         step_device(ctx, capi, p)
     ctx.profile_enable(True)
@@ -384,8 +384,9 @@ def run_ours(args):
                     "api": "rsdsfm_refine_rectify_compact_sequence, pinned host buffers: the float32 flow field, the frame and "
                            "RANSAC's outputs (consensus mask, winner inverse depths) go up, coordinates / alpha factors / pairing "
                            "are rebuilt on the device; depths and the rectified frame come back (the depth raster stays on the "
-                           "device); the upload of pair i+1 and the download of pair i-1 overlap the compute of pair i"},
-            "api": "rsdsfm_refine_rectify_sequence over the rank's shard, device buffers (two solves share the SMs: even / odd pairs), "
+                           "device); up to 8 pairs in flight on compute lanes of their own (four LM solves share the SMs): uploads, solves and "
+                           "downloads of different pairs overlap"},
+            "api": "rsdsfm_refine_rectify_sequence over the rank's shard, device buffers (compute lanes: four LM solves share the SMs, a pair goes to the lane that is free first; results are bit-identical to single calls), "
                    "+ sequence.gather_records",
             "single_call_ms_per_step": ms_single / max(K, 1),
             "gpu_launches": int(launches),
@@ -502,8 +503,8 @@ def emit(line):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)

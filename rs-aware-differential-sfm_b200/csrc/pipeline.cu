@@ -5,6 +5,7 @@
 //   rsdsfm_pipeline_pair / _sequence main.cc:398-523 (flatten .. crack fill) without leaving the device
 // Everything here composes the stage functions of stages.h; there is no arithmetic in this file
 // apart from the reference's sample draw (minimal.cc:226-244) on the host.
+#include <chrono>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -207,15 +208,28 @@ static int sequence_core(rsdsfm_ctx *ctx, int mem, std::vector<SeqPair> &pairs, 
             first_err = fail(ctx, RSDSFM_ERR_ARG, "refine_rectify sequence: bad pair argument");
     }
     if (max_m == 0) return first_err;
+    // Buffers are sized for the frame, not for this call's pairs (m <= n <= rows * cols): a later sequence with a few
+    // more inliers must not reallocate -- cudaFree / cudaMalloc of the lanes' buffers costs tens of milliseconds.
+    if ((size_t)max_m < tot) max_m = (int)tot;
+    {
+        const size_t bound_c[5] = {0, tot, sizeof(double) * tot, 0, tot * 3};
+        const size_t bound_x[5] = {sizeof(double) * 2 * tot, sizeof(double) * 3 * tot, sizeof(double) * tot, sizeof(double) * tot, tot * 3};
+        for (int j = 0; j < 5; ++j) {
+            const size_t bnd = C.compact ? bound_c[j] : bound_x[j];
+            if (max_in[j] && max_in[j] < bnd) max_in[j] = bnd;
+        }
+    }
 
     // Compute lanes (see common.cuh): every pair runs on one lane, a context of its own whose LM solve takes
     // 1/active of the SMs.  A pair goes to whichever lane is free first (the iteration counts of the pairs of a
     // sequence differ by several times: a fixed rotation would leave lanes waiting behind the slowest pair).
-    //   RSDSFM_ACTIVE_LANES  solves that share the SMs   (default 4; 1 = full-GPU solves, I/O still overlapped)
+    //   RSDSFM_ACTIVE_LANES  solves that share the SMs   (default 4, 2 for sequences of fewer than 12 pairs -- the last
+    //                        solves of a sequence run with idle SMs beside them, the longer the more lanes there are;
+    //                        1 = full-GPU solves, I/O still overlapped)
     //   RSDSFM_LANES         lanes                       (default: active + 2 with device buffers, 2 x active with
     //                        host buffers, where a lane spends a third of its time in its copies)
     auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return (e && atoi(e) > 0) ? atoi(e) : dflt; };
-    int active = env_int("RSDSFM_ACTIVE_LANES", 4);
+    int active = env_int("RSDSFM_ACTIVE_LANES", n_ok >= 12 ? 4 : 2);
     if (getenv("RSDSFM_SINGLE_LANE")) active = 1;
     if (active > ctx->num_sms) active = ctx->num_sms;
     int n_lanes = env_int("RSDSFM_LANES", host ? (active > 1 ? 2 * active : 2) : (active > 1 ? active + 2 : 1));
@@ -235,6 +249,8 @@ static int sequence_core(rsdsfm_ctx *ctx, int mem, std::vector<SeqPair> &pairs, 
         for (int l = 0; l < n_lanes; ++l) { lane[l]->lm_grid = 0; lane[l]->io_slot = 0; }
     };
     // size every buffer once, before anything is in flight
+    const bool trace = getenv("RSDSFM_TRACE") != nullptr;
+    const auto tc0 = std::chrono::steady_clock::now();
     drain_all();
     int rc0 = RSDSFM_OK;
     for (int l = 0; l < n_lanes && rc0 == RSDSFM_OK; ++l) {
@@ -296,6 +312,7 @@ static int sequence_core(rsdsfm_ctx *ctx, int mem, std::vector<SeqPair> &pairs, 
         }
     };
 
+    const auto tc1 = std::chrono::steady_clock::now();
     for (int i = 0; i < n_pairs; ++i) {
         SeqPair &p = pairs[i];
         if (*p.status != RSDSFM_OK) continue;
@@ -346,6 +363,11 @@ static int sequence_core(rsdsfm_ctx *ctx, int mem, std::vector<SeqPair> &pairs, 
         if (rc != RSDSFM_OK && first_err == RSDSFM_OK) first_err = rc;
     }
     drain_all();
+    if (trace) {
+        const auto tc2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rsdsfm trace] sequence of %d pairs, %d lanes (%d active): setup %.2f ms, pairs %.2f ms\n", n_ok, n_lanes, active,
+                std::chrono::duration<double, std::milli>(tc1 - tc0).count(), std::chrono::duration<double, std::milli>(tc2 - tc1).count());
+    }
     restore();
     for (int l = 1; l < n_lanes; ++l) {
         rsdsfm_ctx *L = lane[l];
