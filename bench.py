@@ -36,8 +36,8 @@ WORKLOAD = ("synthetic analytic RS flow 1920x1080 (galaxy_stabil K, gamma 0.95),
             "RANSAC winner (H=16 hypotheses, tol 0.05), then per-scanline GS rectification + crack fill")
 ALGO_BYTES_PASS_A = 24.0   # read flow 16 B + inverse depth 8 B per residual block
 ALGO_BYTES_PASS_B = 32.0   # read flow 16 B + inverse depth 8 B, write candidate inverse depth 8 B
-FP64_INSTR_PER_BLOCK = 188.0   # SASS count of the fused sweep's executed path (tools/sass_loops.py): DFMA + DMUL + DADD
-OTHER_INSTR_PER_BLOCK = 130.0  # ... and every other instruction of that path (integer, shuffles, loads, control)
+FP64_INSTR_PER_BLOCK = 184.0   # SASS count of the fused sweep's loop (tools/sass_loops.py, profiles/r02_sass_k_lm_solve7.txt): DFMA + DMUL + DADD + MUFU
+OTHER_INSTR_PER_BLOCK = 135.0  # ... and every other instruction of the executed path (integer, shuffles, loads, control; the refill-duty and exact-path blocks excluded)
 CONST_ACC = True           # headline workload: constant-acceleration trajectory (k estimated); --const-vel: k = 0 fixed
 
 

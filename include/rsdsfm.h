@@ -281,18 +281,18 @@ typedef struct rsdsfm_pair_io {
 } rsdsfm_pair_io;
 
 /* The reference handles one frame pair per run (evaluateSingleRun, main.cc:302-560; the sweep in
- * main.cc:148-300 and errorMeasure.cpp:99-226 repeat it); pairs are independent, so this entry point runs
- * them as a three-stage pipeline on one GPU: while pair i computes, pair i+1's inputs upload on a
- * copy stream and pair i-1's outputs download on another (mem = RSDSFM_HOST; use pinned host
- * memory for the copies to overlap).  With RSDSFM_DEVICE buffers only the result collection is
- * deferred, so that the GPU never waits for the host between pairs, and with two or more pairs the
- * compute itself runs in two lanes (even / odd pairs), each LM solve on half of the SMs, so that one
- * solve's grid barriers and serial controller steps are covered by the other solve's pixel sweeps
- * (the host-buffer path is PCIe-bound and keeps one lane).
- * Results are reproducible to the bit from call to call and agree with n_pairs calls of
- * rsdsfm_refine_rectify to rounding (same arithmetic; the partial sums are reduced over half as many
- * rows; a one-pair sequence is the single call).  Returns the first failing pair's code (all pairs
- * are attempted; see rsdsfm_pair_io.status). */
+ * main.cc:148-300 and errorMeasure.cpp:99-226 repeat it); pairs are independent, so this entry point keeps
+ * several of them in flight on one GPU.  Every pair runs on a compute lane -- an internal context with its own
+ * stream and buffers whose LM solve takes a quarter of the SMs (half of them for sequences of fewer than 12
+ * pairs) -- and goes to whichever lane is free first: one solve's grid exchanges and serial controller steps
+ * are covered by the other solves' pixel sweeps, and with mem = RSDSFM_HOST the uploads (one copy stream, pair
+ * order) and downloads (a copy stream per lane) of some pairs overlap the compute of others (use pinned host
+ * memory for the copies to overlap).  Up to 8 lanes; their buffers are sized for rows * cols on first use and
+ * kept.  Environment: RSDSFM_ACTIVE_LANES (solves sharing the SMs; 1 = full-GPU solves), RSDSFM_LANES,
+ * RSDSFM_TRACE=1 (per-solve device time stamps and per-call host times on stderr).
+ * Results do not depend on the lanes: the LM kernel sums over fixed strips of residual blocks whatever its
+ * grid (csrc/lm_kernel.cuh, kStrips), so every pair comes out bit-identical to a single rsdsfm_refine_rectify
+ * call.  Returns the first failing pair's code (all pairs are attempted; see rsdsfm_pair_io.status). */
 RSDSFM_API int rsdsfm_refine_rectify_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm_pair_io *pairs,
                           int const_acceleration, int gs_mode, int rows, int cols, const double *K4,
                           double gamma, int layout);
@@ -321,8 +321,8 @@ typedef struct rsdsfm_compact_pair_io {
     rsdsfm_lm_summary summary;     /* out */
 } rsdsfm_compact_pair_io;
 
-/* Pipelined like rsdsfm_refine_rectify_sequence (host buffers: upload i+1 | compute i | download i-1; device
- * buffers: two compute lanes).  flow_threshold: the |flow|^2 cut of the flattening (1e-10 in the reference). */
+/* Pipelined over compute lanes like rsdsfm_refine_rectify_sequence (bit-identical to single calls).
+ * flow_threshold: the |flow|^2 cut of the flattening (1e-10 in the reference). */
 RSDSFM_API int rsdsfm_refine_rectify_compact_sequence(rsdsfm_ctx *ctx, int mem, int n_pairs, rsdsfm_compact_pair_io *pairs,
                           int flow_f32, double flow_threshold, int const_acceleration, int gs_mode, int rows, int cols,
                           const double *K4, double gamma, int layout);

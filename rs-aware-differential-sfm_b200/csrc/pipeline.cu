@@ -1,7 +1,7 @@
 // pipeline.cu -- the fused drivers behind include/rsdsfm.h:
 //   rsdsfm_refine_rectify            main.cc:457-523 for one frame pair, one host synchronisation
-//   rsdsfm_refine_rectify_sequence   the same over a sequence, three-stage software pipeline
-//                                    (upload i+1 | compute i | download i-1) on three streams
+//   rsdsfm_refine_rectify_sequence   the same over a sequence: several pairs in flight on compute lanes
+//                                    (uploads | solves on a quarter of the SMs each | downloads overlap)
 //   rsdsfm_pipeline_pair / _sequence main.cc:398-523 (flatten .. crack fill) without leaving the device
 // Everything here composes the stage functions of stages.h; there is no arithmetic in this file
 // apart from the reference's sample draw (minimal.cc:226-244) on the host.

@@ -147,7 +147,7 @@ static int lm_solve_async(rsdsfm_ctx *ctx, const RefineData &D, double *d0, doub
 {
     RS_TRY(ensure(ctx, ctx->lm_shared, sizeof(LmShared)));
     LmShared *sh = (LmShared *)ctx->lm_shared.p;
-    const int grid = lm_grid_size(ctx);                 // one persistent CTA per SM (half of them in a two-lane sequence)
+    const int grid = lm_grid_size(ctx);                 // one persistent CTA per SM (a fraction of them on a lane of a sequence)
     const int nv = (nf == 0) ? Row<0>::NV : (nf == 6 ? Row<6>::NV : Row<7>::NV);
     RS_TRY(ensure(ctx, ctx->partials, sizeof(double) * 2 * (size_t)kStrips * nv));   // rows (one per strip) of even / odd phases
     if (ctx->exc_cap < min_exc_cap()) ctx->exc_cap = min_exc_cap();

@@ -400,7 +400,7 @@ def test_refine_rectify_sequence_bad_pair_is_reported(ctx, oracle, synth):
     # the context stays usable and the valid pairs still run
     ok = ctx.refine_rectify_sequence([pairs[0], pairs[2]], False, False, cases[0]["K4"], cases[0]["gamma"])
     assert [r["status"] for r in ok] == [0, 0]
-    # the same with device buffers (two compute lanes)
+    # the same with device buffers
     import torch
     dpairs = [{k: (torch.from_numpy(np.ascontiguousarray(v)).cuda() if isinstance(v, np.ndarray) and v.size > 7 else v) for k, v in p.items()}
               for p in pairs]
