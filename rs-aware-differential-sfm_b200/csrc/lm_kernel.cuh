@@ -67,7 +67,7 @@ struct LmShared {
     // device timing (globaltimer ns): [0] INIT total, [1] phases, [2] FUSED total, [3] phases,
     // [4..6] INIT pixel loop / CTA reduce / controller, [7..9] same for FUSED, [10], [11] controller logic only
     unsigned long long t_phase[12];
-    unsigned long long t_abs[2];   // globaltimer at the kernel's first / last instruction of CTA 0 (RSDSFM_TRACE: overlap of solves)
+    unsigned long long t_abs[4];   // globaltimer of CTA 0: kernel's first / last instruction, first phase's start, last phase's end (RSDSFM_TRACE)
     // ---- grid synchronisation
     unsigned int arrive, generation;
     unsigned int n_exc[4], exc_overflow, pad1;   // exception lists: current / speculative / being cleared
@@ -1344,6 +1344,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
     if (tid == 0 && P.next != LM_DONE) queue_phase_head(D, P.which_x ? d1 : d0, stages, full, empty, cons, consumed, pre, s_vs);
     __syncthreads();
 
+    if (blockIdx.x == 0 && tid == 0) sh->t_abs[2] = globaltimer();
     for (;;) {
         if (P.next == LM_DONE || P.error) break;
         const bool run_init = (P.next == LM_RUN_A);
@@ -1537,6 +1538,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_lm_solve(const SolveArgs A_)
         }
     }
 
+    if (blockIdx.x == 0 && tid == 0) sh->t_abs[3] = globaltimer();
     // ---- the result: CTA 0 publishes the controller state and the final motion
     if (blockIdx.x == 0) {
         __syncthreads();

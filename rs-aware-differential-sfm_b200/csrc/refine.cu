@@ -206,7 +206,9 @@ int lm_collect_finish(rsdsfm_ctx *ctx, int nf, int m, Motion *mot, rsdsfm_lm_sum
     *overflow = h->exc_overflow != 0;
     if (*overflow) { if (ctx->exc_cap < m + 1024) ctx->exc_cap = m + 1024; return RSDSFM_OK; }
     if (getenv("RSDSFM_TRACE"))
-        fprintf(stderr, "[rsdsfm trace] ctx %p solve m=%d it=%d t0=%llu t1=%llu (%.1f us)\n", (void *)ctx, m, h->ctl.iteration, h->t_abs[0], h->t_abs[1], (double)(h->t_abs[1] - h->t_abs[0]) * 1e-3);
+        fprintf(stderr, "[rsdsfm trace] ctx %p solve m=%d it=%d t0=%llu t1=%llu (%.1f us; before the first phase %.1f, after the last %.1f)\n", (void *)ctx, m,
+                h->ctl.iteration, h->t_abs[0], h->t_abs[1], (double)(h->t_abs[1] - h->t_abs[0]) * 1e-3, (double)(h->t_abs[2] - h->t_abs[0]) * 1e-3,
+                (double)(h->t_abs[1] - h->t_abs[3]) * 1e-3);
     float kms = 0.f;
     if (ctx->profile) cudaEventElapsedTime(&kms, ctx->pe0[ctx->io_slot], ctx->pe1[ctx->io_slot]);
     if (summary) {
