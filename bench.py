@@ -384,7 +384,7 @@ def run_ours(args):
                     "api": "rsdsfm_refine_rectify_compact_sequence, pinned host buffers: the float32 flow field, the frame and "
                            "RANSAC's outputs (consensus mask, winner inverse depths) go up, coordinates / alpha factors / pairing "
                            "are rebuilt on the device; depths and the rectified frame come back (the depth raster stays on the "
-                           "device); up to 8 pairs in flight on compute lanes of their own (four LM solves share the SMs): uploads, solves and "
+                           "device); up to 16 pairs in flight on compute lanes of their own (four LM solves share the SMs): uploads, solves and "
                            "downloads of different pairs overlap"},
             "api": "rsdsfm_refine_rectify_sequence over the rank's shard, device buffers (compute lanes: four LM solves share the SMs, a pair goes to the lane that is free first; results are bit-identical to single calls), "
                    "+ sequence.gather_records",

@@ -287,8 +287,8 @@ typedef struct rsdsfm_pair_io {
  * pairs) -- and goes to whichever lane is free first: one solve's grid exchanges and serial controller steps
  * are covered by the other solves' pixel sweeps, and with mem = RSDSFM_HOST the uploads (one copy stream, pair
  * order) and downloads (a copy stream per lane) of some pairs overlap the compute of others (use pinned host
- * memory for the copies to overlap).  Up to 8 lanes; their buffers are sized for rows * cols on first use and
- * kept.  Environment: RSDSFM_ACTIVE_LANES (solves sharing the SMs; 1 = full-GPU solves), RSDSFM_LANES,
+ * memory for the copies to overlap).  Up to 16 lanes (10 with device buffers); their buffers are sized for
+ * rows * cols on first use and kept.  Environment: RSDSFM_ACTIVE_LANES (solves sharing the SMs; 1 = full-GPU solves), RSDSFM_LANES,
  * RSDSFM_TRACE=1 (per-solve device time stamps and per-call host times on stderr).
  * Results do not depend on the lanes: the LM kernel sums over fixed strips of residual blocks whatever its
  * grid (csrc/lm_kernel.cuh, kStrips), so every pair comes out bit-identical to a single rsdsfm_refine_rectify

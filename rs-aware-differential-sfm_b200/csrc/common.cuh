@@ -29,7 +29,7 @@ struct DevBuf {
 
 }  // namespace rsdsfm
 
-constexpr int kMaxLanes = 8;
+constexpr int kMaxLanes = 16;
 
 struct rsdsfm_ctx {
     int device = 0;

@@ -226,13 +226,16 @@ static int sequence_core(rsdsfm_ctx *ctx, int mem, std::vector<SeqPair> &pairs, 
     //   RSDSFM_ACTIVE_LANES  solves that share the SMs   (default 4, 2 for sequences of fewer than 12 pairs -- the last
     //                        solves of a sequence run with idle SMs beside them, the longer the more lanes there are;
     //                        1 = full-GPU solves, I/O still overlapped)
-    //   RSDSFM_LANES         lanes                       (default: active + 2 with device buffers, 2 x active with
-    //                        host buffers, where a lane spends a third of its time in its copies)
+    //   RSDSFM_LANES         lanes                       (default 10 with device buffers, 16 with host buffers, where a
+    //                        lane spends a third of its time in its copies -- measured 893 / 1000 / 1011 pairs/s end
+    //                        to end with 8 / 12 / 16 lanes; fewer when 16 lanes' buffers would exceed ~8 GB)
     auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return (e && atoi(e) > 0) ? atoi(e) : dflt; };
     int active = env_int("RSDSFM_ACTIVE_LANES", n_ok >= 12 ? 4 : 2);
     if (getenv("RSDSFM_SINGLE_LANE")) active = 1;
     if (active > ctx->num_sms) active = ctx->num_sms;
-    int n_lanes = env_int("RSDSFM_LANES", host ? (active > 1 ? 2 * active : 2) : (active > 1 ? active + 2 : 1));
+    int dflt_lanes = host ? 16 : 10;
+    while (dflt_lanes > 4 && (double)dflt_lanes * (double)tot * (host ? 140.0 : 100.0) > 8e9) dflt_lanes -= 2;   // bytes per pixel a lane holds
+    int n_lanes = env_int("RSDSFM_LANES", dflt_lanes);
     if (n_lanes > kMaxLanes) n_lanes = kMaxLanes;
     if (n_lanes > n_ok) n_lanes = n_ok;
     if (ctx->n_peers > 1) n_lanes = 1;                      // row split: the peers step through the same solves in lockstep
