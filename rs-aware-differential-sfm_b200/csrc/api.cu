@@ -94,7 +94,7 @@ void rsdsfm_destroy(rsdsfm_ctx *ctx)
     if (ctx->pinned_io) cudaFreeHost(ctx->pinned_io);
     DevBuf *all[] = {&ctx->partials, &ctx->sums, &ctx->pix, &ctx->dA, &ctx->dB, &ctx->rdepth, &ctx->misc, &ctx->winner,
                      &ctx->poses, &ctx->hyp, &ctx->rpart, &ctx->scan,
-                     &ctx->lm_shared, &ctx->exc, &ctx->splat_tab};
+                     &ctx->lm_shared, &ctx->exc, &ctx->splat_tab, &ctx->flow_t};
     for (DevBuf *b : all) if (b->p) cudaFree(b->p);
     for (auto &b : ctx->stage) if (b.p) cudaFree(b.p);
     for (auto &b : ctx->pipe) if (b.p) cudaFree(b.p);

@@ -41,7 +41,7 @@ struct rsdsfm_ctx {
     // scratch
     std::vector<rsdsfm::DevBuf *> bufs;
     rsdsfm::DevBuf partials, sums, pix, dA, dB, rdepth, misc, stage[16], winner, poses;
-    rsdsfm::DevBuf hyp, rpart, scan, lm_shared, exc, splat_tab;
+    rsdsfm::DevBuf hyp, rpart, scan, lm_shared, exc, splat_tab, flow_t;
     rsdsfm::DevBuf pipe[16];  // intermediates of the fused a2-a15 driver (pipeline.cu)
     int exc_cap = 0;          // capacity (entries) of the clamped-pixel exception list
     // Row split of one solve over several GPUs (refine.cu / lm_kernel.cuh): this GPU's mailbox (its own allocation, so

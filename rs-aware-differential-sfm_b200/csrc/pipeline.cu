@@ -270,6 +270,7 @@ static int sequence_core(rsdsfm_ctx *ctx, int mem, std::vector<SeqPair> &pairs, 
         if (rc0 == RSDSFM_OK && C.compact) {
             rc0 = ensure(L, L->pipe[14], sizeof(double) * (size_t)max_m);
             if (rc0 == RSDSFM_OK) rc0 = ensure(L, L->pipe[15], sizeof(double) * 2 * (size_t)max_m);
+            if (rc0 == RSDSFM_OK) rc0 = ensure(L, L->flow_t, (C.flow_f32 ? sizeof(float) : sizeof(double)) * 2 * tot);
         }
         if (rc0 != RSDSFM_OK && L != ctx) ctx->err = L->err;
     }

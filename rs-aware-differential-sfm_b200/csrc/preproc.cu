@@ -246,6 +246,7 @@ int gather_inliers_device(rsdsfm_ctx *ctx, const double *q, const double *alpha,
 // solver's tile-blocked layout (lm_layout.h), with the operation order of k_flat_scatter / k_alpha /
 // k_mask_scatter (bit-identical values).  Residual block i takes the coordinates and alpha factors of the
 // i-th inlier and the flow of flattened POINT i (the reference's pairing, nonlinearRefinement.cc:209-216, Q1).
+// flow_img: the caller's row-major field, or (cols < 0) its transposed copy in flattening order (k_flow_transpose)
 template <typename F>
 __device__ __forceinline__ bool flow_kept_t(const F *__restrict__ flow_img, int rows, int cols, long long p, long long total,
                                             double thr, double &dx, double &dy, int &i, int &j)
@@ -253,17 +254,56 @@ __device__ __forceinline__ bool flow_kept_t(const F *__restrict__ flow_img, int 
     if (p >= total) return false;
     i = (int)(p / rows);
     j = (int)(p - (long long)i * rows);
-    const size_t at = ((size_t)j * cols + i) * 2;
+    const size_t at = (cols > 0 ? (size_t)j * cols + i : (size_t)p) * 2;
     dx = (double)flow_img[at]; dy = (double)flow_img[at + 1];      // float32 flow is widened exactly (camera.cc:262-274)
     const double norm = dx * dx + dy * dy;
     return norm > thr;
+}
+
+// The flattening walks the image column by column (main.cc:408), the flow field is stored row by row: a thread per
+// flattened point would use 8 (float32) or 16 bytes of every 32-byte sector it touches, in each of the three
+// compaction passes.  One tiled transpose (coalesced both ways) puts the field into flattening order first.
+template <typename F>
+__global__ void __launch_bounds__(256) k_flow_transpose(const F *__restrict__ flow_img, int rows, int cols, F *__restrict__ out)
+{
+    struct P2 { F x, y; };
+    __shared__ P2 tile[32][33];
+    const P2 *in = reinterpret_cast<const P2 *>(flow_img);
+    P2 *o = reinterpret_cast<P2 *>(out);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8 threads
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    for (int r = ty; r < 32; r += 8) {
+        const int j = j0 + r, i = i0 + tx;
+        if (j < rows && i < cols) tile[r][tx] = in[(size_t)j * cols + i];
+    }
+    __syncthreads();
+    for (int c = ty; c < 32; c += 8) {
+        const int i = i0 + c, j = j0 + tx;
+        if (j < rows && i < cols) o[(size_t)i * rows + j] = tile[tx][c];
+    }
+}
+
+// sum of counts[0 .. blockIdx.x)  (whole CTA; every thread receives it): the CTA's offset into the kept points / the
+// inliers.  A couple of thousand values out of L2 per CTA -- cheaper than a scan launch between the passes.
+__device__ __forceinline__ int preceding_sum(const int *__restrict__ counts)
+{
+    __shared__ int part[kWarps];
+    int v = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += kThreads) v += counts[b];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int t = 0;
+    for (int w2 = 0; w2 < kWarps; ++w2) t += part[w2];
+    return t;
 }
 
 template <typename F>
 __global__ void __launch_bounds__(kThreads) k_compact_count_kept(const F *__restrict__ flow_img, int rows, int cols, double thr,
                                                                  int *block_counts)
 {
-    const long long total = (long long)rows * cols;
+    const long long total = (long long)rows * (cols < 0 ? -cols : cols);      // cols < 0: flow_img is the transposed copy
     int cnt = 0;
     for (int s = 0; s < 4; ++s) {
         const long long p = (long long)blockIdx.x * kChunk + s * kThreads + threadIdx.x;
@@ -284,11 +324,11 @@ __global__ void __launch_bounds__(kThreads) k_compact_count_kept(const F *__rest
 // second level: inliers among the kept pixels of each chunk (mask is indexed by flattened point)
 template <typename F>
 __global__ void __launch_bounds__(kThreads) k_compact_count_inliers(const F *__restrict__ flow_img, int rows, int cols, double thr,
-                                                                    const int *__restrict__ kept_offsets,
+                                                                    const int *__restrict__ kept_counts,
                                                                     const uint8_t *__restrict__ mask, int n, int *block_counts)
 {
-    const long long total = (long long)rows * cols;
-    int base = kept_offsets[blockIdx.x];
+    const long long total = (long long)rows * (cols < 0 ? -cols : cols);      // cols < 0: flow_img is the transposed copy
+    int base = preceding_sum(kept_counts);
     int cnt = 0;
     for (int s = 0; s < 4; ++s) {
         const long long p = (long long)blockIdx.x * kChunk + s * kThreads + threadIdx.x;
@@ -313,16 +353,14 @@ __global__ void __launch_bounds__(kThreads) k_compact_count_inliers(const F *__r
 template <typename F>
 __global__ void __launch_bounds__(kThreads) k_compact_scatter(const F *__restrict__ flow_img, int rows, int cols, double thr,
                                                               double fx, double fy, double cx, double cy, double gamma,
-                                                              const int *__restrict__ kept_offsets,
-                                                              const int *__restrict__ inl_offsets, int nb,
+                                                              const int *__restrict__ kept_counts,
+                                                              const int *__restrict__ inl_counts,
                                                               const uint8_t *__restrict__ mask,
                                                               const double *__restrict__ inv_depth, int n, int m, double2 *blk,
                                                               double *d0, double *z_in, double2 *xy, int *input_flag)
 {
-    const long long total = (long long)rows * cols;
-    // the caller's n / m must be what the flow field and the mask really hold
-    if (blockIdx.x == 0 && threadIdx.x == 0 && (kept_offsets[nb] != n || inl_offsets[nb] != m)) atomicOr(input_flag, 2);
-    int base = kept_offsets[blockIdx.x], ibase = inl_offsets[blockIdx.x];
+    const long long total = (long long)rows * (cols < 0 ? -cols : cols);      // cols < 0: flow_img is the transposed copy
+    int base = preceding_sum(kept_counts), ibase = preceding_sum(inl_counts);
     const double h = (double)rows;
     int bad = 0;
     for (int s = 0; s < 4; ++s) {
@@ -352,6 +390,8 @@ __global__ void __launch_bounds__(kThreads) k_compact_scatter(const F *__restric
         }
         base += tot; ibase += itot;
     }
+    // the caller's n / m must be what the flow field and the mask really hold (the last CTA ends on the totals)
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0 && (base != n || ibase != m)) atomicOr(input_flag, 2);
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(input_flag, 1);
 }
 
@@ -362,15 +402,16 @@ static int compact_build_t(rsdsfm_ctx *ctx, const F *flow_img, int rows, int col
 {
     const long long total = (long long)rows * cols;
     const int nb = (int)((total + kChunk - 1) / kChunk);
-    RS_TRY(ensure(ctx, ctx->scan, sizeof(int) * (4 * (size_t)nb + 4)));
-    int *counts = (int *)ctx->scan.p, *offsets = counts + nb, *icounts = offsets + nb + 1, *ioffsets = icounts + nb;
-    k_compact_count_kept<F><<<nb, kThreads, 0, ctx->stream>>>(flow_img, rows, cols, thr, counts);
-    k_scan_counts<<<1, 1024, 0, ctx->stream>>>(counts, nb, offsets);
-    k_compact_count_inliers<F><<<nb, kThreads, 0, ctx->stream>>>(flow_img, rows, cols, thr, offsets, mask, n, icounts);
-    k_scan_counts<<<1, 1024, 0, ctx->stream>>>(icounts, nb, ioffsets);
-    k_compact_scatter<F><<<nb, kThreads, 0, ctx->stream>>>(flow_img, rows, cols, thr, K4[0], K4[1], K4[2], K4[3], gamma, offsets,
-                                                          ioffsets, nb, mask, inv_depth, n, m, blk, d0, z_in, xy, input_flag);
-    ctx->launches += 5;
+    RS_TRY(ensure(ctx, ctx->scan, sizeof(int) * (2 * (size_t)nb + 4)));
+    int *counts = (int *)ctx->scan.p, *icounts = counts + nb;
+    RS_TRY(ensure(ctx, ctx->flow_t, sizeof(F) * 2 * (size_t)total));
+    F *ft = (F *)ctx->flow_t.p;
+    k_flow_transpose<F><<<dim3((cols + 31) / 32, (rows + 31) / 32), 256, 0, ctx->stream>>>(flow_img, rows, cols, ft);
+    k_compact_count_kept<F><<<nb, kThreads, 0, ctx->stream>>>(ft, rows, -cols, thr, counts);
+    k_compact_count_inliers<F><<<nb, kThreads, 0, ctx->stream>>>(ft, rows, -cols, thr, counts, mask, n, icounts);
+    k_compact_scatter<F><<<nb, kThreads, 0, ctx->stream>>>(ft, rows, -cols, thr, K4[0], K4[1], K4[2], K4[3], gamma, counts, icounts,
+                                                          mask, inv_depth, n, m, blk, d0, z_in, xy, input_flag);
+    ctx->launches += 4;
     RS_CUDA(ctx, cudaGetLastError());
     return RSDSFM_OK;
 }
