@@ -1100,7 +1100,8 @@ constexpr int kRefillLag = 5;
 // in tile order into a row of its own, and the rows are combined in strip order: the sums -- and with them the whole
 // solve -- do not depend on the grid.  A full-GPU solve has one strip per CTA; a solve that shares the GPU with others
 // (rsdsfm_refine_rectify_sequence: grid = a fraction of the SMs) walks through several strips per phase, CTA b taking
-// strips b, b + grid, ...  Bit-identical results either way.
+// strips b, b + grid, ...  Bit-identical results either way.  (The strip count is the B200's SM count and part of the
+// result's definition: grids that do not divide it -- a part with fewer SMs -- still work, with uneven shares.)
 constexpr int kStrips = kNumSMsB200;
 
 template <int NF, bool INIT>
