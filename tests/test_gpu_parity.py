@@ -366,6 +366,34 @@ def test_refine_rectify_sequence_equals_single_calls(ctx, oracle, synth, mem, co
     assert np.array_equal(host(one["rectified"]), host(single[0]["rectified"]))
 
 
+@pytest.mark.parametrize("mem", ["host", "device"])
+def test_long_sequence_on_four_lanes_equals_single_calls(ctx, oracle, synth, mem):
+    """14 pairs: the sequence driver runs four LM solves side by side (37 CTAs each, here 2-3 strips per CTA) on
+    10 / 14 lanes and hands every pair to the lane that is free first -- each pair bit-identical to its single call."""
+    import torch
+    cases = _seq_pairs(oracle, synth, 7, True)
+    dev = torch.device("cuda", 0)
+    to = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)) if mem == "device" else (lambda a: np.ascontiguousarray(a))
+    host = (lambda a: a.cpu().numpy()) if mem == "device" else (lambda a: a)
+    pairs, single = [], []
+    for c in cases + cases:
+        R = c["ransac"]
+        d = dict(flow=to(c["flow"][:2 * c["m"]]), inliers3=to(c["inliers3"]), alpha=to(c["alpha_in"]), alpha_k=to(c["alpha_k_in"]),
+                 image=to(c["P"]["image"]), m=c["m"], v=R["v"], w=R["w"], k=R["k"])
+        pairs.append(d)
+    for d, c in zip(pairs[:7], cases):
+        single.append(ctx.refine_rectify(d["flow"], d["inliers3"], d["alpha"], d["alpha_k"], d["m"], d["v"], d["w"], d["k"], True,
+                                         False, d["image"], c["K4"], c["gamma"]))
+    seq = ctx.refine_rectify_sequence(pairs, True, False, cases[0]["K4"], cases[0]["gamma"])
+    assert len(seq) == 14
+    for i, s_ in enumerate(seq):
+        r = single[i % 7]
+        assert s_["status"] == 0 and s_["summary"]["iterations"] == r["summary"]["iterations"]
+        assert np.array_equal(s_["v"], r["v"]) and np.array_equal(s_["w"], r["w"]) and s_["k"] == r["k"]
+        for key in ("z", "depth_map", "rectified"):
+            assert np.array_equal(host(s_[key]), host(r[key])), (i, key)
+
+
 def test_lm_solve_does_not_depend_on_the_grid(capi):
     """The persistent LM kernel on 148, 74, 37 and 5 CTAs (RSDSFM_LM_GRID, read once per process: one process each):
     the refined motion, the cost and the depths come out identical to the bit."""
