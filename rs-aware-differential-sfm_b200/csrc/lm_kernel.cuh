@@ -578,7 +578,7 @@ __device__ __forceinline__ bool pixel_fast(const Loaded &L, bool inb, int index,
         acc[1] = fma(dc, dc, acc[1]);
         if (!INIT) { acc[2] = fma(mj0, mt0, fma(mj1, mt1, acc[2])); acc[3] = fma(stp, stp, acc[3]); }
         S.gmax = umax64(S.gmax, dbits(fma(e0, r0, e1 * r1)) & 0x7fffffffffffffffull);     // |e^T r|
-        S.eemax = umax64(S.eemax, dbits(ee));
+        if (INIT) S.eemax = umax64(S.eemax, dbits(ee));                // (only the first evaluation's max e^Te is used: lm_controller.h on_eval, phase 0)
     }
     if (NF > 0) {
         const double mu = mask_double(sweep_rsqrt(ee), fast);         // 1/|e|
@@ -1131,6 +1131,7 @@ __device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P,
     long long dbg_wait = 0; const long long dbg_t0 = clock64();
 #endif
     bool ready = false;                    // the early test of this step's full barrier succeeded
+    int kduty = k0 + ((warp - k0) & (kWarps - 1));   // this warp's next refill duty: the steps k with k % 8 == warp
 #pragma unroll 1
     for (int k = k0; k < k1; ++k, idx += kStrips * kTile) {
         const bool inb = idx < D.m;
@@ -1200,8 +1201,10 @@ __device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P,
 #ifdef LM_DBG_NOLOAD
         if (false) {
 #else
-        if (((k & (kWarps - 1)) == warp) & (kd >= 0) & (kd + kStages < n_my)) {
+        if (k == kduty) {
+            kduty += kWarps;
 #endif
+          if ((kd >= 0) & (kd + kStages < n_my)) {
             if (lane == 0) {
                 int sd = s_now - kRefillLag;                       // ring position of tile kd, from this step's
                 unsigned pd = par_now;
@@ -1218,6 +1221,7 @@ __device__ __forceinline__ void sweep(const SolveArgs &A_, const PhaseParams &P,
                 bulk_g2s_s(st, D.blk + (size_t)tile * (3 * kTile), (unsigned)(3 * kTile * sizeof(double2)), fb);
                 bulk_g2s_s(st + (uint32_t)(3 * kTile * 16), dx + (size_t)tile * kTile, (unsigned)(kTile * sizeof(double)), fb);
             }
+          }
         }
     }
 #ifdef LM_DBG_WAITCLK
