@@ -37,8 +37,8 @@ WORKLOAD = ("synthetic analytic RS flow 1920x1080 (galaxy_stabil K, gamma 0.95),
 ALGO_BYTES_PASS_A = 24.0   # read flow 16 B + inverse depth 8 B per residual block
 ALGO_BYTES_PASS_B = 32.0   # read flow 16 B + inverse depth 8 B, write candidate inverse depth 8 B
 MAX_RESIDENT_PAIRS = 128
-FP64_INSTR_PER_BLOCK = 184.0   # SASS count of the fused sweep's loop (tools/sass_loops.py, profiles/r02_sass_k_lm_solve7.txt): DFMA + DMUL + DADD + MUFU
-OTHER_INSTR_PER_BLOCK = 135.0  # ... and every other instruction of the executed path (integer, shuffles, loads, control; the refill-duty and exact-path blocks excluded)
+FP64_INSTR_PER_BLOCK = 180.0   # instructions EXECUTED per warp and step of the fused sweep (ncu source page of the committed capture): DFMA 127 + DMUL 41 + DADD 10 + MUFU 2
+OTHER_INSTR_PER_BLOCK = 120.0  # ... and everything else executed per step (ISETP 24, IMAD 21, SHFL 16, FSEL/SEL 15, branches and their BSSY/BSYNC 16, LDS 4, ...)
 CONST_ACC = True           # headline workload: constant-acceleration trajectory (k estimated); --const-vel: k = 0 fixed
 
 
