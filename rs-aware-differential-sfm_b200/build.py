@@ -25,7 +25,7 @@ UNITS = [
     ("rectify.cu", ["--fmad=false"]),
     ("preproc.cu", ["--fmad=false"]),
 ]
-HEADERS = ["common.cuh", "stages.h", "lm_controller.h", "lm_layout.h", "lm_kernel.cuh", "rs_math.cuh", "solve9.h", os.path.join("..", "..", "include", "rsdsfm.h")]
+HEADERS = ["common.cuh", "stages.h", "lm_controller.h", "lm_layout.h", "lm_kernel.cuh", "solve9.h", os.path.join("..", "..", "include", "rsdsfm.h")]
 
 
 def _nvcc():

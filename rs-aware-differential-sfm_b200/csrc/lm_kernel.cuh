@@ -33,7 +33,6 @@
 #include "common.cuh"
 #include "lm_controller.h"
 #include "lm_layout.h"
-#include "rs_math.cuh"
 
 namespace rsdsfm {
 
@@ -325,7 +324,7 @@ struct PixOut {
 template <int NF>
 __device__ __forceinline__ void ft_rows(double beta, double dbeta, double d, double x, double y, double p0, double p1,
                                         double (&F0)[NF > 0 ? NF : 1], double (&F1)[NF > 0 ? NF : 1])
-{   // F = -beta [d A | B | (dbeta/beta) p]  (rs_math.cuh)
+{   // F = -beta [d A | B | (dbeta/beta) p]  (lm_layout.h)
     if (NF >= 6) {
         F0[0] = -beta * d;        F1[0] = 0.0;
         F0[1] = 0.0;              F1[1] = -beta * d;

@@ -6,7 +6,8 @@
 
 #include "common.cuh"
 #include "lm_controller.h"
-#include "rs_math.cuh"
+#include "lm_controller.h"
+#include "lm_layout.h"
 
 namespace rsdsfm {
 
