@@ -374,6 +374,10 @@ def run_ours(args):
                                    "per-pair records inside the timed region" + (
                                        "" if K <= MAX_RESIDENT_PAIRS else "; %d distinct pairs resident per rank, walked through cyclically" % MAX_RESIDENT_PAIRS),
                        "records_sha256_first_shard": digest,
+                       "lanes": "sequence calls keep several pairs in flight: %s LM solves share the SMs (37 CTAs each), %s lanes with "
+                                "device buffers, %s with host buffers (csrc/pipeline.cu; RSDSFM_ACTIVE_LANES / RSDSFM_LANES)" % (
+                                    os.environ.get("RSDSFM_ACTIVE_LANES", "4" if K >= 12 else "2"), os.environ.get("RSDSFM_LANES", "10"),
+                                    os.environ.get("RSDSFM_LANES", "16")),
                        "l2": "inputs larger than L2: every step is a different pair (~%.0f MB of device inputs each)" % (
                            sum(shard[0][k].numel() * shard[0][k].element_size() for k in ("flow", "inliers3", "alpha", "alpha_k", "image")) / 1e6)},
             "ms_per_lm_iteration": lm_ms,
