@@ -135,3 +135,21 @@ def test_host_shim_pieces_that_need_no_gpu(capi, tmp_path):
     r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ok" in r.stdout
+
+
+def test_bench_module_host_side():
+    """bench.py without a GPU: it imports, the synthetic sequence is deterministic and starts at the bench pair,
+    the roofline denominators and the measured FP64 issue costs load from the committed files."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    p0, p1 = bench.pair_params(0), bench.pair_params(1)
+    assert p0["seed"] == 1000 and p1["seed"] == 1001 and p0 == bench.pair_params(0) and p0["v"] != p1["v"]
+    peak, src = bench.load_peaks()
+    assert 3000.0 < peak < 9000.0 and isinstance(src, str)          # HBM GB/s: measured file or the recipe's fallback
+    two, three = bench.fp64_pipe_cycles()
+    assert 1.9 <= two <= 2.5 and 2.8 <= three <= 3.3               # cycles per warp DFMA per sub-partition (profiles/r02_fp64_operands.txt)
+    assert bench.ALGO_BYTES_PASS_A + bench.ALGO_BYTES_PASS_B == 56.0 and bench.MAX_RESIDENT_PAIRS >= 100
